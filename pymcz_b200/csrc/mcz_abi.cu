@@ -1,0 +1,176 @@
+// extern "C" surface of libmcz_b200.so (declared in include/mcz_b200.h).
+#include <cuda_runtime.h>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include "../../include/mcz_b200.h"
+#include "mcz_common.cuh"
+#include "mcz_internal.h"
+
+namespace mcz {
+
+static thread_local std::string g_error;
+static std::atomic<long long> g_launches{0};
+
+int set_error(const char* msg) {
+  g_error = msg;
+  return 1;
+}
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return 0;
+  g_error = std::string(what) + ": " + cudaGetErrorString(e);
+  return 2;
+}
+void count_launch(int n) { g_launches += n; }
+
+static const char* KEY_NAMES[NKEYS] = {
+    "E(B-V)", "logR23", "D02", "Z94", "M91", "C01_N2S2", "C01_R23", "P05", "P01", "PP04_N2Ha",
+    "PP04_O3N2", "DP00", "P10_ONS", "P10_ON", "M08_R23", "M08_N2Ha", "M08_O3Hb", "M08_O2Hb",
+    "M08_O3O2", "M08_O3N2", "M13_O3N2", "M13_N2", "D13_N2S2_O3S2", "D13_N2S2_O3Hb",
+    "D13_N2S2_O3O2", "D13_N2O2_O3S2", "D13_N2O2_O3Hb", "D13_N2O2_O3O2", "D13_N2Ha_O3Hb",
+    "D13_N2Ha_O3O2", "KD02_N2O2", "KD02_N2S2", "KK04_N2Ha", "KK04_R23", "KD02comb", "PM14", "D16"};
+static const char* LINE_NAMES[NLINES] = {"[OII]3727", "Hb", "[OIII]4959", "[OIII]5007", "[OI]6300", "Ha",
+                                         "[NII]6584", "[SII]6717", "[SII]6731", "[SIII]9069", "[SIII]9532"};
+
+}  // namespace mcz
+
+using namespace mcz;
+
+struct mcz_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  // device buffers (grown on demand)
+  float *meas = nullptr, *err = nullptr, *pct = nullptr;
+  int *nvalid = nullptr, *trips = nullptr, *ret = nullptr;
+  signed char* status = nullptr;
+  void* scratch = nullptr;
+  size_t cap_g = 0, cap_scratch = 0;
+};
+
+extern "C" {
+
+const char* mcz_version(void) { return "pymcz_b200 0.1 (sm_100a)"; }
+const char* mcz_last_error(void) { return g_error.c_str(); }
+const char* mcz_key_name(int i) { return (i >= 0 && i < NKEYS) ? KEY_NAMES[i] : ""; }
+const char* mcz_line_name(int i) { return (i >= 0 && i < NLINES) ? LINE_NAMES[i] : ""; }
+long long mcz_launch_count(void) { return g_launches.load(); }
+
+int mcz_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+size_t mcz_replay_scratch_bytes(long long G, long long N, int precision) {
+  return replay_scratch_bytes(G, N, precision, nullptr);
+}
+
+int mcz_forward_replay(const double* flux_d, const double* noise_d, long long G, long long N,
+                       unsigned tokens, int dust, int precision, double* Z_d,
+                       unsigned long long* present_d, int* trips_d, int* ret_d, void* scratch_d,
+                       size_t scratch_bytes, void* stream) {
+  if (!flux_d || !Z_d || !present_d || !trips_d || !ret_d) return set_error("mcz_forward_replay: null pointer");
+  if (tokens & T_M08ALL) return set_error("mcz_forward_replay: M08all is not built yet");
+  if (precision != 0 && precision != 1) return set_error("mcz_forward_replay: precision must be 0 or 1");
+  if ((tokens & (T_D02 | T_M13)) && !noise_d) return set_error("mcz_forward_replay: D02/M13 need noise_d");
+  return launch_replay(flux_d, noise_d, G, N, tokens, dust, precision, Z_d, present_d, trips_d, ret_d,
+                       scratch_d, scratch_bytes, (cudaStream_t)stream);
+}
+
+int mcz_segmented_percentiles(const double* Z_d, const unsigned char* present_d, long long rows,
+                              long long N, double* pct_d, int* nvalid_d, signed char* status_d,
+                              void* stream) {
+  if (!Z_d || !pct_d || !nvalid_d || !status_d) return set_error("mcz_segmented_percentiles: null pointer");
+  return launch_percentiles_f64(Z_d, present_d, rows, N, pct_d, nvalid_d, status_d, (cudaStream_t)stream);
+}
+
+size_t mcz_production_scratch_bytes(long long G, long long n_draw, unsigned tokens) {
+  return production_scratch_bytes(G, n_draw, tokens);
+}
+
+int mcz_forward_production(const float* meas_d, const float* err_d, long long G, long long n_draw,
+                           unsigned tokens, int dust, unsigned long long seed,
+                           unsigned long long galaxy_offset, int sample_mode, int deterministic,
+                           float* pct_d, int* nvalid_d, signed char* status_d, int* trips_d,
+                           int* ret_d, float* Z_d, void* scratch_d, size_t scratch_bytes,
+                           void* stream) {
+  if (!meas_d || !err_d || !pct_d || !nvalid_d || !status_d || !trips_d || !scratch_d)
+    return set_error("mcz_forward_production: null pointer");
+  return launch_production(meas_d, err_d, G, n_draw, tokens, dust, seed, galaxy_offset, sample_mode,
+                           deterministic, pct_d, nvalid_d, status_d, trips_d, ret_d, Z_d, scratch_d,
+                           scratch_bytes, (cudaStream_t)stream);
+}
+
+mcz_ctx* mcz_ctx_create(int device) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) {
+    set_error("mcz_ctx_create: no such CUDA device (there is no CPU fallback)");
+    return nullptr;
+  }
+  mcz_ctx* c = new mcz_ctx();
+  c->device = device;
+  cudaSetDevice(device);
+  if (check_cuda(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "stream create")) {
+    delete c;
+    return nullptr;
+  }
+  return c;
+}
+
+void mcz_ctx_destroy(mcz_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaFree(c->meas); cudaFree(c->err); cudaFree(c->pct); cudaFree(c->nvalid); cudaFree(c->trips);
+  cudaFree(c->ret); cudaFree(c->status); cudaFree(c->scratch);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int mcz_ctx_run_host(mcz_ctx* c, const float* meas_h, const float* err_h, long long G,
+                     long long n_draw, unsigned tokens, int dust, unsigned long long seed,
+                     unsigned long long galaxy_offset, int sample_mode, int deterministic,
+                     float* pct_h, int* nvalid_h, signed char* status_h, int* trips_h, int* ret_h) {
+  if (!c) return set_error("mcz_ctx_run_host: null context");
+  if (G <= 0) return 0;
+  int rc = check_cuda(cudaSetDevice(c->device), "set device");
+  if (rc) return rc;
+  if ((size_t)G > c->cap_g) {
+    cudaFree(c->meas); cudaFree(c->err); cudaFree(c->pct); cudaFree(c->nvalid); cudaFree(c->trips);
+    cudaFree(c->ret); cudaFree(c->status);
+    c->cap_g = 0;
+    const size_t g = (size_t)G;
+    if ((rc = check_cuda(cudaMalloc(&c->meas, g * NLINES * 4), "malloc"))) return rc;
+    if ((rc = check_cuda(cudaMalloc(&c->err, g * NLINES * 4), "malloc"))) return rc;
+    if ((rc = check_cuda(cudaMalloc(&c->pct, g * NKEYS * 3 * 4), "malloc"))) return rc;
+    if ((rc = check_cuda(cudaMalloc(&c->nvalid, g * NKEYS * 4), "malloc"))) return rc;
+    if ((rc = check_cuda(cudaMalloc(&c->status, g * NKEYS), "malloc"))) return rc;
+    if ((rc = check_cuda(cudaMalloc(&c->trips, g * 2 * 4), "malloc"))) return rc;
+    if ((rc = check_cuda(cudaMalloc(&c->ret, g * 4), "malloc"))) return rc;
+    c->cap_g = g;
+  }
+  const size_t need = production_scratch_bytes(G, n_draw, tokens);
+  if (need > c->cap_scratch) {
+    cudaFree(c->scratch);
+    c->cap_scratch = 0;
+    if ((rc = check_cuda(cudaMalloc(&c->scratch, need), "malloc scratch"))) return rc;
+    c->cap_scratch = need;
+  }
+  const size_t g = (size_t)G;
+  cudaStream_t st = c->stream;
+  if ((rc = check_cuda(cudaMemcpyAsync(c->meas, meas_h, g * NLINES * 4, cudaMemcpyHostToDevice, st), "H2D meas"))) return rc;
+  if ((rc = check_cuda(cudaMemcpyAsync(c->err, err_h, g * NLINES * 4, cudaMemcpyHostToDevice, st), "H2D err"))) return rc;
+  rc = launch_production(c->meas, c->err, G, n_draw, tokens, dust, seed, galaxy_offset, sample_mode,
+                         deterministic, c->pct, c->nvalid, c->status, c->trips, c->ret, nullptr,
+                         c->scratch, c->cap_scratch, st);
+  if (rc) return rc;
+  if ((rc = check_cuda(cudaMemcpyAsync(pct_h, c->pct, g * NKEYS * 3 * 4, cudaMemcpyDeviceToHost, st), "D2H pct"))) return rc;
+  if ((rc = check_cuda(cudaMemcpyAsync(nvalid_h, c->nvalid, g * NKEYS * 4, cudaMemcpyDeviceToHost, st), "D2H nvalid"))) return rc;
+  if ((rc = check_cuda(cudaMemcpyAsync(status_h, c->status, g * NKEYS, cudaMemcpyDeviceToHost, st), "D2H status"))) return rc;
+  if (trips_h && (rc = check_cuda(cudaMemcpyAsync(trips_h, c->trips, g * 2 * 4, cudaMemcpyDeviceToHost, st), "D2H trips"))) return rc;
+  if (ret_h && (rc = check_cuda(cudaMemcpyAsync(ret_h, c->ret, g * 4, cudaMemcpyDeviceToHost, st), "D2H ret"))) return rc;
+  return check_cuda(cudaStreamSynchronize(st), "stream sync");
+}
+
+}  // extern "C"

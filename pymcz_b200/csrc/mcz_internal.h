@@ -1,0 +1,28 @@
+// Internal glue between the translation units of libmcz_b200.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace mcz {
+
+int set_error(const char* msg);
+int check_cuda(cudaError_t e, const char* what);
+void count_launch(int n = 1);
+
+size_t replay_scratch_bytes(long long G, long long N, int precision, int* grid_out);
+int launch_replay(const double* flux, const double* noise, long long G, long long N, uint32_t tok,
+                  int dust, int precision, double* Z, unsigned long long* present, int* trips,
+                  int* ret, void* scratch, size_t scratch_bytes, cudaStream_t stream);
+
+int launch_percentiles_f64(const double* Z, const unsigned char* present, long long rows, long long N,
+                           double* pct, int* nvalid, signed char* status, cudaStream_t stream);
+
+size_t production_scratch_bytes(long long G, long long n_draw, uint32_t tok);
+int launch_production(const float* meas, const float* err, long long G, long long n_draw, uint32_t tok,
+                      int dust, unsigned long long seed, unsigned long long galaxy_offset,
+                      int sample_mode, int deterministic, float* pct, int* nvalid,
+                      signed char* status, int* trips, int* ret, float* Z, void* scratch,
+                      size_t scratch_bytes, cudaStream_t stream);
+
+}  // namespace mcz

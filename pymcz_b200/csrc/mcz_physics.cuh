@@ -206,15 +206,45 @@ template <typename R> MCZ_HD R kk04_r23_trip(IterState<R>& st) {
   return d;
 }
 
+// What phase A hands to the iteration phase for one sample (16 bytes in float).
+template <typename R> struct Carry {
+  R y;         // logO3O2 (metscales.py:338-339)
+  R n2ha;      // logN2Ha (metscales.py:350)
+  R x;         // logR23  (metscales.py:434)
+  uint32_t aux;
+};
+
+// Build the loop constants from the carry; kd = this sample's KD02_N2O2 (NaN when absent).
+template <typename R> MCZ_HD void make_iter(const Carry<R>& c, R kd, IterState<R>& st) {
+  typedef Math<R> M;
+  const R y = c.y, y2 = c.y * c.y, n = c.n2ha, x = c.x;
+  st.num0 = R(32.81) - R(1.153) * y2;                                     // metscales.py:464-465
+  st.num1 = R(-3.396) - R(0.025) * y + R(0.1444) * y2;
+  st.den0 = R(4.603) - R(0.3119) * y - R(0.163) * y2;
+  st.den1 = R(-0.48) + R(0.0271) * y + R(0.02037) * y2;
+  st.A = poly3<R>(n, 7.04, 5.28, 6.28, 2.37);                             // metscales.py:1114-1116
+  st.B = poly3<R>(n, -2.44, -2.01, -0.325, 0.128) - M::exp10(n - R(0.2)) * (R(-3.16) + R(4.65) * n);
+  st.U0 = poly4<R>(x, 9.72, -0.777, -0.951, -0.072, -0.811);              // metscales.py:1172-1176
+  st.U1 = poly4<R>(x, 0.0737, -0.0713, -0.141, 0.0373, -0.058);
+  st.L0 = poly2<R>(x, 9.40, 4.65, -3.17);
+  st.L1 = poly2<R>(x, 0.272, 0.547, -0.513);
+  const uint32_t zi = c.aux & AUX_ZI_MASK;
+  st.Z1 = kd;        // the kernel overrides with 8.6 when KD02_N2O2 is absent / all-NaN (:1099-1103)
+  st.Z2 = zi == 0u ? R(8.2) : (zi == 1u ? R(8.4) : R(8.7));               // metscales.py:1156
+  st.lq1 = R(0);                                                          // logq_save (:1106)
+  st.lq2 = R(100);                                                        // logqold (:1163)
+  st.aux = c.aux;
+}
+
 // ---- phase A: everything that needs no cross-sample information -------------------------------
 // f[NUSED]: sanitised fluxes (non-finite -> 0, negative -> 0; metallicity.py:96-99) in `Used` order
 // e[5]:     scaled coefficient noise: D02 e1,e2 (metscales.py:679-680), M13_N2 e1,e2 (:948-949),
 //           M13_O3N2 e1 (:952; its e2 is drawn but never used, :953-955)
 // put(key, value) is called for every key that is present for this galaxy except the three KK04
-// iteration outputs, which phase C writes.
+// iteration outputs, which phase C writes.  `carry` is filled when the KD02 group is requested.
 template <typename R, class Put>
 MCZ_HD void phase_a(const R* f, const R* e, uint32_t flags, uint32_t tok, int dust_eff,
-                    Put& put, IterState<R>& st) {
+                    Put& put, Carry<R>& carry) {
   typedef Math<R> M;
   const R nan = M::nan();
   const bool ha = flags & F_HA, hb = flags & F_HB, o2 = flags & F_O2, o3 = flags & F_O3;
@@ -400,24 +430,11 @@ MCZ_HD void phase_a(const R* f, const R* e, uint32_t flags, uint32_t tok, int du
       kd = kd02_n2o2<R>(logN2O2);
       put(K_KD02_N2O2, kd);
     }
-    // state for the two KK04 loops
-    const R y2 = y * y;
-    st.num0 = R(32.81) - R(1.153) * y2;                                   // metscales.py:464-465
-    st.num1 = R(-3.396) - R(0.025) * y + R(0.1444) * y2;
-    st.den0 = R(4.603) - R(0.3119) * y - R(0.163) * y2;
-    st.den1 = R(-0.48) + R(0.0271) * y + R(0.02037) * y2;
-    st.A = poly3<R>(logN2Ha, 7.04, 5.28, 6.28, 2.37);                     // metscales.py:1114-1116
-    st.B = poly3<R>(logN2Ha, -2.44, -2.01, -0.325, 0.128) -
-           M::exp10(logN2Ha - R(0.2)) * (R(-3.16) + R(4.65) * logN2Ha);
-    st.U0 = poly4<R>(x, 9.72, -0.777, -0.951, -0.072, -0.811);            // metscales.py:1172-1176
-    st.U1 = poly4<R>(x, 0.0737, -0.0713, -0.141, 0.0373, -0.058);
-    st.L0 = poly2<R>(x, 9.40, 4.65, -3.17);
-    st.L1 = poly2<R>(x, 0.272, 0.547, -0.513);
-    st.Z1 = kd;        // the kernel overrides with 8.6 when KD02_N2O2 is absent / all-NaN (:1099-1103)
-    st.Z2 = zi == 0u ? R(8.2) : (zi == 1u ? R(8.4) : R(8.7));             // metscales.py:1156
-    st.lq1 = R(0);                                                        // logq_save (:1106)
-    st.lq2 = R(100);                                                      // logqold (:1163)
-    st.aux = zi | ((logN2Ha > R(0.8)) ? AUX_N2HA_GT08 : 0u);
+    (void)kd;
+    carry.y = y;
+    carry.n2ha = logN2Ha;
+    carry.x = x;
+    carry.aux = zi | ((logN2Ha > R(0.8)) ? AUX_N2HA_GT08 : 0u);
   }
 }
 

@@ -1,0 +1,726 @@
+// Fused production kernel of the pyMCZ hot path: for every galaxy, in ONE persistent kernel,
+//   A. Philox4x32-10 + Box-Muller perturbation of the line fluxes (reference mcz.py:509-519,
+//      436-442, 580-589), sanitising (metallicity.py:96-99), has* flags (metscales.py:287-378),
+//      E(B-V) + dust, every closed-form scale and the root-based ones (metscales.py:387-1087);
+//   B. the two KK04 fixed-point loops whose trip count is a per-galaxy mean over all samples
+//      (metscales.py:1111-1121, 1166-1181), state held in registers;
+//   C. KK04 validity masks and KD02comb (metscales.py:1127-1129, 1186, 1250-1261);
+//   D. per (galaxy, scale) finite filter, n, sum<=0 test and the 50/16/84th percentiles with
+//      numpy's linear interpolation (mcz.py:273-301), one warp per scale.
+// Layout: one thread block per galaxy (dynamic galaxy queue), per-scale sample columns staged in
+// shared memory [slot][sample] (conflict-free: consecutive threads own consecutive samples);
+// nothing but the 2x11 input floats and the percentile table touches HBM.  A second
+// instantiation keeps the columns in an L2-resident global scratch for N' too large for 227 KB.
+#include <float.h>
+#include "mcz_physics.cuh"
+#include "mcz_philox.cuh"
+#include "mcz_device_utils.cuh"
+#include "mcz_internal.h"
+
+namespace mcz {
+
+static constexpr int PT = 576;            // threads per block: 18 warps
+static constexpr int PW = PT / 32;
+static constexpr int HB = 64;             // histogram bins per selection level
+static constexpr int CAP = 256;           // candidates sorted per target bin
+static constexpr int CTRL_BYTES = 1024;
+
+struct ProdParams {
+  const float* meas;
+  const float* err;
+  long long G;
+  int N, Npad;
+  uint32_t tok;
+  int dust;
+  uint32_t seed_lo, seed_hi;
+  unsigned long long goff;
+  int correlated, deterministic;
+  uint32_t calls;                          // bit c set: Philox call c is needed
+  float* pct;
+  int* nvalid;
+  signed char* status;
+  int* trips;
+  int* ret;
+  float* Z;
+  int nstore;
+  signed char slot_of_key[NKEYS];
+  signed char key_of_slot[NKEYS];
+  unsigned long long* counter;
+  float* gscratch;                         // global variant: per-block columns + stash + loop state
+  long long gscratch_per_block;            // floats
+};
+
+struct Ctrl {
+  long long g;
+  uint32_t flags;
+  int any_valid_kd;
+  float line[2 * NLINES];
+  double red[4 * PW];
+};
+static_assert(sizeof(Ctrl) <= CTRL_BYTES, "control block too large");
+
+// ---- sampling ---------------------------------------------------------------------------------
+// Normal index j: 0..4 coefficient noise, 5..12 the consumed lines in `Used` order.
+__device__ __forceinline__ void draw_normals(uint32_t s, unsigned long long gg, const ProdParams& p,
+                                             float z[16]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    if (p.calls & (1u << c)) {
+      uint32_t o[4];
+      philox4x32_10(s, (uint32_t)c, (uint32_t)gg, (uint32_t)(gg >> 32), p.seed_lo, p.seed_hi, o);
+      box_muller(o[0], o[1], z[4 * c + 0], z[4 * c + 1]);
+      box_muller(o[2], o[3], z[4 * c + 2], z[4 * c + 3]);
+    } else {
+      z[4 * c + 0] = z[4 * c + 1] = z[4 * c + 2] = z[4 * c + 3] = 0.0f;
+    }
+  }
+}
+
+struct SlotPut {
+  float* col;                 // &vals[0][s]
+  int stride;
+  const signed char* slot_of_key;
+  __device__ __forceinline__ void operator()(int key, float v) const {
+    const int sl = slot_of_key[key];
+    if (sl >= 0) col[sl * stride] = v;
+  }
+};
+
+// ---- selection (one warp per stored scale) ----------------------------------------------------
+__device__ __forceinline__ bool finite_f(float x) { return fabsf(x) <= FLT_MAX; }
+
+__device__ __forceinline__ int bin_of(float x, float L, float scale) {
+  int b = __float2int_rz((x - L) * scale);
+  return min(max(b, 0), HB - 1);
+}
+
+template <typename HistT> __device__ __forceinline__ unsigned hist_row_sum(const HistT* row);
+template <> __device__ __forceinline__ unsigned hist_row_sum<unsigned char>(const unsigned char* row) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(row);
+  unsigned acc = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc = __dp4a(w[i], 0x01010101u, acc);
+  return acc;
+}
+template <> __device__ __forceinline__ unsigned hist_row_sum<unsigned short>(const unsigned short* row) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(row);
+  unsigned acc = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc += (w[i] & 0xffffu) + (w[i] >> 16);
+  return acc;
+}
+
+// Histogram of the members of [L, H] into HB linear bins; per-lane private counters
+// hist[bin][lane] (no atomics, no bank conflicts).  On return lane l holds the counts of bins l
+// and l+32 and their exclusive prefix sums.
+template <typename HistT>
+__device__ __forceinline__ void warp_histogram(const float* __restrict__ v, int N, float L, float H,
+                                               float scale, HistT* hist, unsigned& c0, unsigned& c1,
+                                               unsigned& e0, unsigned& e1) {
+  const int lane = threadIdx.x & 31;
+  uint32_t* hw = reinterpret_cast<uint32_t*>(hist);
+#pragma unroll
+  for (int i = 0; i < (int)(HB * 32 * sizeof(HistT) / 4 / 32); ++i) hw[i * 32 + lane] = 0u;
+  __syncwarp();
+  for (int s = lane; s < N; s += 32) {
+    const float x = v[s];
+    if (x >= L && x <= H) {          // NaN fails both; +-inf never inside a finite [L, H]
+      HistT* h = hist + bin_of(x, L, scale) * 32 + lane;
+      *h = (HistT)(*h + 1);
+    }
+  }
+  __syncwarp();
+  c0 = hist_row_sum<HistT>(hist + lane * 32);
+  c1 = hist_row_sum<HistT>(hist + (lane + 32) * 32);
+  unsigned i0 = c0, i1 = c1;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned t0 = __shfl_up_sync(0xffffffffu, i0, o), t1 = __shfl_up_sync(0xffffffffu, i1, o);
+    if (lane >= o) { i0 += t0; i1 += t1; }
+  }
+  const unsigned tot0 = __shfl_sync(0xffffffffu, i0, 31);
+  e0 = i0 - c0;
+  e1 = tot0 + i1 - c1;
+  __syncwarp();
+}
+
+// bin holding 0-based rank r (relative to the histogram) + its exclusive prefix and count
+__device__ __forceinline__ void locate_rank(unsigned r, unsigned c0, unsigned c1, unsigned e0,
+                                            unsigned e1, int& bin, unsigned& excl, unsigned& cnt) {
+  const unsigned m0 = __ballot_sync(0xffffffffu, c0 > 0 && r >= e0 && r < e0 + c0);
+  const unsigned m1 = __ballot_sync(0xffffffffu, c1 > 0 && r >= e1 && r < e1 + c1);
+  if (m0) {
+    const int l = __ffs(m0) - 1;
+    bin = l;
+    excl = __shfl_sync(0xffffffffu, e0, l);
+    cnt = __shfl_sync(0xffffffffu, c0, l);
+  } else {
+    const int l = m1 ? __ffs(m1) - 1 : 31;
+    bin = 32 + l;
+    excl = __shfl_sync(0xffffffffu, e1, l);
+    cnt = __shfl_sync(0xffffffffu, c1, l);
+  }
+}
+
+// gather the members of [L,H] whose bin is `b` into cand[] (cnt <= CAP) and sort them ascending
+__device__ __forceinline__ void gather_sort(const float* __restrict__ v, int N, float L, float H,
+                                            float scale, int b, unsigned cnt, float* cand) {
+  const int lane = threadIdx.x & 31;
+  unsigned filled = 0;
+  for (int s0 = 0; s0 < N; s0 += 32) {
+    const int s = s0 + lane;
+    const float x = s < N ? v[s] : 0.0f;
+    const bool hit = s < N && x >= L && x <= H && bin_of(x, L, scale) == b;
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (hit) cand[filled + __popc(m & ((1u << lane) - 1u))] = x;
+    filled += __popc(m);
+  }
+  unsigned M = 32;
+  while (M < cnt) M <<= 1;
+  for (unsigned i = cnt + lane; i < M; i += 32) cand[i] = __int_as_float(0x7f800000);   // +inf pad
+  __syncwarp();
+  for (unsigned k = 2; k <= M; k <<= 1) {
+    for (unsigned j = k >> 1; j > 0; j >>= 1) {
+      for (unsigned i = lane; i < M; i += 32) {
+        const unsigned ixj = i ^ j;
+        if (ixj > i) {
+          const float a = cand[i], c = cand[ixj];
+          const bool up = (i & k) == 0;
+          if ((a > c) == up) { cand[i] = c; cand[ixj] = a; }
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// min / max of the members of [L,H] falling in bin b
+__device__ __forceinline__ void bin_minmax(const float* __restrict__ v, int N, float L, float H,
+                                           float scale, int b, float& mn, float& mx) {
+  const int lane = threadIdx.x & 31;
+  mn = __int_as_float(0x7f800000);
+  mx = __int_as_float(0xff800000);
+  for (int s = lane; s < N; s += 32) {
+    const float x = v[s];
+    if (x >= L && x <= H && bin_of(x, L, scale) == b) { mn = fminf(mn, x); mx = fmaxf(mx, x); }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+}
+
+// generic exact order statistic: rank r (0-based among the finite values) by repeated narrowing
+template <typename HistT>
+__device__ float select_one(const float* __restrict__ v, int N, unsigned r, float L, float H,
+                            HistT* hist, float* cand) {
+  unsigned base = 0;
+  for (;;) {
+    if (!(H > L)) return L;
+    const float scale = (float)HB / (H - L);
+    unsigned c0, c1, e0, e1, excl, cnt;
+    int b;
+    warp_histogram<HistT>(v, N, L, H, scale, hist, c0, c1, e0, e1);
+    locate_rank(r - base, c0, c1, e0, e1, b, excl, cnt);
+    if (cnt <= (unsigned)CAP) {
+      gather_sort(v, N, L, H, scale, b, cnt, cand);
+      const float out = cand[r - base - excl];
+      __syncwarp();
+      return out;
+    }
+    float mn, mx;
+    bin_minmax(v, N, L, H, scale, b, mn, mx);
+    base += excl;
+    L = mn;
+    H = mx;
+  }
+}
+
+// numpy.lib._function_base_impl._lerp in float64 on the float32 order statistics
+__device__ __forceinline__ float np_lerp_f(float a, float b, double t) {
+  const double da = a, db = b, d = db - da;
+  return (float)((t >= 0.5) ? (db - d * (1.0 - t)) : (da + d * t));
+}
+
+// percentile extraction for one stored column (mcz.py:273-301); all 32 lanes participate
+template <typename HistT>
+__device__ void warp_percentiles(const float* __restrict__ v, int N, HistT* hist, float* cand,
+                                 float pct[3], int& nvalid, int& status) {
+  const int lane = threadIdx.x & 31;
+  int cnt = 0;
+  float sum = 0.0f, mn = __int_as_float(0x7f800000), mx = __int_as_float(0xff800000);
+  for (int s = lane; s < N; s += 32) {
+    const float x = v[s];
+    if (finite_f(x)) { ++cnt; sum += x; mn = fminf(mn, x); mx = fmaxf(mx, x); }   // mcz.py:273
+  }
+  const int n = __reduce_add_sync(0xffffffffu, cnt);
+  const double total = warp_sum((double)sum);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  const float nanf_ = Math<float>::nan();
+  pct[0] = pct[1] = pct[2] = nanf_;
+  nvalid = n;
+  if (n == 0) { status = ST_EMPTY; return; }                                      // mcz.py:277-280
+  if (!(total > 0.0)) { status = ST_NONPOS; return; }                             // mcz.py:282-285
+  status = ST_OK;
+  const double qs[3] = {50.0 / 100.0, 16.0 / 100.0, 84.0 / 100.0};                // mcz.py:288
+  unsigned rk[6];
+  double gam[3];
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    const double vi = (double)(n - 1) * qs[q];
+    const double lo = floor(vi);
+    gam[q] = vi - lo;
+    rk[2 * q] = (unsigned)lo;
+    rk[2 * q + 1] = min((unsigned)lo + 1u, (unsigned)(n - 1));
+  }
+  float res[6];
+  if (!(mx > mn)) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) res[i] = mn;
+  } else {
+    // level-1 histogram shared by all six ranks
+    const float scale = (float)HB / (mx - mn);
+    unsigned c0, c1, e0, e1;
+    warp_histogram<HistT>(v, N, mn, mx, scale, hist, c0, c1, e0, e1);
+    int bins[6];
+    unsigned excl[6], cnts[6];
+    bool fast = true;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      locate_rank(rk[i], c0, c1, e0, e1, bins[i], excl[i], cnts[i]);
+      fast = fast && cnts[i] <= (unsigned)CAP;
+    }
+    if (fast) {
+      unsigned done = 0;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        if (done & (1u << i)) continue;
+        gather_sort(v, N, mn, mx, scale, bins[i], cnts[i], cand);
+#pragma unroll
+        for (int j = i; j < 6; ++j)
+          if (!(done & (1u << j)) && bins[j] == bins[i]) { res[j] = cand[rk[j] - excl[j]]; done |= 1u << j; }
+        __syncwarp();
+      }
+    } else {
+#pragma unroll 1
+      for (int i = 0; i < 6; ++i) {
+        if (i > 0 && rk[i] == rk[i - 1]) { res[i] = res[i - 1]; continue; }
+        res[i] = select_one<HistT>(v, N, rk[i], mn, mx, hist, cand);
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 3; ++q) pct[q] = np_lerp_f(res[2 * q], res[2 * q + 1], gam[q]);
+  (void)lane;
+}
+
+// ---- the kernel -------------------------------------------------------------------------------
+// SLOTS > 0: at most SLOTS samples per thread, loop state in registers, columns in shared memory.
+// SLOTS == 0: any N', columns / stash / loop state in the per-block global scratch.
+template <int SLOTS, typename HistT>
+__global__ void __launch_bounds__(PT, 1)
+production_kernel(const __grid_constant__ ProdParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  constexpr bool GLOBAL = (SLOTS == 0);
+  Ctrl* ctrl = reinterpret_cast<Ctrl*>(smem);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = p.N, Npad = p.Npad;
+
+  float* vals;          // [nstore][Npad]
+  float* stash;         // y, n2ha, x, aux : [4][Npad]
+  float* giter = nullptr;   // global variant: loop state [16][Npad]
+  unsigned char* work;  // selection scratch (aliases the stash in the shared-memory variant)
+  if (GLOBAL) {
+    float* base = p.gscratch + (long long)blockIdx.x * p.gscratch_per_block;
+    vals = base;
+    stash = base + (long long)p.nstore * Npad;
+    giter = stash + 4ll * Npad;
+    work = smem + CTRL_BYTES;
+  } else {
+    vals = reinterpret_cast<float*>(smem + CTRL_BYTES);
+    work = smem + CTRL_BYTES + (size_t)p.nstore * Npad * sizeof(float);
+    stash = reinterpret_cast<float*>(work);
+  }
+  HistT* hist = reinterpret_cast<HistT*>(work) + (size_t)warp * HB * 32;
+  float* cand = reinterpret_cast<float*>(work + (size_t)PW * HB * 32 * sizeof(HistT)) + warp * CAP;
+
+  const int used2line[NUSED] = {L_HA, L_HB, L_O2, L_O3, L_N2, L_S2A, L_S2B, L_S39069};
+  const int nsl = (N + PT - 1) / PT;
+  int phase = 0;
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) ctrl->g = (long long)atomicAdd(p.counter, 1ull);
+    __syncthreads();
+    const long long g = ctrl->g;
+    if (g >= p.G) break;
+    if (tid < NLINES) ctrl->line[tid] = p.meas[g * NLINES + tid];
+    else if (tid < 2 * NLINES) ctrl->line[tid] = p.err[g * NLINES + (tid - NLINES)];
+    if (tid == 0) ctrl->flags = 0u;
+    __syncthreads();
+    float lm[NUSED], le[NUSED];
+    uint32_t assumed = 0u;
+#pragma unroll
+    for (int u = 0; u < NUSED; ++u) {
+      lm[u] = ctrl->line[used2line[u]];
+      le[u] = p.deterministic ? 0.0f : ctrl->line[NLINES + used2line[u]];
+      const float thr = (u >= U_S2B) ? 1e-9f : 0.0f;
+      // any(sample > thr): certain when err == 0, assumed true (and verified below) otherwise
+      bool a = finite_f(lm[u]) && finite_f(le[u]);
+      if (a && le[u] == 0.0f) a = lm[u] > thr;
+      if (a) assumed |= 1u << u;
+    }
+    const unsigned long long gg = p.goff + (unsigned long long)g;
+
+    // ---- phase A (repeated once in the rare case the assumed flags were wrong) ----------------
+    uint32_t flags = assumed;
+    for (;;) {
+      const int de = effective_dust(p.dust, flags);
+      uint32_t seen = 0u;
+#pragma unroll 1
+      for (int i = 0; i < nsl; ++i) {
+        const int s = i * PT + tid;
+        if (s < N) {
+          float z[16];
+          draw_normals((uint32_t)s, gg, p, z);
+          float f[NUSED], e[5];
+#pragma unroll
+          for (int u = 0; u < NUSED; ++u) {
+            float v = fmaf(le[u], p.correlated ? z[5] : z[5 + u], lm[u]);          // mcz.py:442 / :589
+            if (!finite_f(v)) v = 0.0f;                                            // metallicity.py:96
+            if (v < 0.0f) v = 0.0f;                                                // metallicity.py:99
+            f[u] = v;
+            const bool pos = (u >= U_S2B) ? (v > 1e-9f) : (v > 0.0f);
+            if (pos) seen |= 1u << u;
+          }
+          e[0] = 0.05f * z[0];            // metscales.py:679
+          e[1] = 0.1f * z[1];             // metscales.py:680
+          e[2] = 0.027f * z[2];           // metscales.py:948
+          e[3] = 0.024f * z[3];           // metscales.py:949
+          e[4] = 0.012f * z[4];           // metscales.py:952
+          SlotPut put{vals + s, Npad, p.slot_of_key};
+          Carry<float> c;
+          c.y = c.n2ha = c.x = 0.0f;
+          c.aux = 0u;
+          phase_a<float>(f, e, flags, p.tok, de, put, c);
+          stash[s] = c.y;
+          stash[Npad + s] = c.n2ha;
+          stash[2 * Npad + s] = c.x;
+          stash[3 * Npad + s] = __uint_as_float(c.aux);
+        }
+      }
+      seen = __reduce_or_sync(0xffffffffu, seen);
+      if (lane == 0 && seen) atomicOr(&ctrl->flags, seen);
+      __syncthreads();
+      const uint32_t actual = ctrl->flags;
+      if (actual == flags) break;
+      flags = actual;               // deterministic samples: the second pass reproduces `actual`
+    }
+    const uint64_t pm = present_mask(flags, p.tok);
+    const bool ok = minimum_ok(flags);
+
+    // ---- phases B and C ----------------------------------------------------------------------
+    int ii1 = 0, ii2 = 0;
+    if ((p.tok & T_KD02) && ok) {
+      const bool has_kd = (pm >> K_KD02_N2O2) & 1ull;
+      const bool has_kn = (pm >> K_KK04_N2HA) & 1ull, has_kr = (pm >> K_KK04_R23) & 1ull;
+      const bool o3o2 = (flags & F_O2) && (flags & F_O3);
+      const int sl_kd = p.slot_of_key[K_KD02_N2O2], sl_m91 = p.slot_of_key[K_M91];
+      bool act1 = has_kn && o3o2, act2 = has_kr;
+      if constexpr (!GLOBAL) {
+        IterState<float> st[SLOTS];
+        bool any = false;
+#pragma unroll
+        for (int i = 0; i < SLOTS; ++i) {
+          const int s = i * PT + tid;
+          if (s < N) {
+            Carry<float> c;
+            c.y = stash[s]; c.n2ha = stash[Npad + s]; c.x = stash[2 * Npad + s];
+            c.aux = __float_as_uint(stash[3 * Npad + s]);
+            const float kd = has_kd ? vals[sl_kd * Npad + s] : Math<float>::nan();
+            make_iter<float>(c, kd, st[i]);
+            any = any || !Math<float>::isnan(kd);
+          }
+        }
+        // start of the N2Ha loop: 8.6 if KD02_N2O2 is None or all-NaN (metscales.py:1097-1103)
+        if (!__syncthreads_or(any)) {
+#pragma unroll
+          for (int i = 0; i < SLOTS; ++i) st[i].Z1 = 8.6f;
+        }
+        if (has_kn && !o3o2) {
+#pragma unroll
+          for (int i = 0; i < SLOTS; ++i) st[i].Z1 = kk04_n2ha_noq<float>(st[i]);
+        }
+        while (act1 || act2) {
+          float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+          for (int i = 0; i < SLOTS; ++i) {
+            if (i * PT + tid < N) {
+              if (act1) s1 += kk04_n2ha_trip<float>(st[i]);
+              if (act2) s2 += kk04_r23_trip<float>(st[i]);
+            }
+          }
+          double d1 = (double)warp_sum(s1), d2 = (double)warp_sum(s2);
+          double* b = ctrl->red + phase * 2 * PW;
+          if (lane == 0) { b[2 * warp] = d1; b[2 * warp + 1] = d2; }
+          __syncthreads();
+          d1 = 0.0; d2 = 0.0;
+#pragma unroll
+          for (int w = 0; w < PW; ++w) { d1 += b[2 * w]; d2 += b[2 * w + 1]; }
+          phase ^= 1;
+          if (act1) { ++ii1; act1 = (d1 / (double)N > 1.0e-3) && ii1 < 100; }          // metscales.py:1111,1117
+          if (act2) { ++ii2; act2 = (fabs(d2 / (double)N) > 1e-4) && ii2 < 100; }      // metscales.py:1166,1177
+        }
+#pragma unroll
+        for (int i = 0; i < SLOTS; ++i) {
+          const int s = i * PT + tid;
+          if (s < N) {
+            SlotPut put{vals + s, Npad, p.slot_of_key};
+            const float kd = has_kd ? vals[sl_kd * Npad + s] : Math<float>::nan();
+            const float m91 = vals[sl_m91 * Npad + s];
+            phase_c<float>(st[i], pm, ii1 >= 100, ii2 >= 100, kd, m91, put);
+          }
+        }
+      } else {
+        // memory-backed loop state: fields [16][Npad] in the per-block global scratch
+        float* F = giter;
+        bool any = false;
+        for (int s = tid; s < N; s += PT) {
+          Carry<float> c;
+          c.y = stash[s]; c.n2ha = stash[Npad + s]; c.x = stash[2 * Npad + s];
+          c.aux = __float_as_uint(stash[3 * Npad + s]);
+          const float kd = has_kd ? vals[(long long)sl_kd * Npad + s] : Math<float>::nan();
+          IterState<float> st;
+          make_iter<float>(c, kd, st);
+          any = any || !Math<float>::isnan(kd);
+          F[0ll * Npad + s] = st.num0; F[1ll * Npad + s] = st.num1; F[2ll * Npad + s] = st.den0;
+          F[3ll * Npad + s] = st.den1; F[4ll * Npad + s] = st.A; F[5ll * Npad + s] = st.B;
+          F[6ll * Npad + s] = st.U0; F[7ll * Npad + s] = st.U1; F[8ll * Npad + s] = st.L0;
+          F[9ll * Npad + s] = st.L1; F[10ll * Npad + s] = st.Z1; F[11ll * Npad + s] = st.Z2;
+          F[12ll * Npad + s] = st.lq1; F[13ll * Npad + s] = st.lq2;
+        }
+        const bool allnan = !__syncthreads_or(any);
+        if (allnan || (has_kn && !o3o2)) {
+          for (int s = tid; s < N; s += PT) {
+            float z1 = allnan ? 8.6f : F[10ll * Npad + s];
+            if (has_kn && !o3o2) z1 = F[4ll * Npad + s] - 7.37177f * F[5ll * Npad + s];
+            F[10ll * Npad + s] = z1;
+          }
+        }
+        while (act1 || act2) {
+          float s1 = 0.0f, s2 = 0.0f;
+          for (int s = tid; s < N; s += PT) {
+            IterState<float> st;
+            st.num0 = F[0ll * Npad + s]; st.num1 = F[1ll * Npad + s]; st.den0 = F[2ll * Npad + s];
+            st.den1 = F[3ll * Npad + s];
+            st.aux = __float_as_uint(stash[3 * Npad + s]);
+            if (act1) {
+              st.A = F[4ll * Npad + s]; st.B = F[5ll * Npad + s];
+              st.Z1 = F[10ll * Npad + s]; st.lq1 = F[12ll * Npad + s];
+              s1 += kk04_n2ha_trip<float>(st);
+              F[10ll * Npad + s] = st.Z1; F[12ll * Npad + s] = st.lq1;
+            }
+            if (act2) {
+              st.U0 = F[6ll * Npad + s]; st.U1 = F[7ll * Npad + s]; st.L0 = F[8ll * Npad + s];
+              st.L1 = F[9ll * Npad + s];
+              st.Z2 = F[11ll * Npad + s]; st.lq2 = F[13ll * Npad + s];
+              s2 += kk04_r23_trip<float>(st);
+              F[11ll * Npad + s] = st.Z2; F[13ll * Npad + s] = st.lq2;
+            }
+          }
+          double d1 = (double)warp_sum(s1), d2 = (double)warp_sum(s2);
+          double* b = ctrl->red + phase * 2 * PW;
+          if (lane == 0) { b[2 * warp] = d1; b[2 * warp + 1] = d2; }
+          __syncthreads();
+          d1 = 0.0; d2 = 0.0;
+#pragma unroll
+          for (int w = 0; w < PW; ++w) { d1 += b[2 * w]; d2 += b[2 * w + 1]; }
+          phase ^= 1;
+          if (act1) { ++ii1; act1 = (d1 / (double)N > 1.0e-3) && ii1 < 100; }
+          if (act2) { ++ii2; act2 = (fabs(d2 / (double)N) > 1e-4) && ii2 < 100; }
+        }
+        for (int s = tid; s < N; s += PT) {
+          IterState<float> st;
+          st.U0 = F[6ll * Npad + s]; st.U1 = F[7ll * Npad + s]; st.L0 = F[8ll * Npad + s];
+          st.L1 = F[9ll * Npad + s]; st.Z1 = F[10ll * Npad + s]; st.Z2 = F[11ll * Npad + s];
+          st.lq2 = F[13ll * Npad + s];
+          st.aux = __float_as_uint(stash[3 * Npad + s]);
+          SlotPut put{vals + s, Npad, p.slot_of_key};
+          const float kd = has_kd ? vals[(long long)sl_kd * Npad + s] : Math<float>::nan();
+          const float m91 = vals[(long long)sl_m91 * Npad + s];
+          phase_c<float>(st, pm, ii1 >= 100, ii2 >= 100, kd, m91, put);
+        }
+      }
+    }
+    __syncthreads();     // all columns final; the stash is dead from here (selection reuses it)
+
+    // ---- optional per-sample output (pickle / --asciidistrib path) ----------------------------
+    if (p.Z) {
+      for (int k = 0; k < NKEYS; ++k) {
+        const int sl = p.slot_of_key[k];
+        const bool live = ((pm >> k) & 1ull) && sl >= 0;
+        float* dst = p.Z + ((long long)g * NKEYS + k) * N;
+        for (int s = tid; s < N; s += PT) dst[s] = live ? vals[(long long)sl * Npad + s] : Math<float>::nan();
+      }
+    }
+
+    // ---- phase D: percentiles, one warp per stored column -------------------------------------
+    if (tid < NKEYS) {
+      const int k = tid, sl = p.slot_of_key[k];
+      const bool pres = (pm >> k) & 1ull;
+      if (!(pres && sl >= 0)) {
+        const long long o = g * NKEYS + k;
+        p.status[o] = pres ? ST_EMPTY : ST_ABSENT;     // present but constant-NaN (M08_R23): n = 0
+        p.nvalid[o] = 0;
+        p.pct[3 * o] = p.pct[3 * o + 1] = p.pct[3 * o + 2] = Math<float>::nan();
+      }
+    }
+    if (tid == 0) {
+      p.trips[2 * g] = ii1;
+      p.trips[2 * g + 1] = ii2;
+      if (p.ret) p.ret[g] = ok ? 0 : -1;
+    }
+    for (int sl = warp; sl < p.nstore; sl += PW) {
+      const int k = p.key_of_slot[sl];
+      if (!((pm >> k) & 1ull)) continue;
+      float pc[3];
+      int nv, stt;
+      warp_percentiles<HistT>(vals + (long long)sl * Npad, N, hist, cand, pc, nv, stt);
+      if (lane == 0) {
+        const long long o = g * NKEYS + k;
+        p.status[o] = (signed char)stt;
+        p.nvalid[o] = nv;
+        p.pct[3 * o] = pc[0];
+        p.pct[3 * o + 1] = pc[1];
+        p.pct[3 * o + 2] = pc[2];
+      }
+    }
+  }
+}
+
+// ---- host side --------------------------------------------------------------------------------
+static void build_slots(uint32_t tok, ProdParams& p) {
+  // every key that can be present under `tok` with all lines measured, minus constant-NaN ones
+  const uint64_t pm = present_mask(F_ALL, tok);
+  int n = 0;
+  for (int k = 0; k < NKEYS; ++k) {
+    p.slot_of_key[k] = -1;
+    p.key_of_slot[k] = -1;
+  }
+  for (int k = 0; k < NKEYS; ++k) {
+    if (!((pm >> k) & 1ull) || k == K_M08_R23) continue;
+    p.slot_of_key[k] = (signed char)n;
+    p.key_of_slot[n] = (signed char)k;
+    ++n;
+  }
+  p.nstore = n;
+}
+
+static uint32_t philox_calls(uint32_t tok, int correlated, int deterministic) {
+  uint32_t calls = 0;
+  if (tok & (T_D02 | T_M13)) calls |= 1u | 2u;          // normals 0..4
+  if (!deterministic) {
+    calls |= 2u;                                         // normals 5..7 (Ha, Hb, [OII])
+    if (!correlated) {
+      calls |= 4u;                                       // normals 8..11 ([OIII], [NII], [SII] x2)
+      if (tok & T_DP00) calls |= 8u;                     // normal 12 ([SIII]9069)
+    }
+  }
+  return calls;
+}
+
+struct ProdPlan {
+  bool global;
+  int Npad, grid;
+  size_t smem;
+  long long per_block_floats;
+};
+
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+static ProdPlan make_plan(long long G, long long N, int nstore) {
+  ProdPlan pl;
+  pl.Npad = (int)((N + 31) / 32 * 32);
+  const size_t cols = (size_t)nstore * pl.Npad * sizeof(float);
+  const size_t stash = 4ull * pl.Npad * sizeof(float);
+  const size_t sel8 = (size_t)PW * (HB * 32 * sizeof(unsigned char) + CAP * sizeof(float));
+  const size_t sel16 = (size_t)PW * (HB * 32 * sizeof(unsigned short) + CAP * sizeof(float));
+  const size_t smem_local = CTRL_BYTES + cols + (stash > sel8 ? stash : sel8);
+  pl.global = !(N <= 4ll * PT && smem_local <= 227ull * 1024);
+  pl.smem = pl.global ? CTRL_BYTES + sel16 : smem_local;
+  pl.per_block_floats = pl.global ? ((long long)nstore + 4 + 16) * pl.Npad : 0;
+  const long long sms = num_sms();
+  pl.grid = (int)(G < sms ? (G > 0 ? G : 1) : sms);
+  return pl;
+}
+
+size_t production_scratch_bytes(long long G, long long n_draw, uint32_t tok) {
+  ProdParams p;
+  build_slots(tok, p);
+  const ProdPlan pl = make_plan(G, n_draw, p.nstore);
+  return 256 + (size_t)pl.grid * (size_t)pl.per_block_floats * sizeof(float);
+}
+
+int launch_production(const float* meas, const float* err, long long G, long long n_draw, uint32_t tok,
+                      int dust, unsigned long long seed, unsigned long long galaxy_offset,
+                      int sample_mode, int deterministic, float* pct, int* nvalid,
+                      signed char* status, int* trips, int* ret, float* Z, void* scratch,
+                      size_t scratch_bytes, cudaStream_t stream) {
+  if (G <= 0) return 0;
+  if (n_draw <= 0 || n_draw > 0x7fffffffll / 64) return set_error("mcz_forward_production: bad n_draw");
+  if (tok & T_M08ALL) return set_error("mcz_forward_production: M08all is not built yet");
+  ProdParams p;
+  build_slots(tok, p);
+  const ProdPlan pl = make_plan(G, n_draw, p.nstore);
+  if (scratch_bytes < production_scratch_bytes(G, n_draw, tok))
+    return set_error("mcz_forward_production: scratch too small");
+  p.meas = meas; p.err = err; p.G = G; p.N = (int)n_draw; p.Npad = pl.Npad; p.tok = tok; p.dust = dust;
+  p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32); p.goff = galaxy_offset;
+  p.correlated = sample_mode == 1; p.deterministic = deterministic != 0;
+  p.calls = philox_calls(tok, p.correlated, p.deterministic);
+  p.pct = pct; p.nvalid = nvalid; p.status = status; p.trips = trips; p.ret = ret; p.Z = Z;
+  p.counter = reinterpret_cast<unsigned long long*>(scratch);
+  p.gscratch = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(scratch) + 256);
+  p.gscratch_per_block = pl.per_block_floats;
+  int rc = check_cuda(cudaMemsetAsync(scratch, 0, 256, stream), "counter memset");
+  if (rc) return rc;
+  if (!pl.global) {
+    static bool attr_done = false;
+    if (!attr_done) {
+      rc = check_cuda(cudaFuncSetAttribute(production_kernel<4, unsigned char>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
+                      "smem attribute");
+      if (rc) return rc;
+      attr_done = true;
+    }
+    production_kernel<4, unsigned char><<<pl.grid, PT, pl.smem, stream>>>(p);
+  } else {
+    static bool attr_done = false;
+    if (!attr_done) {
+      rc = check_cuda(cudaFuncSetAttribute(production_kernel<0, unsigned short>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
+                      "smem attribute");
+      if (rc) return rc;
+      attr_done = true;
+    }
+    production_kernel<0, unsigned short><<<pl.grid, PT, pl.smem, stream>>>(p);
+  }
+  count_launch();
+  return check_cuda(cudaGetLastError(), "production_kernel launch");
+}
+
+}  // namespace mcz

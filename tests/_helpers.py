@@ -59,3 +59,61 @@ def compare_samples(Z, Zo, present, presento, tol=1e-3, what=""):
     maxdiff = float(np.max(np.abs(Z[fin] - Zo[fin]))) if fin.any() else 0.0
     same_inf = np.all(Z[both & ~fin] == Zo[both & ~fin]) if (both & ~fin).any() else True
     return mism, inf_mism, maxdiff, bool(same_inf)
+
+
+# ---- numpy model of the production sampler (csrc/mcz_philox.cuh + draw_normals) ---------------
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Vectorised Philox4x32-10 (Salmon et al. 2011); uint32 arrays in, 4 uint32 arrays out."""
+    M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+    c0, c1, c2, c3 = (np.asarray(x, dtype=np.uint64) for x in (c0, c1, c2, c3))
+    k0 = np.uint64(k0)
+    k1 = np.uint64(k1)
+    mask = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0 = np.uint64(M0) * c0
+        p1 = np.uint64(M1) * c2
+        hi0, lo0 = p0 >> np.uint64(32), p0 & mask
+        hi1, lo1 = p1 >> np.uint64(32), p1 & mask
+        c0, c1, c2, c3 = (hi1 ^ c1 ^ k0) & mask, lo1, (hi0 ^ c3 ^ k1) & mask, lo0
+        k0 = (k0 + np.uint64(W0)) & mask
+        k1 = (k1 + np.uint64(W1)) & mask
+    return c0.astype(np.uint32), c1.astype(np.uint32), c2.astype(np.uint32), c3.astype(np.uint32)
+
+
+def box_muller(a, b):
+    u1 = (((a >> np.uint32(9)) | np.uint32(0x3f800000)).view(np.float32) - np.float32(0.99999994)).astype(np.float64)
+    u2 = (((b >> np.uint32(9)) | np.uint32(0x3f800000)).view(np.float32) - np.float32(1.5)).astype(np.float64)
+    r = np.sqrt(np.maximum(-2.0 * np.log(u1), 0.0))
+    th = 2.0 * np.pi * u2
+    return r * np.cos(th), r * np.sin(th)
+
+
+def production_normals(seed, galaxy, n):
+    """The 16 standard normals per sample the production kernel derives for global galaxy index
+    `galaxy` (float64 model of the float32/MUFU device arithmetic): returns z[16, n]."""
+    s = np.arange(n, dtype=np.uint32)
+    z = np.zeros((16, n))
+    for c in range(4):
+        o = philox4x32_10(s, np.full(n, c, np.uint32), np.full(n, galaxy & 0xFFFFFFFF, np.uint32),
+                          np.full(n, galaxy >> 32, np.uint32), seed & 0xFFFFFFFF, seed >> 32)
+        z[4 * c + 0], z[4 * c + 1] = box_muller(o[0], o[1])
+        z[4 * c + 2], z[4 * c + 3] = box_muller(o[2], o[3])
+    return z
+
+
+USED_LINES = [5, 1, 0, 3, 6, 7, 8, 9]      # Ha, Hb, [OII], [OIII]5007, [NII], [SII]6717, [SII]6731, [SIII]9069
+NOISE_SIGMA = [0.05, 0.1, 0.027, 0.024, 0.012]
+
+
+def production_flux_model(meas_row, err_row, seed, galaxy, n, correlated=False):
+    """flux [11, n] float64 and noise [5, n] as the production kernel samples them (float32
+    fma of float32 inputs); lines the kernel never reads are left NaN-free copies of meas."""
+    z = production_normals(seed, galaxy, n)
+    flux = np.zeros((11, n))
+    for j in range(11):
+        flux[j] = meas_row[j]
+    for u, line in enumerate(USED_LINES):
+        zz = z[5] if correlated else z[5 + u]
+        flux[line] = (np.float32(meas_row[line]) + np.float32(err_row[line]) * zz.astype(np.float32)).astype(np.float64)
+    noise = np.array([NOISE_SIGMA[j] * z[j] for j in range(5)])
+    return flux, noise

@@ -39,7 +39,13 @@ static void run(const double* flux, const double* noise, int N, uint32_t tok, in
     for (int j = 0; j < 5; ++j) e[j] = (R)noise[(size_t)j * N + s];
     ArrPut<R> put{Z, N, s};
     std::memset(&st[s], 0, sizeof(IterState<R>));
-    phase_a<R>(&f[(size_t)s * NUSED], e, flags, tok, de, put, st[s]);
+    Carry<R> c;
+    std::memset(&c, 0, sizeof(c));
+    phase_a<R>(&f[(size_t)s * NUSED], e, flags, tok, de, put, c);
+    if ((tok & T_KD02) && minimum_ok(flags)) {
+      const R kd = (present & (1ull << K_KD02_N2O2)) ? (R)Z[(size_t)K_KD02_N2O2 * N + s] : Math<R>::nan();
+      make_iter<R>(c, kd, st[s]);
+    }
   }
   trips[0] = trips[1] = 0;
   if (!(tok & T_KD02) || !minimum_ok(flags)) return;
@@ -90,4 +96,12 @@ extern "C" int hostemu_galaxy(int use_float, const double* flux, const double* n
   else run<double>(flux, noise, N, tok, dust, Z, &p, trips, ret);
   *present = p;
   return 0;
+}
+
+#include "../../pymcz_b200/csrc/mcz_philox.cuh"
+extern "C" void hostemu_philox(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0,
+                               unsigned k1, unsigned* out) {
+  uint32_t o[4];
+  mcz::philox4x32_10(c0, c1, c2, c3, k0, k1, o);
+  for (int i = 0; i < 4; ++i) out[i] = o[i];
 }

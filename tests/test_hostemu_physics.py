@@ -104,3 +104,18 @@ def test_hostemu_missing_lines(emu, golden_dir):
         mism, inf_mism, maxdiff, same_inf = compare_samples(Z, Zo, pm, po, what="row %d" % i)
         assert mism == 0 and inf_mism == 0 and same_inf and maxdiff < 1e-9, (i, mism, maxdiff)
         assert trips == trips_o
+
+
+def test_philox_known_answers(emu):
+    """Random123 kat_vectors for philox4x32-10, against the header the kernel compiles."""
+    kats = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+            ((0xffffffff,) * 4, (0xffffffff, 0xffffffff), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+            ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+             (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    from tests._helpers import philox4x32_10
+    for c, k, want in kats:
+        out = (ctypes.c_uint * 4)()
+        emu.hostemu_philox(*[ctypes.c_uint(x) for x in c], ctypes.c_uint(k[0]), ctypes.c_uint(k[1]), out)
+        assert tuple(out) == want
+        model = philox4x32_10(*[np.array([x], np.uint32) for x in c], k[0], k[1])
+        assert tuple(int(v[0]) for v in model) == want
