@@ -55,7 +55,7 @@ struct Ctrl {
   uint32_t flags;
   int any_valid_kd;
   float line[2 * NLINES];
-  double red[4 * PW];
+  float2 redf[2 * PW];
 };
 static_assert(sizeof(Ctrl) <= CTRL_BYTES, "control block too large");
 
@@ -76,6 +76,21 @@ __device__ __forceinline__ void draw_normals(uint32_t s, unsigned long long gg, 
   }
 }
 
+// Block-wide sums of two floats, every thread gets both totals (NaN propagates); one barrier per
+// call thanks to the alternating buffer.
+__device__ __forceinline__ void block_sum2f(float& a, float& c, float2* buf, int& phase) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  a = warp_sum(a);
+  c = warp_sum(c);
+  float2* b = buf + phase * PW;
+  if (lane == 0) b[warp] = make_float2(a, c);
+  __syncthreads();
+  const float2 pr = lane < PW ? b[lane] : make_float2(0.0f, 0.0f);
+  a = warp_sum(pr.x);
+  c = warp_sum(pr.y);
+  phase ^= 1;
+}
+
 struct SlotPut {
   float* col;                 // &vals[0][s]
   int stride;
@@ -86,238 +101,9 @@ struct SlotPut {
   }
 };
 
-// ---- selection (one warp per stored scale) ----------------------------------------------------
-__device__ __forceinline__ bool finite_f(float x) { return fabsf(x) <= FLT_MAX; }
-
-__device__ __forceinline__ int bin_of(float x, float L, float scale) {
-  int b = __float2int_rz((x - L) * scale);
-  return min(max(b, 0), HB - 1);
-}
-
-template <typename HistT> __device__ __forceinline__ unsigned hist_row_sum(const HistT* row);
-template <> __device__ __forceinline__ unsigned hist_row_sum<unsigned char>(const unsigned char* row) {
-  const uint32_t* w = reinterpret_cast<const uint32_t*>(row);
-  unsigned acc = 0;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) acc = __dp4a(w[i], 0x01010101u, acc);
-  return acc;
-}
-template <> __device__ __forceinline__ unsigned hist_row_sum<unsigned short>(const unsigned short* row) {
-  const uint32_t* w = reinterpret_cast<const uint32_t*>(row);
-  unsigned acc = 0;
-#pragma unroll
-  for (int i = 0; i < 16; ++i) acc += (w[i] & 0xffffu) + (w[i] >> 16);
-  return acc;
-}
-
-// Histogram of the members of [L, H] into HB linear bins; per-lane private counters
-// hist[bin][lane] (no atomics, no bank conflicts).  On return lane l holds the counts of bins l
-// and l+32 and their exclusive prefix sums.
-template <typename HistT>
-__device__ __forceinline__ void warp_histogram(const float* __restrict__ v, int N, float L, float H,
-                                               float scale, HistT* hist, unsigned& c0, unsigned& c1,
-                                               unsigned& e0, unsigned& e1) {
-  const int lane = threadIdx.x & 31;
-  uint32_t* hw = reinterpret_cast<uint32_t*>(hist);
-#pragma unroll
-  for (int i = 0; i < (int)(HB * 32 * sizeof(HistT) / 4 / 32); ++i) hw[i * 32 + lane] = 0u;
-  __syncwarp();
-  for (int s = lane; s < N; s += 32) {
-    const float x = v[s];
-    if (x >= L && x <= H) {          // NaN fails both; +-inf never inside a finite [L, H]
-      HistT* h = hist + bin_of(x, L, scale) * 32 + lane;
-      *h = (HistT)(*h + 1);
-    }
-  }
-  __syncwarp();
-  c0 = hist_row_sum<HistT>(hist + lane * 32);
-  c1 = hist_row_sum<HistT>(hist + (lane + 32) * 32);
-  unsigned i0 = c0, i1 = c1;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const unsigned t0 = __shfl_up_sync(0xffffffffu, i0, o), t1 = __shfl_up_sync(0xffffffffu, i1, o);
-    if (lane >= o) { i0 += t0; i1 += t1; }
-  }
-  const unsigned tot0 = __shfl_sync(0xffffffffu, i0, 31);
-  e0 = i0 - c0;
-  e1 = tot0 + i1 - c1;
-  __syncwarp();
-}
-
-// bin holding 0-based rank r (relative to the histogram) + its exclusive prefix and count
-__device__ __forceinline__ void locate_rank(unsigned r, unsigned c0, unsigned c1, unsigned e0,
-                                            unsigned e1, int& bin, unsigned& excl, unsigned& cnt) {
-  const unsigned m0 = __ballot_sync(0xffffffffu, c0 > 0 && r >= e0 && r < e0 + c0);
-  const unsigned m1 = __ballot_sync(0xffffffffu, c1 > 0 && r >= e1 && r < e1 + c1);
-  if (m0) {
-    const int l = __ffs(m0) - 1;
-    bin = l;
-    excl = __shfl_sync(0xffffffffu, e0, l);
-    cnt = __shfl_sync(0xffffffffu, c0, l);
-  } else {
-    const int l = m1 ? __ffs(m1) - 1 : 31;
-    bin = 32 + l;
-    excl = __shfl_sync(0xffffffffu, e1, l);
-    cnt = __shfl_sync(0xffffffffu, c1, l);
-  }
-}
-
-// gather the members of [L,H] whose bin is `b` into cand[] (cnt <= CAP) and sort them ascending
-__device__ __forceinline__ void gather_sort(const float* __restrict__ v, int N, float L, float H,
-                                            float scale, int b, unsigned cnt, float* cand) {
-  const int lane = threadIdx.x & 31;
-  unsigned filled = 0;
-  for (int s0 = 0; s0 < N; s0 += 32) {
-    const int s = s0 + lane;
-    const float x = s < N ? v[s] : 0.0f;
-    const bool hit = s < N && x >= L && x <= H && bin_of(x, L, scale) == b;
-    const unsigned m = __ballot_sync(0xffffffffu, hit);
-    if (hit) cand[filled + __popc(m & ((1u << lane) - 1u))] = x;
-    filled += __popc(m);
-  }
-  unsigned M = 32;
-  while (M < cnt) M <<= 1;
-  for (unsigned i = cnt + lane; i < M; i += 32) cand[i] = __int_as_float(0x7f800000);   // +inf pad
-  __syncwarp();
-  for (unsigned k = 2; k <= M; k <<= 1) {
-    for (unsigned j = k >> 1; j > 0; j >>= 1) {
-      for (unsigned i = lane; i < M; i += 32) {
-        const unsigned ixj = i ^ j;
-        if (ixj > i) {
-          const float a = cand[i], c = cand[ixj];
-          const bool up = (i & k) == 0;
-          if ((a > c) == up) { cand[i] = c; cand[ixj] = a; }
-        }
-      }
-      __syncwarp();
-    }
-  }
-}
-
-// min / max of the members of [L,H] falling in bin b
-__device__ __forceinline__ void bin_minmax(const float* __restrict__ v, int N, float L, float H,
-                                           float scale, int b, float& mn, float& mx) {
-  const int lane = threadIdx.x & 31;
-  mn = __int_as_float(0x7f800000);
-  mx = __int_as_float(0xff800000);
-  for (int s = lane; s < N; s += 32) {
-    const float x = v[s];
-    if (x >= L && x <= H && bin_of(x, L, scale) == b) { mn = fminf(mn, x); mx = fmaxf(mx, x); }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  }
-}
-
-// generic exact order statistic: rank r (0-based among the finite values) by repeated narrowing
-template <typename HistT>
-__device__ float select_one(const float* __restrict__ v, int N, unsigned r, float L, float H,
-                            HistT* hist, float* cand) {
-  unsigned base = 0;
-  for (;;) {
-    if (!(H > L)) return L;
-    const float scale = (float)HB / (H - L);
-    unsigned c0, c1, e0, e1, excl, cnt;
-    int b;
-    warp_histogram<HistT>(v, N, L, H, scale, hist, c0, c1, e0, e1);
-    locate_rank(r - base, c0, c1, e0, e1, b, excl, cnt);
-    if (cnt <= (unsigned)CAP) {
-      gather_sort(v, N, L, H, scale, b, cnt, cand);
-      const float out = cand[r - base - excl];
-      __syncwarp();
-      return out;
-    }
-    float mn, mx;
-    bin_minmax(v, N, L, H, scale, b, mn, mx);
-    base += excl;
-    L = mn;
-    H = mx;
-  }
-}
-
-// numpy.lib._function_base_impl._lerp in float64 on the float32 order statistics
-__device__ __forceinline__ float np_lerp_f(float a, float b, double t) {
-  const double da = a, db = b, d = db - da;
-  return (float)((t >= 0.5) ? (db - d * (1.0 - t)) : (da + d * t));
-}
-
-// percentile extraction for one stored column (mcz.py:273-301); all 32 lanes participate
-template <typename HistT>
-__device__ void warp_percentiles(const float* __restrict__ v, int N, HistT* hist, float* cand,
-                                 float pct[3], int& nvalid, int& status) {
-  const int lane = threadIdx.x & 31;
-  int cnt = 0;
-  float sum = 0.0f, mn = __int_as_float(0x7f800000), mx = __int_as_float(0xff800000);
-  for (int s = lane; s < N; s += 32) {
-    const float x = v[s];
-    if (finite_f(x)) { ++cnt; sum += x; mn = fminf(mn, x); mx = fmaxf(mx, x); }   // mcz.py:273
-  }
-  const int n = __reduce_add_sync(0xffffffffu, cnt);
-  const double total = warp_sum((double)sum);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  }
-  const float nanf_ = Math<float>::nan();
-  pct[0] = pct[1] = pct[2] = nanf_;
-  nvalid = n;
-  if (n == 0) { status = ST_EMPTY; return; }                                      // mcz.py:277-280
-  if (!(total > 0.0)) { status = ST_NONPOS; return; }                             // mcz.py:282-285
-  status = ST_OK;
-  const double qs[3] = {50.0 / 100.0, 16.0 / 100.0, 84.0 / 100.0};                // mcz.py:288
-  unsigned rk[6];
-  double gam[3];
-#pragma unroll
-  for (int q = 0; q < 3; ++q) {
-    const double vi = (double)(n - 1) * qs[q];
-    const double lo = floor(vi);
-    gam[q] = vi - lo;
-    rk[2 * q] = (unsigned)lo;
-    rk[2 * q + 1] = min((unsigned)lo + 1u, (unsigned)(n - 1));
-  }
-  float res[6];
-  if (!(mx > mn)) {
-#pragma unroll
-    for (int i = 0; i < 6; ++i) res[i] = mn;
-  } else {
-    // level-1 histogram shared by all six ranks
-    const float scale = (float)HB / (mx - mn);
-    unsigned c0, c1, e0, e1;
-    warp_histogram<HistT>(v, N, mn, mx, scale, hist, c0, c1, e0, e1);
-    int bins[6];
-    unsigned excl[6], cnts[6];
-    bool fast = true;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      locate_rank(rk[i], c0, c1, e0, e1, bins[i], excl[i], cnts[i]);
-      fast = fast && cnts[i] <= (unsigned)CAP;
-    }
-    if (fast) {
-      unsigned done = 0;
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        if (done & (1u << i)) continue;
-        gather_sort(v, N, mn, mx, scale, bins[i], cnts[i], cand);
-#pragma unroll
-        for (int j = i; j < 6; ++j)
-          if (!(done & (1u << j)) && bins[j] == bins[i]) { res[j] = cand[rk[j] - excl[j]]; done |= 1u << j; }
-        __syncwarp();
-      }
-    } else {
-#pragma unroll 1
-      for (int i = 0; i < 6; ++i) {
-        if (i > 0 && rk[i] == rk[i - 1]) { res[i] = res[i - 1]; continue; }
-        res[i] = select_one<HistT>(v, N, rk[i], mn, mx, hist, cand);
-      }
-    }
-  }
-#pragma unroll
-  for (int q = 0; q < 3; ++q) pct[q] = np_lerp_f(res[2 * q], res[2 * q + 1], gam[q]);
-  (void)lane;
-}
+}  // namespace mcz
+#include "mcz_select.cuh"   // needs PT / PW / HB / CAP from above
+namespace mcz {
 
 // ---- the kernel -------------------------------------------------------------------------------
 // SLOTS > 0: at most SLOTS samples per thread, loop state in registers, columns in shared memory.
@@ -350,7 +136,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
   float* cand = reinterpret_cast<float*>(work + (size_t)PW * HB * 32 * sizeof(HistT)) + warp * CAP;
 
   const int used2line[NUSED] = {L_HA, L_HB, L_O2, L_O3, L_N2, L_S2A, L_S2B, L_S39069};
-  const int nsl = (N + PT - 1) / PT;
+  const int nsl = (Npad + PT - 1) / PT;     // Npad is a multiple of 128; [N, Npad) is NaN-filled
   int phase = 0;
 
   for (;;) {
@@ -412,6 +198,8 @@ production_kernel(const __grid_constant__ ProdParams p) {
           stash[Npad + s] = c.n2ha;
           stash[2 * Npad + s] = c.x;
           stash[3 * Npad + s] = __uint_as_float(c.aux);
+        } else if (s < Npad) {
+          for (int sl = 0; sl < p.nstore; ++sl) vals[(long long)sl * Npad + s] = Math<float>::nan();
         }
       }
       seen = __reduce_or_sync(0xffffffffu, seen);
@@ -432,6 +220,8 @@ production_kernel(const __grid_constant__ ProdParams p) {
       const bool o3o2 = (flags & F_O2) && (flags & F_O3);
       const int sl_kd = p.slot_of_key[K_KD02_N2O2], sl_m91 = p.slot_of_key[K_M91];
       bool act1 = has_kn && o3o2, act2 = has_kr;
+      // mean > tol  <=>  sum > tol * N  (NaN sum compares false: the loop stops, as in numpy)
+      const float tol1 = 1.0e-3f * (float)N, tol2 = 1.0e-4f * (float)N;
       if constexpr (!GLOBAL) {
         IterState<float> st[SLOTS];
         bool any = false;
@@ -465,16 +255,9 @@ production_kernel(const __grid_constant__ ProdParams p) {
               if (act2) s2 += kk04_r23_trip<float>(st[i]);
             }
           }
-          double d1 = (double)warp_sum(s1), d2 = (double)warp_sum(s2);
-          double* b = ctrl->red + phase * 2 * PW;
-          if (lane == 0) { b[2 * warp] = d1; b[2 * warp + 1] = d2; }
-          __syncthreads();
-          d1 = 0.0; d2 = 0.0;
-#pragma unroll
-          for (int w = 0; w < PW; ++w) { d1 += b[2 * w]; d2 += b[2 * w + 1]; }
-          phase ^= 1;
-          if (act1) { ++ii1; act1 = (d1 / (double)N > 1.0e-3) && ii1 < 100; }          // metscales.py:1111,1117
-          if (act2) { ++ii2; act2 = (fabs(d2 / (double)N) > 1e-4) && ii2 < 100; }      // metscales.py:1166,1177
+          block_sum2f(s1, s2, ctrl->redf, phase);
+          if (act1) { ++ii1; act1 = (s1 > tol1) && ii1 < 100; }            // metscales.py:1111,1117
+          if (act2) { ++ii2; act2 = (fabsf(s2) > tol2) && ii2 < 100; }     // metscales.py:1166,1177
         }
 #pragma unroll
         for (int i = 0; i < SLOTS; ++i) {
@@ -533,16 +316,9 @@ production_kernel(const __grid_constant__ ProdParams p) {
               F[11ll * Npad + s] = st.Z2; F[13ll * Npad + s] = st.lq2;
             }
           }
-          double d1 = (double)warp_sum(s1), d2 = (double)warp_sum(s2);
-          double* b = ctrl->red + phase * 2 * PW;
-          if (lane == 0) { b[2 * warp] = d1; b[2 * warp + 1] = d2; }
-          __syncthreads();
-          d1 = 0.0; d2 = 0.0;
-#pragma unroll
-          for (int w = 0; w < PW; ++w) { d1 += b[2 * w]; d2 += b[2 * w + 1]; }
-          phase ^= 1;
-          if (act1) { ++ii1; act1 = (d1 / (double)N > 1.0e-3) && ii1 < 100; }
-          if (act2) { ++ii2; act2 = (fabs(d2 / (double)N) > 1e-4) && ii2 < 100; }
+          block_sum2f(s1, s2, ctrl->redf, phase);
+          if (act1) { ++ii1; act1 = (s1 > tol1) && ii1 < 100; }            // metscales.py:1111,1117
+          if (act2) { ++ii2; act2 = (fabsf(s2) > tol2) && ii2 < 100; }     // metscales.py:1166,1177
         }
         for (int s = tid; s < N; s += PT) {
           IterState<float> st;
@@ -590,7 +366,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
       if (!((pm >> k) & 1ull)) continue;
       float pc[3];
       int nv, stt;
-      warp_percentiles<HistT>(vals + (long long)sl * Npad, N, hist, cand, pc, nv, stt);
+      warp_percentiles<HistT>(vals + (long long)sl * Npad, N, Npad, hist, cand, pc, nv, stt);
       if (lane == 0) {
         const long long o = g * NKEYS + k;
         p.status[o] = (signed char)stt;
@@ -654,7 +430,7 @@ static int num_sms() {
 
 static ProdPlan make_plan(long long G, long long N, int nstore) {
   ProdPlan pl;
-  pl.Npad = (int)((N + 31) / 32 * 32);
+  pl.Npad = (int)((N + 127) / 128 * 128);
   const size_t cols = (size_t)nstore * pl.Npad * sizeof(float);
   const size_t stash = 4ull * pl.Npad * sizeof(float);
   const size_t sel8 = (size_t)PW * (HB * 32 * sizeof(unsigned char) + CAP * sizeof(float));
