@@ -103,6 +103,11 @@ int mcz_forward_production(const float* meas_d, const float* err_d, long long G,
                            scratch_bytes, (cudaStream_t)stream);
 }
 
+// diagnostics (not part of the public header): selection-path counters since the last reset:
+// [0] columns, [1] fast path, [2] fallback: degenerate range, [3] fallback: target in an edge bin
+// or > 4 target bins, [4] fallback: > 64 candidates (ties), [5] empty / non-positive columns
+int mcz_debug_counters(unsigned long long* out8, int reset) { return read_sel_counters(out8, reset); }
+
 mcz_ctx* mcz_ctx_create(int device) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) {

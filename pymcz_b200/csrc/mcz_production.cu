@@ -132,8 +132,9 @@ production_kernel(const __grid_constant__ ProdParams p) {
     work = smem + CTRL_BYTES + (size_t)p.nstore * Npad * sizeof(float);
     stash = reinterpret_cast<float*>(work);
   }
-  HistT* hist = reinterpret_cast<HistT*>(work) + (size_t)warp * HB * 32;
-  float* cand = reinterpret_cast<float*>(work + (size_t)PW * HB * 32 * sizeof(HistT)) + warp * CAP;
+  constexpr size_t HIST_BYTES = (size_t)PrivHist<HistT>::ROWS * 128;     // >= HB*32*sizeof(HistT)
+  HistT* hist = reinterpret_cast<HistT*>(work + (size_t)warp * HIST_BYTES);
+  float* cand = reinterpret_cast<float*>(work + (size_t)PW * HIST_BYTES) + warp * CAP;
 
   const int used2line[NUSED] = {L_HA, L_HB, L_O2, L_O3, L_N2, L_S2A, L_S2B, L_S39069};
   const int nsl = (Npad + PT - 1) / PT;     // Npad is a multiple of 128; [N, Npad) is NaN-filled
@@ -433,8 +434,8 @@ static ProdPlan make_plan(long long G, long long N, int nstore) {
   pl.Npad = (int)((N + 127) / 128 * 128);
   const size_t cols = (size_t)nstore * pl.Npad * sizeof(float);
   const size_t stash = 4ull * pl.Npad * sizeof(float);
-  const size_t sel8 = (size_t)PW * (HB * 32 * sizeof(unsigned char) + CAP * sizeof(float));
-  const size_t sel16 = (size_t)PW * (HB * 32 * sizeof(unsigned short) + CAP * sizeof(float));
+  const size_t sel8 = (size_t)PW * (PrivHist<unsigned char>::ROWS * 128 + CAP * sizeof(float));
+  const size_t sel16 = (size_t)PW * (PrivHist<unsigned short>::ROWS * 128 + CAP * sizeof(float));
   const size_t smem_local = CTRL_BYTES + cols + (stash > sel8 ? stash : sel8);
   pl.global = !(N <= 4ll * PT && smem_local <= 227ull * 1024);
   pl.smem = pl.global ? CTRL_BYTES + sel16 : smem_local;
@@ -442,6 +443,16 @@ static ProdPlan make_plan(long long G, long long N, int nstore) {
   const long long sms = num_sms();
   pl.grid = (int)(G < sms ? (G > 0 ? G : 1) : sms);
   return pl;
+}
+
+int read_sel_counters(unsigned long long* out8, int reset) {
+  int rc = check_cuda(cudaMemcpyFromSymbol(out8, g_sel_counters, 8 * sizeof(unsigned long long)), "read counters");
+  if (rc) return rc;
+  if (reset) {
+    unsigned long long z[8] = {0};
+    rc = check_cuda(cudaMemcpyToSymbol(g_sel_counters, z, sizeof(z)), "reset counters");
+  }
+  return rc;
 }
 
 size_t production_scratch_bytes(long long G, long long n_draw, uint32_t tok) {
