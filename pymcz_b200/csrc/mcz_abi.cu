@@ -108,6 +108,9 @@ int mcz_forward_production(const float* meas_d, const float* err_d, long long G,
 // or > 4 target bins, [4] fallback: > 64 candidates (ties), [5] empty / non-positive columns
 int mcz_debug_counters(unsigned long long* out8, int reset) { return read_sel_counters(out8, reset); }
 
+int mcz_debug_col_cycles(unsigned long long* out74, int reset) { return read_col_cycles(out74, reset); }
+int mcz_debug_phase_cycles(unsigned long long* out8, int reset) { return read_phase_cycles(out8, reset); }
+
 mcz_ctx* mcz_ctx_create(int device) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) {

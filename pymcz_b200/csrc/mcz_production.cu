@@ -105,6 +105,19 @@ struct SlotPut {
 #include "mcz_select.cuh"   // needs PT / PW / HB / CAP from above
 namespace mcz {
 
+// optional phase timing (build with -DMCZ_PHASE_TIMING): cycles summed over blocks, read back with
+// mcz_debug_phase_cycles: [0] galaxies, [1] phase A, [2] phases B+C, [3] phase D own work (mean
+// over the 18 warps), [4] phase D wall (start of D to the block barrier), [5] other
+__device__ unsigned long long g_phase_cycles[8];
+__device__ unsigned long long g_col_cycles[2 * NKEYS];   // per key: cycles, max-cycles accumulators
+#ifdef MCZ_PHASE_TIMING
+#define MCZ_T(var) const long long var = clock64()
+#define MCZ_TADD(idx, val) do { if (tid == 0) atomicAdd(&g_phase_cycles[idx], (unsigned long long)(val)); } while (0)
+#else
+#define MCZ_T(var)
+#define MCZ_TADD(idx, val)
+#endif
+
 // ---- the kernel -------------------------------------------------------------------------------
 // SLOTS > 0: at most SLOTS samples per thread, loop state in registers, columns in shared memory.
 // SLOTS == 0: any N', columns / stash / loop state in the per-block global scratch.
@@ -164,6 +177,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
     }
     const unsigned long long gg = p.goff + (unsigned long long)g;
 
+    MCZ_T(tA0);
     // ---- phase A (repeated once in the rare case the assumed flags were wrong) ----------------
     uint32_t flags = assumed;
     for (;;) {
@@ -213,6 +227,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
     const uint64_t pm = present_mask(flags, p.tok);
     const bool ok = minimum_ok(flags);
 
+    MCZ_T(tB0);
     // ---- phases B and C ----------------------------------------------------------------------
     int ii1 = 0, ii2 = 0;
     if ((p.tok & T_KD02) && ok) {
@@ -336,6 +351,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
     }
     __syncthreads();     // all columns final; the stash is dead from here (selection reuses it)
 
+    MCZ_T(tD0);
     // ---- optional per-sample output (pickle / --asciidistrib path) ----------------------------
     if (p.Z) {
       for (int k = 0; k < NKEYS; ++k) {
@@ -367,7 +383,17 @@ production_kernel(const __grid_constant__ ProdParams p) {
       if (!((pm >> k) & 1ull)) continue;
       float pc[3];
       int nv, stt;
+#ifdef MCZ_PHASE_TIMING
+      const long long tc0 = clock64();
+#endif
       warp_percentiles<HistT>(vals + (long long)sl * Npad, N, Npad, hist, cand, pc, nv, stt);
+#ifdef MCZ_PHASE_TIMING
+      if (lane == 0) {
+        const unsigned long long dt = (unsigned long long)(clock64() - tc0);
+        atomicAdd(&g_col_cycles[k], dt);
+        atomicMax(&g_col_cycles[NKEYS + k], dt);
+      }
+#endif
       if (lane == 0) {
         const long long o = g * NKEYS + k;
         p.status[o] = (signed char)stt;
@@ -377,6 +403,18 @@ production_kernel(const __grid_constant__ ProdParams p) {
         p.pct[3 * o + 2] = pc[2];
       }
     }
+#ifdef MCZ_PHASE_TIMING
+    {
+      const long long tD1 = clock64();
+      if (lane == 0) atomicAdd(&g_phase_cycles[3], (unsigned long long)((tD1 - tD0) / PW));
+      __syncthreads();
+      const long long tD2 = clock64();
+      MCZ_TADD(0, 1);
+      MCZ_TADD(1, tB0 - tA0);
+      MCZ_TADD(2, tD0 - tB0);
+      MCZ_TADD(4, tD2 - tD0);
+    }
+#endif
   }
 }
 
@@ -443,6 +481,26 @@ static ProdPlan make_plan(long long G, long long N, int nstore) {
   const long long sms = num_sms();
   pl.grid = (int)(G < sms ? (G > 0 ? G : 1) : sms);
   return pl;
+}
+
+int read_col_cycles(unsigned long long* out, int reset) {
+  int rc = check_cuda(cudaMemcpyFromSymbol(out, g_col_cycles, 2 * NKEYS * sizeof(unsigned long long)), "read col cycles");
+  if (rc) return rc;
+  if (reset) {
+    unsigned long long z[2 * NKEYS] = {0};
+    rc = check_cuda(cudaMemcpyToSymbol(g_col_cycles, z, sizeof(z)), "reset col cycles");
+  }
+  return rc;
+}
+
+int read_phase_cycles(unsigned long long* out8, int reset) {
+  int rc = check_cuda(cudaMemcpyFromSymbol(out8, g_phase_cycles, 8 * sizeof(unsigned long long)), "read cycles");
+  if (rc) return rc;
+  if (reset) {
+    unsigned long long z[8] = {0};
+    rc = check_cuda(cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z)), "reset cycles");
+  }
+  return rc;
 }
 
 int read_sel_counters(unsigned long long* out8, int reset) {

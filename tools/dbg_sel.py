@@ -10,7 +10,7 @@ L.mcz_debug_counters(out,1)
 pct,nv,st,tr,ret,Z=ops.forward_production(m,e,2200,sc.T_ALL)
 torch.cuda.synchronize()
 L.mcz_debug_counters(out,1)
-print('counters',list(out))
+print('counters [total, fast, no_subsample, general, crowded, trivial, narrow_rounds]',list(out))
 st=st.cpu().numpy(); nv=nv.cpu().numpy()
 # per key: fraction of galaxies with status ok & nvalid
 for j,k in enumerate(sc.KEYS):
