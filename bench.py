@@ -298,7 +298,7 @@ def run_ours(args):
             "achieved": per_gpu_gs * w_alu / 1e12, "peak": peak_alu / 1e12, "unit": "Tlane-op/s",
             "frac": per_gpu_gs * w_alu / peak_alu,
             "traffic": None,
-            "kernel": "production_kernel<4,uchar>", "kernel_ms": k_ms, "mean_trips": mean_trips,
+            "kernel": "production_kernel<4>", "kernel_ms": k_ms, "mean_trips": mean_trips,
             "w_alu_per_gs": w_alu, "w_sfu_per_gs": w_sfu, "sfu_frac": per_gpu_gs * w_sfu / peak_sfu,
             "sm_mhz_used": f_mhz, "sms": sms,
             "hbm": {"algorithmic_bytes_per_launch": bytes_per_galaxy * G,

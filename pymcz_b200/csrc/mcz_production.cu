@@ -21,8 +21,7 @@ namespace mcz {
 
 static constexpr int PT = 576;            // threads per block: 18 warps
 static constexpr int PW = PT / 32;
-static constexpr int HB = 64;             // histogram bins per selection level
-static constexpr int CAP = 256;           // candidates sorted per target bin
+static constexpr int CAND_FLOATS = 128;   // per-warp candidate area (counter + 64-entry list)
 static constexpr int CTRL_BYTES = 1024;
 
 struct ProdParams {
@@ -102,7 +101,7 @@ struct SlotPut {
 };
 
 }  // namespace mcz
-#include "mcz_select.cuh"   // needs PT / PW / HB / CAP from above
+#include "mcz_select.cuh"
 namespace mcz {
 
 // optional phase timing (build with -DMCZ_PHASE_TIMING): cycles summed over blocks, read back with
@@ -121,7 +120,7 @@ __device__ unsigned long long g_col_cycles[2 * NKEYS];   // per key: cycles, max
 // ---- the kernel -------------------------------------------------------------------------------
 // SLOTS > 0: at most SLOTS samples per thread, loop state in registers, columns in shared memory.
 // SLOTS == 0: any N', columns / stash / loop state in the per-block global scratch.
-template <int SLOTS, typename HistT>
+template <int SLOTS>
 __global__ void __launch_bounds__(PT, 1)
 production_kernel(const __grid_constant__ ProdParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -145,9 +144,10 @@ production_kernel(const __grid_constant__ ProdParams p) {
     work = smem + CTRL_BYTES + (size_t)p.nstore * Npad * sizeof(float);
     stash = reinterpret_cast<float*>(work);
   }
-  constexpr size_t HIST_BYTES = (size_t)PrivHist<HistT>::ROWS * 128;     // >= HB*32*sizeof(HistT)
-  HistT* hist = reinterpret_cast<HistT*>(work + (size_t)warp * HIST_BYTES);
-  float* cand = reinterpret_cast<float*>(work + (size_t)PW * HIST_BYTES) + warp * CAP;
+  constexpr bool PACK16 = !GLOBAL;        // shared-memory variant: columns of < 65536 samples
+  constexpr size_t HIST_BYTES = FineHist<PACK16>::BYTES;
+  unsigned* hist = reinterpret_cast<unsigned*>(work + (size_t)warp * HIST_BYTES);
+  float* cand = reinterpret_cast<float*>(work + (size_t)PW * HIST_BYTES) + warp * CAND_FLOATS;
 
   const int used2line[NUSED] = {L_HA, L_HB, L_O2, L_O3, L_N2, L_S2A, L_S2B, L_S39069};
   const int nsl = (Npad + PT - 1) / PT;     // Npad is a multiple of 128; [N, Npad) is NaN-filled
@@ -386,7 +386,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
 #ifdef MCZ_PHASE_TIMING
       const long long tc0 = clock64();
 #endif
-      warp_percentiles<HistT>(vals + (long long)sl * Npad, N, Npad, hist, cand, pc, nv, stt);
+      warp_percentiles<PACK16>(vals + (long long)sl * Npad, Npad, hist, cand, pc, nv, stt);
 #ifdef MCZ_PHASE_TIMING
       if (lane == 0) {
         const unsigned long long dt = (unsigned long long)(clock64() - tc0);
@@ -472,8 +472,8 @@ static ProdPlan make_plan(long long G, long long N, int nstore) {
   pl.Npad = (int)((N + 127) / 128 * 128);
   const size_t cols = (size_t)nstore * pl.Npad * sizeof(float);
   const size_t stash = 4ull * pl.Npad * sizeof(float);
-  const size_t sel8 = (size_t)PW * (PrivHist<unsigned char>::ROWS * 128 + CAP * sizeof(float));
-  const size_t sel16 = (size_t)PW * (PrivHist<unsigned short>::ROWS * 128 + CAP * sizeof(float));
+  const size_t sel8 = (size_t)PW * (FineHist<true>::BYTES + CAND_FLOATS * sizeof(float));
+  const size_t sel16 = (size_t)PW * (FineHist<false>::BYTES + CAND_FLOATS * sizeof(float));
   const size_t smem_local = CTRL_BYTES + cols + (stash > sel8 ? stash : sel8);
   pl.global = !(N <= 4ll * PT && smem_local <= 227ull * 1024);
   pl.smem = pl.global ? CTRL_BYTES + sel16 : smem_local;
@@ -546,23 +546,23 @@ int launch_production(const float* meas, const float* err, long long G, long lon
   if (!pl.global) {
     static bool attr_done = false;
     if (!attr_done) {
-      rc = check_cuda(cudaFuncSetAttribute(production_kernel<4, unsigned char>,
+      rc = check_cuda(cudaFuncSetAttribute(production_kernel<4>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
                       "smem attribute");
       if (rc) return rc;
       attr_done = true;
     }
-    production_kernel<4, unsigned char><<<pl.grid, PT, pl.smem, stream>>>(p);
+    production_kernel<4><<<pl.grid, PT, pl.smem, stream>>>(p);
   } else {
     static bool attr_done = false;
     if (!attr_done) {
-      rc = check_cuda(cudaFuncSetAttribute(production_kernel<0, unsigned short>,
+      rc = check_cuda(cudaFuncSetAttribute(production_kernel<0>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
                       "smem attribute");
       if (rc) return rc;
       attr_done = true;
     }
-    production_kernel<0, unsigned short><<<pl.grid, PT, pl.smem, stream>>>(p);
+    production_kernel<0><<<pl.grid, PT, pl.smem, stream>>>(p);
   }
   count_launch();
   return check_cuda(cudaGetLastError(), "production_kernel launch");
