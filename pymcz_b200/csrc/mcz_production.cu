@@ -55,6 +55,7 @@ struct Ctrl {
   int any_valid_kd;
   float line[2 * NLINES];
   float2 redf[2 * PW];
+  int acc[3][2];           // fixed-point block sums of the two KK04 convergence measures
 };
 static_assert(sizeof(Ctrl) <= CTRL_BYTES, "control block too large");
 
@@ -88,6 +89,34 @@ __device__ __forceinline__ void block_sum2f(float& a, float& c, float2* buf, int
   a = warp_sum(pr.x);
   c = warp_sum(pr.y);
   phase ^= 1;
+}
+
+// Block-wide sums of the two convergence measures in 16.16 fixed point: one REDUX per warp, one
+// shared atomic per warp, and a single barrier that also ORs the NaN flags (BAR.RED.OR).
+// Per-sample terms are clamped to +-8 by the caller, which cannot change the outcome of
+// "mean > tol" (tol * N < 8) and keeps the total within int32 for N <= 2304 * ... (N * 8 * 2^16 < 2^31).
+__device__ __forceinline__ void block_sum2_fx(float s1, float s2, bool nan, Ctrl* ctrl, int& ph,
+                                              int& t1, int& t2, bool& anynan) {
+  const int lane = threadIdx.x & 31;
+  int q1 = __reduce_add_sync(0xffffffffu, __float2int_rn(s1 * 65536.0f));
+  int q2 = __reduce_add_sync(0xffffffffu, __float2int_rn(s2 * 65536.0f));
+  if (lane == 0) {
+    atomicAdd(&ctrl->acc[ph][0], q1);
+    atomicAdd(&ctrl->acc[ph][1], q2);
+  }
+  const int nx = ph == 2 ? 0 : ph + 1;
+  if (threadIdx.x == 0) { ctrl->acc[nx][0] = 0; ctrl->acc[nx][1] = 0; }
+  anynan = __syncthreads_or(nan);
+  t1 = ctrl->acc[ph][0];
+  t2 = ctrl->acc[ph][1];
+  ph = nx;
+}
+
+// MUFU.RCP without the range checks of __fdividef (the KK04 denominators are O(1))
+__device__ __forceinline__ float fast_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
 }
 
 struct SlotPut {
@@ -161,7 +190,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
     if (g >= p.G) break;
     if (tid < NLINES) ctrl->line[tid] = p.meas[g * NLINES + tid];
     else if (tid < 2 * NLINES) ctrl->line[tid] = p.err[g * NLINES + (tid - NLINES)];
-    if (tid == 0) ctrl->flags = 0u;
+    if (tid == 0) { ctrl->flags = 0u; ctrl->acc[0][0] = 0; ctrl->acc[0][1] = 0; }
     __syncthreads();
     float lm[NUSED], le[NUSED];
     uint32_t assumed = 0u;
@@ -239,41 +268,84 @@ production_kernel(const __grid_constant__ ProdParams p) {
       // mean > tol  <=>  sum > tol * N  (NaN sum compares false: the loop stops, as in numpy)
       const float tol1 = 1.0e-3f * (float)N, tol2 = 1.0e-4f * (float)N;
       if constexpr (!GLOBAL) {
-        IterState<float> st[SLOTS];
+        // Loop state: 11 registers per sample; the four R23 branch constants of each sample live
+        // in shared memory, in the space of the (now dead) stash.  Slots without a sample get
+        // constants that make every trip contribute exactly 0.
+        float num0[SLOTS], num1[SLOTS], den0[SLOTS], den1[SLOTS], cA[SLOTS], cB[SLOTS];
+        float Z1[SLOTS], lq1[SLOTS], Z2[SLOTS], lq2[SLOTS];
+        uint32_t aux[SLOTS];
+        float* const cst = stash;            // U0, U1, L0, L1 : [4][Npad]
         bool any = false;
 #pragma unroll
         for (int i = 0; i < SLOTS; ++i) {
           const int s = i * PT + tid;
+          num0[i] = 0.0f; num1[i] = 0.0f; den0[i] = 1.0f; den1[i] = 0.0f; cA[i] = 0.0f; cB[i] = 0.0f;
+          Z1[i] = 0.0f; lq1[i] = 0.0f; Z2[i] = 0.0f; lq2[i] = 0.0f; aux[i] = 2u;
           if (s < N) {
             Carry<float> c;
             c.y = stash[s]; c.n2ha = stash[Npad + s]; c.x = stash[2 * Npad + s];
             c.aux = __float_as_uint(stash[3 * Npad + s]);
             const float kd = has_kd ? vals[sl_kd * Npad + s] : Math<float>::nan();
-            make_iter<float>(c, kd, st[i]);
+            IterState<float> st;
+            make_iter<float>(c, kd, st);
             any = any || !Math<float>::isnan(kd);
+            num0[i] = st.num0; num1[i] = st.num1; den0[i] = st.den0; den1[i] = st.den1;
+            cA[i] = st.A; cB[i] = st.B; Z1[i] = st.Z1; lq1[i] = st.lq1; Z2[i] = st.Z2; lq2[i] = st.lq2;
+            aux[i] = st.aux;
+            cst[s] = st.U0; cst[Npad + s] = st.U1; cst[2 * Npad + s] = st.L0; cst[3 * Npad + s] = st.L1;
+          } else if (s < Npad) {
+            cst[s] = 0.0f; cst[Npad + s] = 0.0f; cst[2 * Npad + s] = 0.0f; cst[3 * Npad + s] = 0.0f;
           }
         }
         // start of the N2Ha loop: 8.6 if KD02_N2O2 is None or all-NaN (metscales.py:1097-1103)
         if (!__syncthreads_or(any)) {
 #pragma unroll
-          for (int i = 0; i < SLOTS; ++i) st[i].Z1 = 8.6f;
+          for (int i = 0; i < SLOTS; ++i) if (i * PT + tid < N) Z1[i] = 8.6f;
         }
-        if (has_kn && !o3o2) {
+        if (has_kn && !o3o2) {                                          // metscales.py:1122-1126
 #pragma unroll
-          for (int i = 0; i < SLOTS; ++i) st[i].Z1 = kk04_n2ha_noq<float>(st[i]);
+          for (int i = 0; i < SLOTS; ++i) Z1[i] = cA[i] - 7.37177f * cB[i];
         }
+        const int itol1 = (int)(tol1 * 65536.0f), itol2 = (int)(tol2 * 65536.0f);
+        int ph = 0;
         while (act1 || act2) {
           float s1 = 0.0f, s2 = 0.0f;
+          bool nan1 = false, nan2 = false;
+          if (act1) {
 #pragma unroll
-          for (int i = 0; i < SLOTS; ++i) {
-            if (i * PT + tid < N) {
-              if (act1) s1 += kk04_n2ha_trip<float>(st[i]);
-              if (act2) s2 += kk04_r23_trip<float>(st[i]);
+            for (int i = 0; i < SLOTS; ++i) {                            // metscales.py:1112-1118
+              const float lq = (num0[i] + Z1[i] * num1[i]) * fast_rcp(den0[i] + Z1[i] * den1[i]);
+              Z1[i] = cA[i] - lq * cB[i];
+              const float d = fabsf(lq - lq1[i]);
+              lq1[i] = lq;
+              nan1 = nan1 || (d != d);
+              s1 += fminf(d, 8.0f);
             }
           }
-          block_sum2f(s1, s2, ctrl->redf, phase);
-          if (act1) { ++ii1; act1 = (s1 > tol1) && ii1 < 100; }            // metscales.py:1111,1117
-          if (act2) { ++ii2; act2 = (fabsf(s2) > tol2) && ii2 < 100; }     // metscales.py:1166,1177
+          if (act2) {
+#pragma unroll
+            for (int i = 0; i < SLOTS; ++i) {                            // metscales.py:1167-1178
+              const float lq = (num0[i] + Z2[i] * num1[i]) * fast_rcp(den0[i] + Z2[i] * den1[i]);
+              const bool lower = ((aux[i] & AUX_ZI_MASK) <= 1u) && (lq >= 6.7f) && (lq < 8.3f);
+              const int sidx = min(i * PT + tid, Npad - 1);
+              const float* cc = cst + (lower ? 2 * Npad : 0) + sidx;
+              Z2[i] = (i * PT + tid < N) ? (cc[0] - lq * cc[Npad]) : 0.0f;
+              const float d = lq2[i] - lq;
+              lq2[i] = lq;
+              nan2 = nan2 || (d != d);
+              s2 += fminf(fmaxf(d, -8.0f), 8.0f);
+            }
+          }
+          int t1, t2;
+          bool anynan;
+          block_sum2_fx(s1, s2, nan1 || nan2, ctrl, ph, t1, t2, anynan);
+          bool n1 = false, n2 = false;
+          if (anynan) {      // rare: find out which loop saw the NaN (a NaN mean stops that loop)
+            n1 = __syncthreads_or(nan1);
+            n2 = __syncthreads_or(nan2);
+          }
+          if (act1) { ++ii1; act1 = !n1 && (t1 > itol1) && ii1 < 100; }                 // metscales.py:1111,1117
+          if (act2) { ++ii2; act2 = !n2 && ((t2 < 0 ? -t2 : t2) > itol2) && ii2 < 100; } // metscales.py:1166,1177
         }
 #pragma unroll
         for (int i = 0; i < SLOTS; ++i) {
@@ -282,7 +354,10 @@ production_kernel(const __grid_constant__ ProdParams p) {
             SlotPut put{vals + s, Npad, p.slot_of_key};
             const float kd = has_kd ? vals[sl_kd * Npad + s] : Math<float>::nan();
             const float m91 = vals[sl_m91 * Npad + s];
-            phase_c<float>(st[i], pm, ii1 >= 100, ii2 >= 100, kd, m91, put);
+            IterState<float> st;
+            st.U0 = cst[s]; st.U1 = cst[Npad + s]; st.L0 = cst[2 * Npad + s]; st.L1 = cst[3 * Npad + s];
+            st.Z1 = Z1[i]; st.Z2 = Z2[i]; st.lq2 = lq2[i]; st.aux = aux[i];
+            phase_c<float>(st, pm, ii1 >= 100, ii2 >= 100, kd, m91, put);
           }
         }
       } else {
