@@ -44,6 +44,7 @@ struct ProdParams {
   int nstore;
   signed char slot_of_key[NKEYS];
   signed char key_of_slot[NKEYS];
+  int col_off[NKEYS];                      // slot * Npad (float index of the column), -1 if not stored
   unsigned long long* counter;
   float* gscratch;                         // global variant: per-block columns + stash + loop state
   long long gscratch_per_block;            // floats
@@ -121,11 +122,12 @@ __device__ __forceinline__ float fast_rcp(float x) {
 
 struct SlotPut {
   float* col;                 // &vals[0][s]
-  int stride;
-  const signed char* slot_of_key;
+  const int* col_off;         // per key: float offset of its column (kernel parameter space)
   __device__ __forceinline__ void operator()(int key, float v) const {
-    const int sl = slot_of_key[key];
-    if (sl >= 0) col[sl * stride] = v;
+    // every key the physics can emit under the launch's tokens owns a column, except the
+    // constant-NaN M08_R23 (reference metscales.py:1013-1018), which is never stored
+    if (key == K_M08_R23) return;
+    col[col_off[key]] = v;
   }
 };
 
@@ -233,7 +235,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
           e[2] = 0.027f * z[2];           // metscales.py:948
           e[3] = 0.024f * z[3];           // metscales.py:949
           e[4] = 0.012f * z[4];           // metscales.py:952
-          SlotPut put{vals + s, Npad, p.slot_of_key};
+          SlotPut put{vals + s, p.col_off};
           Carry<float> c;
           c.y = c.n2ha = c.x = 0.0f;
           c.aux = 0u;
@@ -274,13 +276,16 @@ production_kernel(const __grid_constant__ ProdParams p) {
         float num0[SLOTS], num1[SLOTS], den0[SLOTS], den1[SLOTS], cA[SLOTS], cB[SLOTS];
         float Z1[SLOTS], lq1[SLOTS], Z2[SLOTS], lq2[SLOTS];
         uint32_t aux[SLOTS];
-        float* const cst = stash;            // U0, U1, L0, L1 : [4][Npad]
+        constexpr int CS = SLOTS * PT;       // stride of the shared-memory constant arrays
+        float* const cst = stash;            // U0, U1, L0, L1 : [4][CS] (the work area is >= 4*CS floats)
+        float tU0[SLOTS], tU1[SLOTS], tL0[SLOTS], tL1[SLOTS];
         bool any = false;
 #pragma unroll
         for (int i = 0; i < SLOTS; ++i) {
           const int s = i * PT + tid;
           num0[i] = 0.0f; num1[i] = 0.0f; den0[i] = 1.0f; den1[i] = 0.0f; cA[i] = 0.0f; cB[i] = 0.0f;
           Z1[i] = 0.0f; lq1[i] = 0.0f; Z2[i] = 0.0f; lq2[i] = 0.0f; aux[i] = 2u;
+          tU0[i] = 0.0f; tU1[i] = 0.0f; tL0[i] = 0.0f; tL1[i] = 0.0f;
           if (s < N) {
             Carry<float> c;
             c.y = stash[s]; c.n2ha = stash[Npad + s]; c.x = stash[2 * Npad + s];
@@ -292,13 +297,18 @@ production_kernel(const __grid_constant__ ProdParams p) {
             num0[i] = st.num0; num1[i] = st.num1; den0[i] = st.den0; den1[i] = st.den1;
             cA[i] = st.A; cB[i] = st.B; Z1[i] = st.Z1; lq1[i] = st.lq1; Z2[i] = st.Z2; lq2[i] = st.lq2;
             aux[i] = st.aux;
-            cst[s] = st.U0; cst[Npad + s] = st.U1; cst[2 * Npad + s] = st.L0; cst[3 * Npad + s] = st.L1;
-          } else if (s < Npad) {
-            cst[s] = 0.0f; cst[Npad + s] = 0.0f; cst[2 * Npad + s] = 0.0f; cst[3 * Npad + s] = 0.0f;
+            tU0[i] = st.U0; tU1[i] = st.U1; tL0[i] = st.L0; tL1[i] = st.L1;
           }
         }
+        // (barrier: every thread has read its stash entries before the constants overwrite them)
+        const bool anykd = __syncthreads_or(any);
+#pragma unroll
+        for (int i = 0; i < SLOTS; ++i) {
+          const int s = i * PT + tid;
+          cst[s] = tU0[i]; cst[CS + s] = tU1[i]; cst[2 * CS + s] = tL0[i]; cst[3 * CS + s] = tL1[i];
+        }
         // start of the N2Ha loop: 8.6 if KD02_N2O2 is None or all-NaN (metscales.py:1097-1103)
-        if (!__syncthreads_or(any)) {
+        if (!anykd) {
 #pragma unroll
           for (int i = 0; i < SLOTS; ++i) if (i * PT + tid < N) Z1[i] = 8.6f;
         }
@@ -327,9 +337,8 @@ production_kernel(const __grid_constant__ ProdParams p) {
             for (int i = 0; i < SLOTS; ++i) {                            // metscales.py:1167-1178
               const float lq = (num0[i] + Z2[i] * num1[i]) * fast_rcp(den0[i] + Z2[i] * den1[i]);
               const bool lower = ((aux[i] & AUX_ZI_MASK) <= 1u) && (lq >= 6.7f) && (lq < 8.3f);
-              const int sidx = min(i * PT + tid, Npad - 1);
-              const float* cc = cst + (lower ? 2 * Npad : 0) + sidx;
-              Z2[i] = (i * PT + tid < N) ? (cc[0] - lq * cc[Npad]) : 0.0f;
+              const float* cc = cst + (lower ? 2 * CS : 0) + (i * PT + tid);
+              Z2[i] = cc[0] - lq * cc[CS];
               const float d = lq2[i] - lq;
               lq2[i] = lq;
               nan2 = nan2 || (d != d);
@@ -351,11 +360,11 @@ production_kernel(const __grid_constant__ ProdParams p) {
         for (int i = 0; i < SLOTS; ++i) {
           const int s = i * PT + tid;
           if (s < N) {
-            SlotPut put{vals + s, Npad, p.slot_of_key};
+            SlotPut put{vals + s, p.col_off};
             const float kd = has_kd ? vals[sl_kd * Npad + s] : Math<float>::nan();
             const float m91 = vals[sl_m91 * Npad + s];
             IterState<float> st;
-            st.U0 = cst[s]; st.U1 = cst[Npad + s]; st.L0 = cst[2 * Npad + s]; st.L1 = cst[3 * Npad + s];
+            st.U0 = cst[s]; st.U1 = cst[CS + s]; st.L0 = cst[2 * CS + s]; st.L1 = cst[3 * CS + s];
             st.Z1 = Z1[i]; st.Z2 = Z2[i]; st.lq2 = lq2[i]; st.aux = aux[i];
             phase_c<float>(st, pm, ii1 >= 100, ii2 >= 100, kd, m91, put);
           }
@@ -417,7 +426,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
           st.L1 = F[9ll * Npad + s]; st.Z1 = F[10ll * Npad + s]; st.Z2 = F[11ll * Npad + s];
           st.lq2 = F[13ll * Npad + s];
           st.aux = __float_as_uint(stash[3 * Npad + s]);
-          SlotPut put{vals + s, Npad, p.slot_of_key};
+          SlotPut put{vals + s, p.col_off};
           const float kd = has_kd ? vals[(long long)sl_kd * Npad + s] : Math<float>::nan();
           const float m91 = vals[(long long)sl_m91 * Npad + s];
           phase_c<float>(st, pm, ii1 >= 100, ii2 >= 100, kd, m91, put);
@@ -509,6 +518,9 @@ static void build_slots(uint32_t tok, ProdParams& p) {
     ++n;
   }
   p.nstore = n;
+}
+static void finish_slots(ProdParams& p) {
+  for (int k = 0; k < NKEYS; ++k) p.col_off[k] = p.slot_of_key[k] >= 0 ? p.slot_of_key[k] * p.Npad : -1;
 }
 
 static uint32_t philox_calls(uint32_t tok, int correlated, int deterministic) {
@@ -612,6 +624,7 @@ int launch_production(const float* meas, const float* err, long long G, long lon
   p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32); p.goff = galaxy_offset;
   p.correlated = sample_mode == 1; p.deterministic = deterministic != 0;
   p.calls = philox_calls(tok, p.correlated, p.deterministic);
+  finish_slots(p);
   p.pct = pct; p.nvalid = nvalid; p.status = status; p.trips = trips; p.ret = ret; p.Z = Z;
   p.counter = reinterpret_cast<unsigned long long*>(scratch);
   p.gscratch = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(scratch) + 256);
