@@ -108,6 +108,8 @@ int mcz_forward_production(const float* meas_d, const float* err_d, long long G,
 // or > 4 target bins, [4] fallback: > 64 candidates (ties), [5] empty / non-positive columns
 int mcz_debug_counters(unsigned long long* out8, int reset) { return read_sel_counters(out8, reset); }
 
+// [0] galaxies, [1] N2Ha loop trips executed, [2] R23 loop trips executed, [3] proven-divergence early exits
+int mcz_debug_trip_counters(unsigned long long* out4, int reset) { return read_trip_counters(out4, reset); }
 int mcz_debug_col_cycles(unsigned long long* out74, int reset) { return read_col_cycles(out74, reset); }
 int mcz_debug_phase_cycles(unsigned long long* out8, int reset) { return read_phase_cycles(out8, reset); }
 

@@ -18,6 +18,7 @@ int launch_replay(const double* flux, const double* noise, long long G, long lon
 int launch_percentiles_f64(const double* Z, const unsigned char* present, long long rows, long long N,
                            double* pct, int* nvalid, signed char* status, cudaStream_t stream);
 
+int read_trip_counters(unsigned long long* out4, int reset);
 int read_col_cycles(unsigned long long* out, int reset);
 int read_phase_cycles(unsigned long long* out8, int reset);
 int read_sel_counters(unsigned long long* out8, int reset);

@@ -23,6 +23,7 @@ static constexpr int PT = 576;            // threads per block: 18 warps
 static constexpr int PW = PT / 32;
 static constexpr int CAND_FLOATS = 128;   // per-warp candidate area (counter + 64-entry list)
 static constexpr int CTRL_BYTES = 1024;
+static constexpr int DIVERGENCE_CHECK_TRIP = 8;   // when to test a still-running N2Ha loop for provable divergence
 
 struct ProdParams {
   const float* meas;
@@ -138,6 +139,7 @@ namespace mcz {
 // optional phase timing (build with -DMCZ_PHASE_TIMING): cycles summed over blocks, read back with
 // mcz_debug_phase_cycles: [0] galaxies, [1] phase A, [2] phases B+C, [3] phase D own work (mean
 // over the 18 warps), [4] phase D wall (start of D to the block barrier), [5] other
+__device__ unsigned long long g_trip_counters[4];   // [0] galaxies, [1] N2Ha trips executed, [2] R23 trips executed, [3] early exits
 __device__ unsigned long long g_phase_cycles[8];
 __device__ unsigned long long g_col_cycles[2 * NKEYS];   // per key: cycles, max-cycles accumulators
 #ifdef MCZ_PHASE_TIMING
@@ -261,6 +263,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
     MCZ_T(tB0);
     // ---- phases B and C ----------------------------------------------------------------------
     int ii1 = 0, ii2 = 0;
+    int executed1 = -1;       // N2Ha trips actually executed (differs from ii1 after a proven early exit)
     if ((p.tok & T_KD02) && ok) {
       const bool has_kd = (pm >> K_KD02_N2O2) & 1ull;
       const bool has_kn = (pm >> K_KK04_N2HA) & 1ull, has_kr = (pm >> K_KK04_R23) & 1ull;
@@ -355,7 +358,37 @@ production_kernel(const __grid_constant__ ProdParams p) {
           }
           if (act1) { ++ii1; act1 = !n1 && (t1 > itol1) && ii1 < 100; }                 // metscales.py:1111,1117
           if (act2) { ++ii2; act2 = !n2 && ((t2 < 0 ? -t2 : t2) > itol2) && ii2 < 100; } // metscales.py:1166,1177
+          if (act1 && ii1 == DIVERGENCE_CHECK_TRIP) {
+            // Early exit for galaxies whose N2Ha loop provably never converges (SURVEY A.3 item 4:
+            // log N2Ha >~ -0.35).  Per sample the trip is the Moebius map
+            //   lq' = (al - be lq) / (ga - de lq),  al = num0 + A num1, be = B num1, ga = den0 + A den1, de = B den1.
+            // When it has no real fixed point ((be+ga)^2 < 4 al de) the step |lq' - lq| is bounded
+            // below, for EVERY lq, by m = min |q(u)| / r over the two critical points
+            // u = (ga +- r)/de, r = sqrt(al de - be ga), q(u) = de u^2 - (be+ga) u + al.
+            // If sum_s m_s > 4 tol N, mean|dlogq| > tol at every trip: the reference runs to its
+            // 100-trip cap and blanks the galaxy (metscales.py:1119-1121) -- so do that now.
+            float sm = 0.0f;
+#pragma unroll
+            for (int i = 0; i < SLOTS; ++i) {
+              const float al = num0[i] + cA[i] * num1[i], be = cB[i] * num1[i];
+              const float ga = den0[i] + cA[i] * den1[i], de = cB[i] * den1[i];
+              const float bg = be + ga, disc = bg * bg - 4.0f * al * de;
+              float m = 0.0f;
+              if (disc < 0.0f) {
+                const float r = __fsqrt_rn(al * de - be * ga), ide = fast_rcp(de);
+                const float u1 = (ga + r) * ide, u2 = (ga - r) * ide;
+                const float q1 = (de * u1 - bg) * u1 + al, q2 = (de * u2 - bg) * u2 + al;
+                m = fminf(fabsf(q1), fabsf(q2)) * fast_rcp(r);
+              }
+              sm += (m == m) ? fminf(m, 8.0f) : 0.0f;
+            }
+            int tm, tdummy;
+            bool nandummy;
+            block_sum2_fx(sm, 0.0f, false, ctrl, ph, tm, tdummy, nandummy);
+            if (tm > 4 * itol1) { executed1 = ii1; ii1 = 100; act1 = false; }
+          }
         }
+        if (executed1 < 0) executed1 = ii1;
 #pragma unroll
         for (int i = 0; i < SLOTS; ++i) {
           const int s = i * PT + tid;
@@ -458,6 +491,10 @@ production_kernel(const __grid_constant__ ProdParams p) {
       }
     }
     if (tid == 0) {
+      atomicAdd(&g_trip_counters[0], 1ull);
+      atomicAdd(&g_trip_counters[1], (unsigned long long)(executed1 < 0 ? ii1 : executed1));
+      atomicAdd(&g_trip_counters[2], (unsigned long long)ii2);
+      if (executed1 >= 0 && executed1 != ii1) atomicAdd(&g_trip_counters[3], 1ull);
       p.trips[2 * g] = ii1;
       p.trips[2 * g + 1] = ii2;
       if (p.ret) p.ret[g] = ok ? 0 : -1;
@@ -568,6 +605,16 @@ static ProdPlan make_plan(long long G, long long N, int nstore) {
   const long long sms = num_sms();
   pl.grid = (int)(G < sms ? (G > 0 ? G : 1) : sms);
   return pl;
+}
+
+int read_trip_counters(unsigned long long* out4, int reset) {
+  int rc = check_cuda(cudaMemcpyFromSymbol(out4, g_trip_counters, 4 * sizeof(unsigned long long)), "read trip counters");
+  if (rc) return rc;
+  if (reset) {
+    unsigned long long z[4] = {0};
+    rc = check_cuda(cudaMemcpyToSymbol(g_trip_counters, z, sizeof(z)), "reset trip counters");
+  }
+  return rc;
 }
 
 int read_col_cycles(unsigned long long* out, int reset) {
