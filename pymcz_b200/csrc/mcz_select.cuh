@@ -259,7 +259,220 @@ __device__ void select_in_interval(const SelWarp& w, float lo, float hi, unsigne
   }
 }
 
-// percentile extraction for one stored column (mcz.py:273-301); all 32 lanes participate.
+// Robust fine-index range of a column from its first 64 samples (i.i.d. draws: any fixed subset is
+// a fair subsample): [q06 - 1.5 w, q94 + 1.5 w], w = q94 - q06, so that a few wild values do not
+// stretch the index.  Returns false when that prefix has fewer than 8 finite values or is constant.
+__device__ __forceinline__ bool subsample_range(const float* __restrict__ v, int lane, float& scale, float& nLs) {
+  const float pinf = __int_as_float(0x7f800000);
+  float a = v[lane], b = v[lane + 32];
+  a = finite_f(a) ? a : pinf;
+  b = finite_f(b) ? b : pinf;
+  const int m = __popc(__ballot_sync(0xffffffffu, a < pinf)) + __popc(__ballot_sync(0xffffffffu, b < pinf));
+  sort64_regs(a, b, lane);
+  if (m < 8) return false;
+  float qlo = sorted64_get(a, b, (unsigned)(0.06f * (float)(m - 1)));
+  float qhi = sorted64_get(a, b, (unsigned)(m - 1) - (unsigned)(0.06f * (float)(m - 1)));
+  if (!(qhi > qlo)) { qlo = sorted64_get(a, b, 0u); qhi = sorted64_get(a, b, (unsigned)(m - 1)); }
+  if (!(qhi > qlo)) return false;
+  const float ww = 1.5f * (qhi - qlo);
+  const float L = qlo - ww, H = qhi + ww;
+  scale = (float)FB / (H - L);
+  nLs = -L * scale;
+  return finite_f(scale) && finite_f(nLs);
+}
+
+// ---- the selection of one column, in stages --------------------------------------------------
+// Stage "plan" (after the histogram is complete): n, the six ranks, the fine-index ranges that
+// hold them and which of those are gathered (<= 64 candidates in all) or crowded.
+struct SelPlan {
+  int n;
+  unsigned rk[6];          // ascending: p16 pair, median pair, p84 pair
+  double gam[3];
+  int nr;                  // number of merged ranges (<= 3)
+  int rlo[3], rhi[3];      // fine-index range
+  unsigned rE[3], rM[3];   // samples below the range / inside it
+  int rq[3];               // range of pair q
+  bool crowded[3];
+  unsigned ncand;
+};
+
+template <bool PACK16>
+__device__ __forceinline__ void sel_make_plan(const SelWarp& w, SelPlan& P) {
+  unsigned lex, ltot, un;
+  fine_prefix<PACK16>(w, lex, ltot, un);
+  P.n = (int)un;
+  P.nr = 0;
+  P.ncand = 0;
+  if (P.n == 0) return;
+  const double qs[3] = {16.0 / 100.0, 50.0 / 100.0, 84.0 / 100.0};                  // mcz.py:288
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    const double vi = (double)(P.n - 1) * qs[q];
+    const double lo = floor(vi);
+    P.gam[q] = vi - lo;
+    P.rk[2 * q] = (unsigned)lo;
+    P.rk[2 * q + 1] = min((unsigned)lo + 1u, (unsigned)(P.n - 1));
+  }
+  int fi[6];
+  unsigned ex[6], cn[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) fine_locate<PACK16>(w, lex, ltot, P.rk[i], fi[i], ex[i], cn[i]);
+  // Merge the three pair ranges [fi[2q], fi[2q+1]] where they touch or overlap (small n, ties).
+  int nr = 0;
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    const int a = fi[2 * q], b = fi[2 * q + 1];
+    const unsigned endcount = ex[2 * q + 1] + cn[2 * q + 1];      // samples with f <= b
+    if (nr > 0 && a <= P.rhi[nr - 1]) {
+      if (b > P.rhi[nr - 1]) { P.rhi[nr - 1] = b; P.rM[nr - 1] = endcount - P.rE[nr - 1]; }
+    } else {
+      P.rlo[nr] = a; P.rhi[nr] = b; P.rE[nr] = ex[2 * q]; P.rM[nr] = endcount - ex[2 * q];
+      ++nr;
+    }
+    P.rq[q] = nr - 1;
+  }
+  P.nr = nr;
+  // gather the ranges that fit in the 64-candidate list; the others are "crowded"
+  unsigned ncand = 0;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    P.crowded[r] = false;
+    if (r < nr) {
+      if (ncand + P.rM[r] <= 64u) ncand += P.rM[r];
+      else P.crowded[r] = true;
+    }
+  }
+  P.ncand = ncand;
+}
+
+// range tests of pass G: (unsigned)(f - tlo) <= tsp; `gathered` selects the ranges that are
+// gathered (true) or the crowded ones (false); the others get a test that never matches
+__device__ __forceinline__ void sel_tests(const SelPlan& P, bool gathered, int tlo[3], unsigned tsp[3]) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const bool use = r < P.nr && (P.crowded[r] != gathered);
+    tlo[r] = use ? P.rlo[r] : 0x40000000;
+    tsp[r] = use ? (unsigned)(P.rhi[r] - P.rlo[r]) : 0u;
+  }
+}
+
+// Per-warp statistics pass: sum of the finite samples (if want_sum) and, for the crowded ranges,
+// min / max of their members and how many equal the min.
+__device__ __forceinline__ void sel_stats_pass(const SelWarp& w, float scale, float nLs, const SelPlan& P,
+                                               bool want_sum, double& total, float bmn[3], float bmx[3],
+                                               unsigned nmin[3]) {
+  const float pinf = __int_as_float(0x7f800000), ninf = __int_as_float(0xff800000);
+  int tlo[3];
+  unsigned tsp[3];
+  sel_tests(P, false, tlo, tsp);
+  int bcm[3] = {0, 0, 0};
+  float sum = 0.0f;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) { bmn[r] = pinf; bmx[r] = ninf; }
+  for (int s0 = 4 * w.lane; s0 < w.Npad; s0 += 128) {
+    const float4 x4 = *reinterpret_cast<const float4*>(w.v + s0);
+    const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float x = xs[j];
+      if (finite_f(x)) {
+        sum += x;
+        const int f = fine_index(x, scale, nLs);
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+          if ((unsigned)(f - tlo[r]) <= tsp[r]) {
+            if (x < bmn[r]) { bmn[r] = x; bcm[r] = 1; }
+            else if (x == bmn[r]) ++bcm[r];
+            bmx[r] = fmaxf(bmx[r], x);
+          }
+      }
+    }
+  }
+  if (want_sum) total = warp_sum((double)sum);
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    float gm = bmn[r];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      gm = fminf(gm, __shfl_xor_sync(0xffffffffu, gm, o));
+      bmx[r] = fmaxf(bmx[r], __shfl_xor_sync(0xffffffffu, bmx[r], o));
+    }
+    nmin[r] = (unsigned)__reduce_add_sync(0xffffffffu, bmn[r] == gm ? bcm[r] : 0);
+    bmn[r] = gm;
+  }
+}
+
+// Stage "finish": the gathered candidates are in w.clist (P.ncand of them, any order); sort them,
+// read the order statistics, resolve crowded ranges, interpolate.
+template <bool PACK16>
+__device__ __forceinline__ void sel_finish(const SelWarp& w, float scale, float nLs, const SelPlan& P,
+                                           bool have_stats, float bmn[3], float bmx[3], unsigned nmin[3],
+                                           float pct[3]) {
+  const float pinf = __int_as_float(0x7f800000);
+  const int lane = w.lane;
+  __syncwarp();
+  float ca = (unsigned)lane < P.ncand ? w.clist[lane] : pinf;
+  float cb = (unsigned)(lane + 32) < P.ncand ? w.clist[lane + 32] : pinf;
+  sort64_regs(ca, cb, lane);
+  float res[6];
+  {
+    // candidates of lower gathered ranges come first in the sorted list
+    unsigned below[3];
+    unsigned acc = 0;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      below[r] = acc;
+      if (r < P.nr && !P.crowded[r]) acc += P.rM[r];
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const int r = P.rq[i >> 1];
+      const unsigned bl = r == 0 ? below[0] : (r == 1 ? below[1] : below[2]);
+      const unsigned E = r == 0 ? P.rE[0] : (r == 1 ? P.rE[1] : P.rE[2]);
+      res[i] = sorted64_get(ca, cb, (bl + P.rk[i] - E) & 63u);
+    }
+  }
+  if (P.crowded[0] || P.crowded[1] || P.crowded[2]) {
+    // A crowded range is exactly the set of finite values in [bmn, bmx] (the fine index is
+    // monotone), so a rank inside it is an order statistic of that interval.
+    sel_count(SEL_CROWDED);
+    if (!have_stats) {
+      double dummy;
+      sel_stats_pass(w, scale, nLs, P, false, dummy, bmn, bmx, nmin);
+    }
+#pragma unroll 1
+    for (int q = 0; q < 3; ++q) {
+      const int r = P.rq[q];
+      const bool cr = r == 0 ? P.crowded[0] : (r == 1 ? P.crowded[1] : P.crowded[2]);
+      if (!cr) continue;
+      const float lo = r == 0 ? bmn[0] : (r == 1 ? bmn[1] : bmn[2]);
+      const float hi = r == 0 ? bmx[0] : (r == 1 ? bmx[1] : bmx[2]);
+      const unsigned nm = r == 0 ? nmin[0] : (r == 1 ? nmin[1] : nmin[2]);
+      const unsigned E = r == 0 ? P.rE[0] : (r == 1 ? P.rE[1] : P.rE[2]);
+      const unsigned ra = P.rk[2 * q] - E, rb = P.rk[2 * q + 1] - E;
+      if (lo == hi || rb < nm) { res[2 * q] = lo; res[2 * q + 1] = lo; continue; }
+      select_in_interval<PACK16>(w, lo, hi, ra, rb, res[2 * q], res[2 * q + 1]);
+    }
+  }
+  pct[0] = np_lerp_f(res[2], res[3], P.gam[1]);       // median
+  pct[1] = np_lerp_f(res[0], res[1], P.gam[0]);       // 16th
+  pct[2] = np_lerp_f(res[4], res[5], P.gam[2]);       // 84th
+}
+
+// Fine-index range of a column when the 64-sample estimate is not usable: the exact range.
+// Returns false for a column without finite values.
+__device__ __forceinline__ bool exact_range(const SelWarp& w, float& scale, float& nLs) {
+  float qlo, qhi;
+  column_minmax(w, qlo, qhi);
+  if (!(qhi >= qlo)) return false;
+  if (!(qhi > qlo)) { qlo -= 1.0f; qhi += 1.0f; }       // constant column: any range will do
+  scale = (float)FB / (qhi - qlo);
+  nLs = -qlo * scale;
+  if (!finite_f(scale) || !finite_f(nLs)) { scale = (float)FB / (FLT_MAX * 0.5f); nLs = 0.5f * (float)FB; }
+  return true;
+}
+
+// Whole selection of one column by one warp (mcz.py:273-301); all 32 lanes participate.
 // v has Npad (multiple of 128) readable entries; entries in [N, Npad) are NaN.
 // hist: FineHist<PACK16>::WORDS words; cand: 128 floats.
 template <bool PACK16>
@@ -271,42 +484,35 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
   w.v = v; w.Npad = Npad; w.hist = hist; w.lane = lane;
   w.ccount = reinterpret_cast<unsigned*>(cand);
   w.clist = cand + 32;
-  const float pinf = __int_as_float(0x7f800000), ninf = __int_as_float(0xff800000);
   const float nanf_ = Math<float>::nan();
   pct[0] = pct[1] = pct[2] = nanf_;
+  nvalid = 0;
   sel_count(SEL_TOTAL);
-  // ---- robust range from the first 64 samples (i.i.d. draws: any fixed subset is a fair subsample)
-  float L, H;
-  {
-    float a = v[lane], b = v[lane + 32];
-    a = finite_f(a) ? a : pinf;
-    b = finite_f(b) ? b : pinf;
-    const int m = __popc(__ballot_sync(0xffffffffu, a < pinf)) + __popc(__ballot_sync(0xffffffffu, b < pinf));
-    sort64_regs(a, b, lane);
-    float qlo = pinf, qhi = ninf;
-    if (m >= 8) {
-      qlo = sorted64_get(a, b, (unsigned)(0.06f * (float)(m - 1)));
-      qhi = sorted64_get(a, b, (unsigned)(m - 1) - (unsigned)(0.06f * (float)(m - 1)));
-      if (!(qhi > qlo)) { qlo = sorted64_get(a, b, 0u); qhi = sorted64_get(a, b, (unsigned)(m - 1)); }
-    }
-    if (!(qhi > qlo)) {
-      // too few finite values up front, or a constant prefix: use the exact range of the column
-      sel_count(SEL_NO_SUBSAMPLE);
-      column_minmax(w, qlo, qhi);
-      if (!(qhi >= qlo)) { nvalid = 0; status = ST_EMPTY; return; }                 // mcz.py:277-280
-      if (!(qhi > qlo)) { qlo -= 1.0f; qhi += 1.0f; }       // constant column: any range will do
-      L = qlo; H = qhi;
-    } else {
-      const float ww = 1.5f * (qhi - qlo);
-      L = qlo - ww;
-      H = qhi + ww;
-    }
+  float scale, nLs;
+  if (!subsample_range(v, lane, scale, nLs)) {
+    sel_count(SEL_NO_SUBSAMPLE);
+    if (!exact_range(w, scale, nLs)) { status = ST_EMPTY; return; }                 // mcz.py:277-280
   }
-  float scale = (float)FB / (H - L), nLs = -L * scale;
-  if (!finite_f(scale) || !finite_f(nLs)) { L = -FLT_MAX * 0.25f; H = FLT_MAX * 0.25f; scale = (float)FB / (H - L); nLs = -L * scale; }
-
-  // ---- pass H: sum and the 1024-bin histogram (out-of-range finite values land in the end bins)
+  // ---- pass H: the 1024-bin histogram (out-of-range finite values land in the end bins)
   FH::zero(hist, lane);
+#pragma unroll 2
+  for (int s0 = 4 * lane; s0 < Npad; s0 += 128) {
+    const float4 x4 = *reinterpret_cast<const float4*>(v + s0);
+    const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (finite_f(xs[j])) FH::add(hist, fine_index(xs[j], scale, nLs));            // mcz.py:273
+  }
+  SelPlan P;
+  sel_make_plan<PACK16>(w, P);
+  nvalid = P.n;
+  if (P.n == 0) { sel_count(SEL_TRIVIAL); status = ST_EMPTY; return; }              // mcz.py:277-280
+  // ---- pass G: gather the members of the uncrowded ranges, sum everything
+  int tlo[3];
+  unsigned tsp[3];
+  sel_tests(P, true, tlo, tsp);
+  if (lane == 0) *w.ccount = 0u;
+  __syncwarp();
   float sum = 0.0f;
 #pragma unroll 2
   for (int s0 = 4 * lane; s0 < Npad; s0 += 128) {
@@ -315,169 +521,20 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float x = xs[j];
-      const bool fin = finite_f(x);                                                 // mcz.py:273
-      if (fin) FH::add(hist, fine_index(x, scale, nLs));
+      const int f = fine_index(x, scale, nLs);
+      const bool fin = finite_f(x);
+      const bool hit = ((unsigned)(f - tlo[0]) <= tsp[0]) || ((unsigned)(f - tlo[1]) <= tsp[1]) ||
+                       ((unsigned)(f - tlo[2]) <= tsp[2]);
       sum += fin ? x : 0.0f;
+      if (hit && fin) w.clist[atomicAdd(w.ccount, 1u) & 63u] = x;
     }
   }
-  unsigned lex, ltot, un;
-  fine_prefix<PACK16>(w, lex, ltot, un);
-  const int n = (int)un;
-  const double total = warp_sum((double)sum);
-  nvalid = n;
-  if (n == 0) { sel_count(SEL_TRIVIAL); status = ST_EMPTY; return; }                // mcz.py:277-280
-  if (!(total > 0.0)) { sel_count(SEL_TRIVIAL); status = ST_NONPOS; return; }       // mcz.py:282-285
+  if (!(warp_sum((double)sum) > 0.0)) { sel_count(SEL_TRIVIAL); status = ST_NONPOS; return; }   // mcz.py:282-285
   status = ST_OK;
-  // ranks in ascending order: p16 pair, median pair, p84 pair
-  const double qs[3] = {16.0 / 100.0, 50.0 / 100.0, 84.0 / 100.0};                  // mcz.py:288
-  unsigned rk[6];
-  double gam[3];
-#pragma unroll
-  for (int q = 0; q < 3; ++q) {
-    const double vi = (double)(n - 1) * qs[q];
-    const double lo = floor(vi);
-    gam[q] = vi - lo;
-    rk[2 * q] = (unsigned)lo;
-    rk[2 * q + 1] = min((unsigned)lo + 1u, (unsigned)(n - 1));
-  }
-  int fi[6];
-  unsigned ex[6], cn[6];
-#pragma unroll
-  for (int i = 0; i < 6; ++i) fine_locate<PACK16>(w, lex, ltot, rk[i], fi[i], ex[i], cn[i]);
-  // Merge the three pair ranges [fi[2q], fi[2q+1]] where they touch or overlap (small n, ties).
-  // rlo/rhi: fine-index range; rE: samples below it; rM: samples inside it; rq[q]: range of pair q.
-  int rlo[3], rhi[3], rq[3];
-  unsigned rE[3], rM[3];
-  int nr = 0;
-#pragma unroll
-  for (int q = 0; q < 3; ++q) {
-    const int a = fi[2 * q], b = fi[2 * q + 1];
-    const unsigned endcount = ex[2 * q + 1] + cn[2 * q + 1];      // samples with f <= b
-    if (nr > 0 && a <= rhi[nr - 1]) {
-      if (b > rhi[nr - 1]) { rhi[nr - 1] = b; rM[nr - 1] = endcount - rE[nr - 1]; }
-    } else {
-      rlo[nr] = a; rhi[nr] = b; rE[nr] = ex[2 * q]; rM[nr] = endcount - ex[2 * q];
-      ++nr;
-    }
-    rq[q] = nr - 1;
-  }
-  // gather the ranges that fit in the 64-candidate list; the others are "crowded"
-  bool crowded[3] = {false, false, false};
-  unsigned ncand = 0;
-#pragma unroll
-  for (int r = 0; r < 3; ++r)
-    if (r < nr) {
-      if (ncand + rM[r] <= 64u) ncand += rM[r];
-      else crowded[r] = true;
-    }
-  const bool anycrowded = crowded[0] || crowded[1] || crowded[2];
-  // per-range test: (unsigned)(f - lo) <= span; an unused or crowded-free slot gets an empty test
-  int tlo[3];
-  unsigned tsp[3];
-#pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    tlo[r] = r < nr ? rlo[r] : 0x40000000;
-    tsp[r] = r < nr ? (unsigned)(rhi[r] - rlo[r]) : 0u;
-  }
-  if (lane == 0) *w.ccount = 0u;
-  __syncwarp();
-  float bmn[3] = {pinf, pinf, pinf}, bmx[3] = {ninf, ninf, ninf};
-  int bcm[3] = {0, 0, 0};
-  if (!anycrowded) {
-#pragma unroll 2
-    for (int s0 = 4 * lane; s0 < Npad; s0 += 128) {
-      const float4 x4 = *reinterpret_cast<const float4*>(v + s0);
-      const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float x = xs[j];
-        const int f = fine_index(x, scale, nLs);
-        const bool hit = ((unsigned)(f - tlo[0]) <= tsp[0]) || ((unsigned)(f - tlo[1]) <= tsp[1]) ||
-                         ((unsigned)(f - tlo[2]) <= tsp[2]);
-        if (hit && finite_f(x)) w.clist[atomicAdd(w.ccount, 1u) & 63u] = x;
-      }
-    }
-  } else {
-    sel_count(SEL_CROWDED);
-    for (int s0 = 4 * lane; s0 < Npad; s0 += 128) {
-      const float4 x4 = *reinterpret_cast<const float4*>(v + s0);
-      const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float x = xs[j];
-        const int f = fine_index(x, scale, nLs);
-        if (finite_f(x)) {
-#pragma unroll
-          for (int r = 0; r < 3; ++r) {
-            if ((unsigned)(f - tlo[r]) <= tsp[r]) {
-              if (!crowded[r]) {
-                w.clist[atomicAdd(w.ccount, 1u) & 63u] = x;
-              } else {
-                if (x < bmn[r]) { bmn[r] = x; bcm[r] = 1; }
-                else if (x == bmn[r]) ++bcm[r];
-                bmx[r] = fmaxf(bmx[r], x);
-              }
-            }
-          }
-        }
-      }
-    }
-  }
   sel_count(SEL_FAST);
-  __syncwarp();
-  float ca = (unsigned)lane < ncand ? w.clist[lane] : pinf;
-  float cb = (unsigned)(lane + 32) < ncand ? w.clist[lane + 32] : pinf;
-  sort64_regs(ca, cb, lane);
-  float res[6];
-  {
-    // candidates of lower gathered ranges come first in the sorted list
-    unsigned below[3];
-    unsigned acc = 0;
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      below[r] = acc;
-      if (r < nr && !crowded[r]) acc += rM[r];
-    }
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      const int r = rq[i >> 1];
-      const unsigned bl = r == 0 ? below[0] : (r == 1 ? below[1] : below[2]);
-      const unsigned E = r == 0 ? rE[0] : (r == 1 ? rE[1] : rE[2]);
-      res[i] = sorted64_get(ca, cb, (bl + rk[i] - E) & 63u);
-    }
-  }
-  if (anycrowded) {
-    // A crowded range is exactly the set of finite values in [bmn, bmx] (the fine index is
-    // monotone), so a rank inside it is an order statistic of that interval.
-    unsigned nmin[3];
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      float gm = bmn[r];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        gm = fminf(gm, __shfl_xor_sync(0xffffffffu, gm, o));
-        bmx[r] = fmaxf(bmx[r], __shfl_xor_sync(0xffffffffu, bmx[r], o));
-      }
-      nmin[r] = (unsigned)__reduce_add_sync(0xffffffffu, bmn[r] == gm ? bcm[r] : 0);
-      bmn[r] = gm;
-    }
-#pragma unroll 1
-    for (int q = 0; q < 3; ++q) {
-      const int r = rq[q];
-      const bool cr = r == 0 ? crowded[0] : (r == 1 ? crowded[1] : crowded[2]);
-      if (!cr) continue;
-      const float lo = r == 0 ? bmn[0] : (r == 1 ? bmn[1] : bmn[2]);
-      const float hi = r == 0 ? bmx[0] : (r == 1 ? bmx[1] : bmx[2]);
-      const unsigned nm = r == 0 ? nmin[0] : (r == 1 ? nmin[1] : nmin[2]);
-      const unsigned E = r == 0 ? rE[0] : (r == 1 ? rE[1] : rE[2]);
-      const unsigned ra = rk[2 * q] - E, rb = rk[2 * q + 1] - E;
-      if (lo == hi || rb < nm) { res[2 * q] = lo; res[2 * q + 1] = lo; continue; }
-      select_in_interval<PACK16>(w, lo, hi, ra, rb, res[2 * q], res[2 * q + 1]);
-    }
-  }
-  pct[0] = np_lerp_f(res[2], res[3], gam[1]);       // median
-  pct[1] = np_lerp_f(res[0], res[1], gam[0]);       // 16th
-  pct[2] = np_lerp_f(res[4], res[5], gam[2]);       // 84th
+  float bmn[3], bmx[3];
+  unsigned nmin[3];
+  sel_finish<PACK16>(w, scale, nLs, P, false, bmn, bmx, nmin, pct);
 }
 
 }  // namespace mcz
