@@ -162,23 +162,32 @@ production_kernel(const __grid_constant__ ProdParams p) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = p.N, Npad = p.Npad;
 
-  float* vals;          // [nstore][Npad]
-  float* stash;         // y, n2ha, x, aux : [4][Npad]
+  constexpr bool PACK16 = !GLOBAL;        // shared-memory variant: columns of < 65536 samples
+  constexpr size_t HIST_BYTES = FineHist<PACK16>::BYTES;
+  float* vals;              // columns [nstore][Npad]
+  float* st0; float* st1; float* st2; float* st3;   // four per-sample scratch arrays (phase-A carry, then R23 constants)
   float* giter = nullptr;   // global variant: loop state [16][Npad]
-  unsigned char* work;  // selection scratch (aliases the stash in the shared-memory variant)
+  unsigned char* work;      // selection scratch: PW histograms, then PW candidate areas
   if (GLOBAL) {
     float* base = p.gscratch + (long long)blockIdx.x * p.gscratch_per_block;
     vals = base;
-    stash = base + (long long)p.nstore * Npad;
-    giter = stash + 4ll * Npad;
+    st0 = base + (long long)p.nstore * Npad;
+    st1 = st0 + Npad; st2 = st1 + Npad; st3 = st2 + Npad;
+    giter = st3 + Npad;
     work = smem + CTRL_BYTES;
   } else {
+    // Shared-memory variant (Npad == SLOTS*PT always).  The histograms are live from phase B on
+    // (they are filled while the KK04 loops wait on their barriers), so the per-sample scratch
+    // arrays must not alias them: three of them are the columns that only phase C writes
+    // (KK04_N2Ha, KK04_R23, KD02comb), the fourth is an extra array after the candidate areas.
     vals = reinterpret_cast<float*>(smem + CTRL_BYTES);
     work = smem + CTRL_BYTES + (size_t)p.nstore * Npad * sizeof(float);
-    stash = reinterpret_cast<float*>(work);
+    st3 = reinterpret_cast<float*>(work + (size_t)PW * (HIST_BYTES + CAND_FLOATS * sizeof(float)));
+    const bool kd = p.tok & T_KD02;
+    st0 = kd ? vals + p.col_off[K_KK04_N2HA] : st3;
+    st1 = kd ? vals + p.col_off[K_KK04_R23] : st3;
+    st2 = kd ? vals + p.col_off[K_KD02COMB] : st3;
   }
-  constexpr bool PACK16 = !GLOBAL;        // shared-memory variant: columns of < 65536 samples
-  constexpr size_t HIST_BYTES = FineHist<PACK16>::BYTES;
   unsigned* hist = reinterpret_cast<unsigned*>(work + (size_t)warp * HIST_BYTES);
   float* cand = reinterpret_cast<float*>(work + (size_t)PW * HIST_BYTES) + warp * CAND_FLOATS;
 
@@ -242,10 +251,10 @@ production_kernel(const __grid_constant__ ProdParams p) {
           c.y = c.n2ha = c.x = 0.0f;
           c.aux = 0u;
           phase_a<float>(f, e, flags, p.tok, de, put, c);
-          stash[s] = c.y;
-          stash[Npad + s] = c.n2ha;
-          stash[2 * Npad + s] = c.x;
-          stash[3 * Npad + s] = __uint_as_float(c.aux);
+          st0[s] = c.y;
+          st1[s] = c.n2ha;
+          st2[s] = c.x;
+          st3[s] = __uint_as_float(c.aux);
         } else if (s < Npad) {
           for (int sl = 0; sl < p.nstore; ++sl) vals[(long long)sl * Npad + s] = Math<float>::nan();
         }
@@ -280,7 +289,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
         float Z1[SLOTS], lq1[SLOTS], Z2[SLOTS], lq2[SLOTS];
         uint32_t aux[SLOTS];
         constexpr int CS = SLOTS * PT;       // stride of the shared-memory constant arrays
-        float* const cst = stash;            // U0, U1, L0, L1 : [4][CS] (the work area is >= 4*CS floats)
+        // U0, U1, L0, L1 of every sample replace the carry in st0..st3 (Npad == CS in this variant)
         float tU0[SLOTS], tU1[SLOTS], tL0[SLOTS], tL1[SLOTS];
         bool any = false;
 #pragma unroll
@@ -291,8 +300,8 @@ production_kernel(const __grid_constant__ ProdParams p) {
           tU0[i] = 0.0f; tU1[i] = 0.0f; tL0[i] = 0.0f; tL1[i] = 0.0f;
           if (s < N) {
             Carry<float> c;
-            c.y = stash[s]; c.n2ha = stash[Npad + s]; c.x = stash[2 * Npad + s];
-            c.aux = __float_as_uint(stash[3 * Npad + s]);
+            c.y = st0[s]; c.n2ha = st1[s]; c.x = st2[s];
+            c.aux = __float_as_uint(st3[s]);
             const float kd = has_kd ? vals[sl_kd * Npad + s] : Math<float>::nan();
             IterState<float> st;
             make_iter<float>(c, kd, st);
@@ -308,7 +317,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
 #pragma unroll
         for (int i = 0; i < SLOTS; ++i) {
           const int s = i * PT + tid;
-          cst[s] = tU0[i]; cst[CS + s] = tU1[i]; cst[2 * CS + s] = tL0[i]; cst[3 * CS + s] = tL1[i];
+          st0[s] = tU0[i]; st1[s] = tU1[i]; st2[s] = tL0[i]; st3[s] = tL1[i];
         }
         // start of the N2Ha loop: 8.6 if KD02_N2O2 is None or all-NaN (metscales.py:1097-1103)
         if (!anykd) {
@@ -340,8 +349,8 @@ production_kernel(const __grid_constant__ ProdParams p) {
             for (int i = 0; i < SLOTS; ++i) {                            // metscales.py:1167-1178
               const float lq = (num0[i] + Z2[i] * num1[i]) * fast_rcp(den0[i] + Z2[i] * den1[i]);
               const bool lower = ((aux[i] & AUX_ZI_MASK) <= 1u) && (lq >= 6.7f) && (lq < 8.3f);
-              const float* cc = cst + (lower ? 2 * CS : 0) + (i * PT + tid);
-              Z2[i] = cc[0] - lq * cc[CS];
+              const int s = i * PT + tid;
+              Z2[i] = (lower ? st2[s] : st0[s]) - lq * (lower ? st3[s] : st1[s]);
               const float d = lq2[i] - lq;
               lq2[i] = lq;
               nan2 = nan2 || (d != d);
@@ -397,9 +406,12 @@ production_kernel(const __grid_constant__ ProdParams p) {
             const float kd = has_kd ? vals[sl_kd * Npad + s] : Math<float>::nan();
             const float m91 = vals[sl_m91 * Npad + s];
             IterState<float> st;
-            st.U0 = cst[s]; st.U1 = cst[CS + s]; st.L0 = cst[2 * CS + s]; st.L1 = cst[3 * CS + s];
+            st.U0 = st0[s]; st.U1 = st1[s]; st.L0 = st2[s]; st.L1 = st3[s];
             st.Z1 = Z1[i]; st.Z2 = Z2[i]; st.lq2 = lq2[i]; st.aux = aux[i];
             phase_c<float>(st, pm, ii1 >= 100, ii2 >= 100, kd, m91, put);
+          } else {
+            // the scratch use of the three phase-C columns ends here: restore their NaN padding
+            st0[s] = Math<float>::nan(); st1[s] = Math<float>::nan(); st2[s] = Math<float>::nan();
           }
         }
       } else {
@@ -408,8 +420,8 @@ production_kernel(const __grid_constant__ ProdParams p) {
         bool any = false;
         for (int s = tid; s < N; s += PT) {
           Carry<float> c;
-          c.y = stash[s]; c.n2ha = stash[Npad + s]; c.x = stash[2 * Npad + s];
-          c.aux = __float_as_uint(stash[3 * Npad + s]);
+          c.y = st0[s]; c.n2ha = st1[s]; c.x = st2[s];
+          c.aux = __float_as_uint(st3[s]);
           const float kd = has_kd ? vals[(long long)sl_kd * Npad + s] : Math<float>::nan();
           IterState<float> st;
           make_iter<float>(c, kd, st);
@@ -434,7 +446,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
             IterState<float> st;
             st.num0 = F[0ll * Npad + s]; st.num1 = F[1ll * Npad + s]; st.den0 = F[2ll * Npad + s];
             st.den1 = F[3ll * Npad + s];
-            st.aux = __float_as_uint(stash[3 * Npad + s]);
+            st.aux = __float_as_uint(st3[s]);
             if (act1) {
               st.A = F[4ll * Npad + s]; st.B = F[5ll * Npad + s];
               st.Z1 = F[10ll * Npad + s]; st.lq1 = F[12ll * Npad + s];
@@ -458,7 +470,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
           st.U0 = F[6ll * Npad + s]; st.U1 = F[7ll * Npad + s]; st.L0 = F[8ll * Npad + s];
           st.L1 = F[9ll * Npad + s]; st.Z1 = F[10ll * Npad + s]; st.Z2 = F[11ll * Npad + s];
           st.lq2 = F[13ll * Npad + s];
-          st.aux = __float_as_uint(stash[3 * Npad + s]);
+          st.aux = __float_as_uint(st3[s]);
           SlotPut put{vals + s, p.col_off};
           const float kd = has_kd ? vals[(long long)sl_kd * Npad + s] : Math<float>::nan();
           const float m91 = vals[(long long)sl_m91 * Npad + s];
@@ -593,15 +605,21 @@ static int num_sms() {
 
 static ProdPlan make_plan(long long G, long long N, int nstore) {
   ProdPlan pl;
-  pl.Npad = (int)((N + 127) / 128 * 128);
-  const size_t cols = (size_t)nstore * pl.Npad * sizeof(float);
-  const size_t stash = 4ull * pl.Npad * sizeof(float);
-  const size_t sel8 = (size_t)PW * (FineHist<true>::BYTES + CAND_FLOATS * sizeof(float));
-  const size_t sel16 = (size_t)PW * (FineHist<false>::BYTES + CAND_FLOATS * sizeof(float));
-  const size_t smem_local = CTRL_BYTES + cols + (stash > sel8 ? stash : sel8);
+  // shared-memory variant: fixed column stride of 4*PT samples; layout = control block, columns,
+  // PW histograms, PW candidate areas, one extra per-sample array
+  const size_t smem_local = CTRL_BYTES + (size_t)nstore * 4 * PT * sizeof(float) +
+                            (size_t)PW * (FineHist<true>::BYTES + CAND_FLOATS * sizeof(float)) +
+                            (size_t)4 * PT * sizeof(float);
   pl.global = !(N <= 4ll * PT && smem_local <= 227ull * 1024);
-  pl.smem = pl.global ? CTRL_BYTES + sel16 : smem_local;
-  pl.per_block_floats = pl.global ? ((long long)nstore + 4 + 16) * pl.Npad : 0;
+  if (!pl.global) {
+    pl.Npad = 4 * PT;
+    pl.smem = smem_local;
+    pl.per_block_floats = 0;
+  } else {
+    pl.Npad = (int)((N + 127) / 128 * 128);
+    pl.smem = CTRL_BYTES + (size_t)PW * (FineHist<false>::BYTES + CAND_FLOATS * sizeof(float));
+    pl.per_block_floats = ((long long)nstore + 4 + 16) * pl.Npad;
+  }
   const long long sms = num_sms();
   pl.grid = (int)(G < sms ? (G > 0 ? G : 1) : sms);
   return pl;

@@ -11,6 +11,7 @@ __global__ void __launch_bounds__(576, 1) k(int mode, int iters, const float* __
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned* hw = reinterpret_cast<unsigned*>(smem) + warp * 512;   // 2 KB per warp
   unsigned char* hb = reinterpret_cast<unsigned char*>(hw);
+  unsigned* hw2 = reinterpret_cast<unsigned*>(smem) + warp * 1024;
   for (int i = lane; i < 512; i += 32) hw[i] = 0;
   __syncthreads();
   const float* v = vals + (blockIdx.x * 18 + warp) * 2208;
@@ -28,6 +29,19 @@ __global__ void __launch_bounds__(576, 1) k(int mode, int iters, const float* __
         atomicAdd(hw + (b >> 1), 1u << (16 * (b & 1)));
       } else if (mode == 2) {
         atomicAdd(hw + 7, 1u);
+      } else if (mode == 4) {
+        int b = min(max(__float2int_rz((x + 4.0f) * 64.0f), 0), 511);
+        atomicAdd(hw + b, 1u);
+      } else if (mode == 5) {
+        int b = min(max(__float2int_rz((x + 4.0f) * 128.0f), 0), 1023);
+        atomicAdd(hw2 + b, 1u);
+      } else if (mode == 6) {
+        int b = min(max(__float2int_rz((x + 4.0f) * 128.0f), 0), 1023);
+        unsigned addr = (unsigned)__cvta_generic_to_shared(hw + (b >> 1));
+        asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(addr), "r"(1u << (16 * (b & 1))));
+      } else if (mode == 7) {
+        int b = min(max(__float2int_rz((x + 4.0f) * 128.0f), 0), 1023);
+        atomicAdd(hw + (b & 511), 1u << (16 * (b >> 9)));
       } else {
         int b = min(max(__float2int_rz((x + 4.0f) * 128.0f), 0), 1023);
         unsigned peers = __match_any_sync(0xffffffffu, b);
@@ -50,11 +64,12 @@ int main() {
   for (size_t i = 0; i < n; ++i) { float a = 0; for (int j = 0; j < 12; ++j) { s = s * 1664525u + 1013904223u; a += (s >> 8) * (1.0f / 16777216.0f); } h[i] = a - 6.0f; }
   cudaMalloc(&d, n * 4); cudaMemcpy(d, h, n * 4, cudaMemcpyHostToDevice);
   cudaMalloc(&o, nb * 8); cudaMalloc(&sink, 4);
-  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-  for (int mode = 0; mode < 4; ++mode) {
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  for (int mode = 0; mode < 8; ++mode) {
+    if (mode == 3) continue;
     const int iters = 20;
-    k<<<nb, 576, 40 * 1024>>>(mode, 2, d, o, sink);
-    k<<<nb, 576, 40 * 1024>>>(mode, iters, d, o, sink);
+    k<<<nb, 576, 80 * 1024>>>(mode, 2, d, o, sink);
+    k<<<nb, 576, 80 * 1024>>>(mode, iters, d, o, sink);
     cudaDeviceSynchronize();
     long long ho[148]; cudaMemcpy(ho, o, nb * 8, cudaMemcpyDeviceToHost);
     double avg = 0; for (int i = 0; i < nb; ++i) avg += ho[i]; avg /= nb;
