@@ -109,14 +109,18 @@ template <> struct Math<float> {
   }
   static MCZ_HD float exp10(float x) {
 #if defined(__CUDA_ARCH__)
-    return exp2f(x * 3.3219280948873623f);
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 3.3219280948873623f));   // MUFU.EX2, 2 ulp
+    return r;
 #else
     return ::powf(10.0f, x);
 #endif
   }
   static MCZ_HD float sqrt(float x) {
 #if defined(__CUDA_ARCH__)
-    return __fsqrt_rn(x);
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));                        // MUFU.SQRT, 1 ulp
+    return r;
 #else
     return ::sqrtf(x);
 #endif

@@ -36,7 +36,8 @@ MCZ_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, ui
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
   const float u1 = __uint_as_float((a >> 9) | 0x3f800000u) - 0.99999994f;
   const float u2 = __uint_as_float((b >> 9) | 0x3f800000u) - 1.5f;        // [-0.5, 0.5)
-  const float r = __fsqrt_rn(fmaxf(-1.3862943611198906f * __log2f(u1), 0.0f));   // sqrt(-2 ln u1)
+  float r;                                                                       // sqrt(-2 ln u1)
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaxf(-1.3862943611198906f * __log2f(u1), 0.0f)));
   float sn, cs;
   __sincosf(6.283185307179586f * u2, &sn, &cs);
   z0 = r * cs;

@@ -534,6 +534,7 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
   sel_count(SEL_FAST);
   float bmn[3], bmx[3];
   unsigned nmin[3];
+  // (crowded ranges: sel_finish makes one more pass for the min / max / tie count of their members)
   sel_finish<PACK16>(w, scale, nLs, P, false, bmn, bmx, nmin, pct);
 }
 
