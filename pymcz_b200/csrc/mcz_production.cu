@@ -57,7 +57,7 @@ struct Ctrl {
   int any_valid_kd;
   float line[2 * NLINES];
   float2 redf[2 * PW];
-  int acc[3][2];           // fixed-point block sums of the two KK04 convergence measures
+  int acc[3][4];           // fixed-point block sums: two KK04 convergence measures x two trips per barrier
 };
 static_assert(sizeof(Ctrl) <= CTRL_BYTES, "control block too large");
 
@@ -107,10 +107,29 @@ __device__ __forceinline__ void block_sum2_fx(float s1, float s2, bool nan, Ctrl
     atomicAdd(&ctrl->acc[ph][1], q2);
   }
   const int nx = ph == 2 ? 0 : ph + 1;
-  if (threadIdx.x == 0) { ctrl->acc[nx][0] = 0; ctrl->acc[nx][1] = 0; }
+  if (threadIdx.x < 4) ctrl->acc[nx][threadIdx.x] = 0;
   anynan = __syncthreads_or(nan);
   t1 = ctrl->acc[ph][0];
   t2 = ctrl->acc[ph][1];
+  ph = nx;
+}
+
+// Same for four sums (two loops x two trips per barrier); `nanbits` is OR-ed over the block.
+__device__ __forceinline__ void block_sum4_fx(const float s[4], unsigned nanbits, Ctrl* ctrl, int& ph,
+                                              int t[4], bool& anynan) {
+  const int lane = threadIdx.x & 31;
+  int q[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) q[k] = __reduce_add_sync(0xffffffffu, __float2int_rn(s[k] * 65536.0f));
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) atomicAdd(&ctrl->acc[ph][k], q[k]);
+  }
+  const int nx = ph == 2 ? 0 : ph + 1;
+  if (threadIdx.x < 4) ctrl->acc[nx][threadIdx.x] = 0;
+  anynan = __syncthreads_or(nanbits != 0u);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) t[k] = ctrl->acc[ph][k];
   ph = nx;
 }
 
@@ -203,7 +222,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
     if (g >= p.G) break;
     if (tid < NLINES) ctrl->line[tid] = p.meas[g * NLINES + tid];
     else if (tid < 2 * NLINES) ctrl->line[tid] = p.err[g * NLINES + (tid - NLINES)];
-    if (tid == 0) { ctrl->flags = 0u; ctrl->acc[0][0] = 0; ctrl->acc[0][1] = 0; }
+    if (tid == 0) { ctrl->flags = 0u; ctrl->acc[0][0] = 0; ctrl->acc[0][1] = 0; ctrl->acc[0][2] = 0; ctrl->acc[0][3] = 0; }
     __syncthreads();
     float lm[NUSED], le[NUSED];
     uint32_t assumed = 0u;
@@ -330,43 +349,89 @@ production_kernel(const __grid_constant__ ProdParams p) {
         }
         const int itol1 = (int)(tol1 * 65536.0f), itol2 = (int)(tol2 * 65536.0f);
         int ph = 0;
+        // Two trips per barrier: trips a and b are computed back to back, their four sums are
+        // reduced together, then the reference's loop conditions are replayed trip by trip.  If a
+        // loop turns out to have ended after trip a, its state is put back to that point (logq of
+        // trip a is kept; Z follows from it).
         while (act1 || act2) {
-          float s1 = 0.0f, s2 = 0.0f;
-          bool nan1 = false, nan2 = false;
+          float sm4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+          unsigned nanb = 0u;
+          float lq1a[SLOTS], lq2a[SLOTS];
           if (act1) {
 #pragma unroll
             for (int i = 0; i < SLOTS; ++i) {                            // metscales.py:1112-1118
-              const float lq = (num0[i] + Z1[i] * num1[i]) * fast_rcp(den0[i] + Z1[i] * den1[i]);
-              Z1[i] = cA[i] - lq * cB[i];
-              const float d = fabsf(lq - lq1[i]);
-              lq1[i] = lq;
-              nan1 = nan1 || (d != d);
-              s1 += fminf(d, 8.0f);
+              float lq = (num0[i] + Z1[i] * num1[i]) * fast_rcp(den0[i] + Z1[i] * den1[i]);
+              float z = cA[i] - lq * cB[i];
+              float d = fabsf(lq - lq1[i]);
+              nanb |= (d != d) ? 1u : 0u;
+              sm4[0] += fminf(d, 8.0f);
+              lq1a[i] = lq;
+              const float lqb = (num0[i] + z * num1[i]) * fast_rcp(den0[i] + z * den1[i]);
+              Z1[i] = cA[i] - lqb * cB[i];
+              d = fabsf(lqb - lq);
+              nanb |= (d != d) ? 2u : 0u;
+              sm4[1] += fminf(d, 8.0f);
+              lq1[i] = lqb;
             }
           }
           if (act2) {
 #pragma unroll
             for (int i = 0; i < SLOTS; ++i) {                            // metscales.py:1167-1178
-              const float lq = (num0[i] + Z2[i] * num1[i]) * fast_rcp(den0[i] + Z2[i] * den1[i]);
-              const bool lower = ((aux[i] & AUX_ZI_MASK) <= 1u) && (lq >= 6.7f) && (lq < 8.3f);
               const int s = i * PT + tid;
-              Z2[i] = (lower ? st2[s] : st0[s]) - lq * (lower ? st3[s] : st1[s]);
-              const float d = lq2[i] - lq;
-              lq2[i] = lq;
-              nan2 = nan2 || (d != d);
-              s2 += fminf(fmaxf(d, -8.0f), 8.0f);
+              const float u0 = st0[s], u1 = st1[s], l0 = st2[s], l1 = st3[s];
+              const bool lowz = (aux[i] & AUX_ZI_MASK) <= 1u;
+              float lq = (num0[i] + Z2[i] * num1[i]) * fast_rcp(den0[i] + Z2[i] * den1[i]);
+              bool lower = lowz && (lq >= 6.7f) && (lq < 8.3f);
+              float z = (lower ? l0 : u0) - lq * (lower ? l1 : u1);
+              float d = lq2[i] - lq;
+              nanb |= (d != d) ? 4u : 0u;
+              sm4[2] += fminf(fmaxf(d, -8.0f), 8.0f);
+              lq2a[i] = lq;
+              const float lqb = (num0[i] + z * num1[i]) * fast_rcp(den0[i] + z * den1[i]);
+              lower = lowz && (lqb >= 6.7f) && (lqb < 8.3f);
+              Z2[i] = (lower ? l0 : u0) - lqb * (lower ? l1 : u1);
+              d = lq - lqb;
+              nanb |= (d != d) ? 8u : 0u;
+              sm4[3] += fminf(fmaxf(d, -8.0f), 8.0f);
+              lq2[i] = lqb;
             }
           }
-          int t1, t2;
+          int t4[4];
           bool anynan;
-          block_sum2_fx(s1, s2, nan1 || nan2, ctrl, ph, t1, t2, anynan);
-          bool n1 = false, n2 = false;
-          if (anynan) {      // rare: find out which loop saw the NaN (a NaN mean stops that loop)
-            n1 = __syncthreads_or(nan1);
-            n2 = __syncthreads_or(nan2);
+          block_sum4_fx(sm4, nanb, ctrl, ph, t4, anynan);
+          unsigned nb = 0u;
+          if (anynan) {      // rare: which loop / trip saw the NaN (a NaN mean stops that loop)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) nb |= __syncthreads_or((nanb >> k) & 1u) ? (1u << k) : 0u;
           }
-          if (act1) { ++ii1; act1 = !n1 && (t1 > itol1) && ii1 < 100; }                 // metscales.py:1111,1117
-          if (act2) { ++ii2; act2 = !n2 && ((t2 < 0 ? -t2 : t2) > itol2) && ii2 < 100; } // metscales.py:1166,1177
+          if (act1) {                                                     // metscales.py:1111,1117
+            ++ii1;
+            if ((nb & 1u) || !(t4[0] > itol1) || ii1 >= 100) {
+              act1 = false;       // ended after trip a: undo trip b
+#pragma unroll
+              for (int i = 0; i < SLOTS; ++i) { lq1[i] = lq1a[i]; Z1[i] = cA[i] - lq1a[i] * cB[i]; }
+            } else {
+              ++ii1;
+              act1 = !(nb & 2u) && (t4[1] > itol1) && ii1 < 100;
+            }
+          }
+          if (act2) {                                                     // metscales.py:1166,1177
+            ++ii2;
+            if ((nb & 4u) || !((t4[2] < 0 ? -t4[2] : t4[2]) > itol2) || ii2 >= 100) {
+              act2 = false;
+#pragma unroll
+              for (int i = 0; i < SLOTS; ++i) {
+                const int s = i * PT + tid;
+                const float lq = lq2a[i];
+                const bool lower = ((aux[i] & AUX_ZI_MASK) <= 1u) && (lq >= 6.7f) && (lq < 8.3f);
+                lq2[i] = lq;
+                Z2[i] = (lower ? st2[s] : st0[s]) - lq * (lower ? st3[s] : st1[s]);
+              }
+            } else {
+              ++ii2;
+              act2 = !(nb & 8u) && ((t4[3] < 0 ? -t4[3] : t4[3]) > itol2) && ii2 < 100;
+            }
+          }
           if (act1 && ii1 == DIVERGENCE_CHECK_TRIP) {
             // Early exit for galaxies whose N2Ha loop provably never converges (SURVEY A.3 item 4:
             // log N2Ha >~ -0.35).  Per sample the trip is the Moebius map
