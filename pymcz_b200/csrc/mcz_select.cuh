@@ -102,6 +102,8 @@ __device__ __forceinline__ float np_lerp_f(float a, float b, double t) {
 struct SelWarp {
   const float* v;          // the column, Npad readable floats, [N, Npad) NaN
   int Npad;
+  int ngroups;             // 128-sample groups select_in_interval scans: Npad/128, or fewer once the
+  int nmine;               // members of the crowded ranges were compacted (nmine = this lane's count)
   unsigned* hist;          // FineHist<>::WORDS words
   unsigned* ccount;        // candidate counter
   float* clist;            // 64 candidates
@@ -187,13 +189,13 @@ __device__ void select_in_interval(const SelWarp& w, float lo, float hi, unsigne
       return;
     }
     FH::zero(w.hist, w.lane);
-    for (int s0 = 4 * w.lane; s0 < w.Npad; s0 += 128) {
-      const float4 x4 = *reinterpret_cast<const float4*>(w.v + s0);
+    for (int g = 0; g < w.ngroups; ++g) {
+      const float4 x4 = *reinterpret_cast<const float4*>(w.v + 4 * w.lane + 128 * g);
       const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float x = xs[j];
-        if (x >= lo && x <= hi) FH::add(w.hist, fine_index(x, scale, nLs));      // NaN fails both
+        if (4 * g + j < w.nmine && x >= lo && x <= hi) FH::add(w.hist, fine_index(x, scale, nLs));   // NaN fails
       }
     }
     unsigned lex, ltot, n;
@@ -207,14 +209,14 @@ __device__ void select_in_interval(const SelWarp& w, float lo, float hi, unsigne
     __syncwarp();
     const unsigned span = (unsigned)(fb - fa);
     if (m <= 64u) {
-      for (int s0 = 4 * w.lane; s0 < w.Npad; s0 += 128) {
-        const float4 x4 = *reinterpret_cast<const float4*>(w.v + s0);
+      for (int g = 0; g < w.ngroups; ++g) {
+        const float4 x4 = *reinterpret_cast<const float4*>(w.v + 4 * w.lane + 128 * g);
         const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float x = xs[j];
           const unsigned d = (unsigned)(fine_index(x, scale, nLs) - fa);
-          if (x >= lo && x <= hi && d <= span) w.clist[atomicAdd(w.ccount, 1u) & 63u] = x;
+          if (4 * g + j < w.nmine && x >= lo && x <= hi && d <= span) w.clist[atomicAdd(w.ccount, 1u) & 63u] = x;
         }
       }
       __syncwarp();
@@ -229,14 +231,14 @@ __device__ void select_in_interval(const SelWarp& w, float lo, float hi, unsigne
     // crowded: narrow to the exact range of the members of [fa, fb]
     float mn = pinf, mx = ninf;
     int neq = 0;
-    for (int s0 = 4 * w.lane; s0 < w.Npad; s0 += 128) {
-      const float4 x4 = *reinterpret_cast<const float4*>(w.v + s0);
+    for (int g = 0; g < w.ngroups; ++g) {
+      const float4 x4 = *reinterpret_cast<const float4*>(w.v + 4 * w.lane + 128 * g);
       const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float x = xs[j];
         const unsigned d = (unsigned)(fine_index(x, scale, nLs) - fa);
-        if (x >= lo && x <= hi && d <= span) {
+        if (4 * g + j < w.nmine && x >= lo && x <= hi && d <= span) {
           if (x < mn) { mn = x; neq = 1; }
           else if (x == mn) ++neq;
           mx = fmaxf(mx, x);
@@ -356,58 +358,13 @@ __device__ __forceinline__ void sel_tests(const SelPlan& P, bool gathered, int t
   }
 }
 
-// Per-warp statistics pass: sum of the finite samples (if want_sum) and, for the crowded ranges,
-// min / max of their members and how many equal the min.
-__device__ __forceinline__ void sel_stats_pass(const SelWarp& w, float scale, float nLs, const SelPlan& P,
-                                               bool want_sum, double& total, float bmn[3], float bmx[3],
-                                               unsigned nmin[3]) {
-  const float pinf = __int_as_float(0x7f800000), ninf = __int_as_float(0xff800000);
-  int tlo[3];
-  unsigned tsp[3];
-  sel_tests(P, false, tlo, tsp);
-  int bcm[3] = {0, 0, 0};
-  float sum = 0.0f;
-#pragma unroll
-  for (int r = 0; r < 3; ++r) { bmn[r] = pinf; bmx[r] = ninf; }
-  for (int s0 = 4 * w.lane; s0 < w.Npad; s0 += 128) {
-    const float4 x4 = *reinterpret_cast<const float4*>(w.v + s0);
-    const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float x = xs[j];
-      if (finite_f(x)) {
-        sum += x;
-        const int f = fine_index(x, scale, nLs);
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-          if ((unsigned)(f - tlo[r]) <= tsp[r]) {
-            if (x < bmn[r]) { bmn[r] = x; bcm[r] = 1; }
-            else if (x == bmn[r]) ++bcm[r];
-            bmx[r] = fmaxf(bmx[r], x);
-          }
-      }
-    }
-  }
-  if (want_sum) total = warp_sum((double)sum);
-#pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    float gm = bmn[r];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      gm = fminf(gm, __shfl_xor_sync(0xffffffffu, gm, o));
-      bmx[r] = fmaxf(bmx[r], __shfl_xor_sync(0xffffffffu, bmx[r], o));
-    }
-    nmin[r] = (unsigned)__reduce_add_sync(0xffffffffu, bmn[r] == gm ? bcm[r] : 0);
-    bmn[r] = gm;
-  }
-}
-
 // Stage "finish": the gathered candidates are in w.clist (P.ncand of them, any order); sort them,
 // read the order statistics, resolve crowded ranges, interpolate.
+// For crowded ranges the caller supplies the min / max of their members and how many equal the
+// min, and has compacted those members to the front of each lane's slots (w.nmine, w.ngroups).
 template <bool PACK16>
-__device__ __forceinline__ void sel_finish(const SelWarp& w, float scale, float nLs, const SelPlan& P,
-                                           bool have_stats, float bmn[3], float bmx[3], unsigned nmin[3],
-                                           float pct[3]) {
+__device__ __forceinline__ void sel_finish(const SelWarp& w, const SelPlan& P, const float bmn[3],
+                                           const float bmx[3], const unsigned nmin[3], float pct[3]) {
   const float pinf = __int_as_float(0x7f800000);
   const int lane = w.lane;
   __syncwarp();
@@ -436,10 +393,6 @@ __device__ __forceinline__ void sel_finish(const SelWarp& w, float scale, float 
     // A crowded range is exactly the set of finite values in [bmn, bmx] (the fine index is
     // monotone), so a rank inside it is an order statistic of that interval.
     sel_count(SEL_CROWDED);
-    if (!have_stats) {
-      double dummy;
-      sel_stats_pass(w, scale, nLs, P, false, dummy, bmn, bmx, nmin);
-    }
 #pragma unroll 1
     for (int q = 0; q < 3; ++q) {
       const int r = P.rq[q];
@@ -514,28 +467,87 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
   if (lane == 0) *w.ccount = 0u;
   __syncwarp();
   float sum = 0.0f;
+  const float pinf = __int_as_float(0x7f800000), ninf = __int_as_float(0xff800000);
+  float bmn[3] = {pinf, pinf, pinf}, bmx[3] = {ninf, ninf, ninf};
+  unsigned nmin[3] = {0u, 0u, 0u};
+  w.ngroups = Npad / 128;
+  w.nmine = Npad;
+  if (!(P.crowded[0] || P.crowded[1] || P.crowded[2])) {
 #pragma unroll 2
-  for (int s0 = 4 * lane; s0 < Npad; s0 += 128) {
-    const float4 x4 = *reinterpret_cast<const float4*>(v + s0);
-    const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+    for (int s0 = 4 * lane; s0 < Npad; s0 += 128) {
+      const float4 x4 = *reinterpret_cast<const float4*>(v + s0);
+      const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float x = xs[j];
-      const int f = fine_index(x, scale, nLs);
-      const bool fin = finite_f(x);
-      const bool hit = ((unsigned)(f - tlo[0]) <= tsp[0]) || ((unsigned)(f - tlo[1]) <= tsp[1]) ||
-                       ((unsigned)(f - tlo[2]) <= tsp[2]);
-      sum += fin ? x : 0.0f;
-      if (hit && fin) w.clist[atomicAdd(w.ccount, 1u) & 63u] = x;
+      for (int j = 0; j < 4; ++j) {
+        const float x = xs[j];
+        const int f = fine_index(x, scale, nLs);
+        const bool fin = finite_f(x);
+        const bool hit = ((unsigned)(f - tlo[0]) <= tsp[0]) || ((unsigned)(f - tlo[1]) <= tsp[1]) ||
+                         ((unsigned)(f - tlo[2]) <= tsp[2]);
+        sum += fin ? x : 0.0f;
+        if (hit && fin) w.clist[atomicAdd(w.ccount, 1u) & 63u] = x;
+      }
+    }
+  } else {
+    // Some range is crowded (ties, end bins).  Same pass, but the members of the crowded ranges
+    // are also (a) reduced to min / max / number equal to the min and (b) compacted, in place, to
+    // the front of this lane's own slots: from here on the column is only needed for them, so
+    // the follow-up rounds of select_in_interval scan a few groups instead of the whole column.
+    int clo[3];
+    unsigned csp[3];
+    sel_tests(P, false, clo, csp);
+    int bcm[3] = {0, 0, 0};
+    int cw = 0;                                  // members compacted by this lane so far
+    float* const vm = const_cast<float*>(v);
+    for (int s0 = 4 * lane; s0 < Npad; s0 += 128) {
+      const float4 x4 = *reinterpret_cast<const float4*>(v + s0);
+      const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float x = xs[j];
+        if (finite_f(x)) {
+          sum += x;
+          const int f = fine_index(x, scale, nLs);
+          const bool hit = ((unsigned)(f - tlo[0]) <= tsp[0]) || ((unsigned)(f - tlo[1]) <= tsp[1]) ||
+                           ((unsigned)(f - tlo[2]) <= tsp[2]);
+          if (hit) w.clist[atomicAdd(w.ccount, 1u) & 63u] = x;
+          bool member = false;
+#pragma unroll
+          for (int r = 0; r < 3; ++r)
+            if ((unsigned)(f - clo[r]) <= csp[r]) {
+              member = true;
+              if (x < bmn[r]) { bmn[r] = x; bcm[r] = 1; }
+              else if (x == bmn[r]) ++bcm[r];
+              bmx[r] = fmaxf(bmx[r], x);
+            }
+          if (member) {                          // write position <= read position: safe in place
+            vm[4 * lane + 128 * (cw >> 2) + (cw & 3)] = x;
+            ++cw;
+          }
+        }
+      }
+    }
+    int mxc = cw;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mxc = max(mxc, __shfl_xor_sync(0xffffffffu, mxc, o));
+    w.ngroups = (mxc + 3) >> 2;
+    w.nmine = cw;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      float gm = bmn[r];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        gm = fminf(gm, __shfl_xor_sync(0xffffffffu, gm, o));
+        bmx[r] = fmaxf(bmx[r], __shfl_xor_sync(0xffffffffu, bmx[r], o));
+      }
+      nmin[r] = (unsigned)__reduce_add_sync(0xffffffffu, bmn[r] == gm ? bcm[r] : 0);
+      bmn[r] = gm;
     }
   }
   if (!(warp_sum((double)sum) > 0.0)) { sel_count(SEL_TRIVIAL); status = ST_NONPOS; return; }   // mcz.py:282-285
   status = ST_OK;
   sel_count(SEL_FAST);
-  float bmn[3], bmx[3];
-  unsigned nmin[3];
-  // (crowded ranges: sel_finish makes one more pass for the min / max / tie count of their members)
-  sel_finish<PACK16>(w, scale, nLs, P, false, bmn, bmx, nmin, pct);
+  sel_finish<PACK16>(w, P, bmn, bmx, nmin, pct);
 }
 
 }  // namespace mcz
