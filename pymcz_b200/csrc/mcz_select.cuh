@@ -48,6 +48,10 @@ template <bool PACK16> struct FineHist {
     if (PACK16) atomicAdd(h + (f >> 1), 1u << ((f & 1) << 4));
     else atomicAdd(h + f, 1u);
   }
+  static __device__ __forceinline__ void add_n(unsigned* h, int f, unsigned n) {      // n < 65536 when PACK16
+    if (PACK16) atomicAdd(h + (f >> 1), n << ((f & 1) << 4));
+    else atomicAdd(h + f, n);
+  }
   static __device__ __forceinline__ unsigned get(const unsigned* h, int f) {
     if (PACK16) return (h[f >> 1] >> ((f & 1) << 4)) & 0xffffu;
     return h[f];
@@ -264,13 +268,26 @@ __device__ void select_in_interval(const SelWarp& w, float lo, float hi, unsigne
 // Robust fine-index range of a column from its first 64 samples (i.i.d. draws: any fixed subset is
 // a fair subsample): [q06 - 1.5 w, q94 + 1.5 w], w = q94 - q06, so that a few wild values do not
 // stretch the index.  Returns false when that prefix has fewer than 8 finite values or is constant.
-__device__ __forceinline__ bool subsample_range(const float* __restrict__ v, int lane, float& scale, float& nLs) {
+// Also reports a heavily repeated value of the prefix (>= 5 equal samples out of 64), e.g. the
+// E(B-V) = 1e-5 clamp: the histogram pass counts such a value with a vote instead of one shared
+// atomic per sample (same-address atomics serialise).
+__device__ __forceinline__ bool subsample_range(const float* __restrict__ v, int lane, float& scale, float& nLs,
+                                                bool& has_tie, float& tie) {
   const float pinf = __int_as_float(0x7f800000);
   float a = v[lane], b = v[lane + 32];
   a = finite_f(a) ? a : pinf;
   b = finite_f(b) ? b : pinf;
   const int m = __popc(__ballot_sync(0xffffffffu, a < pinf)) + __popc(__ballot_sync(0xffffffffu, b < pinf));
   sort64_regs(a, b, lane);
+  {
+    // sorted[i] == sorted[i + 4]  <=>  at least five copies of that value
+    const float a4 = sorted64_get(a, b, (unsigned)lane + 4u);
+    const float b4 = sorted64_get(a, b, min((unsigned)lane + 36u, 63u));
+    const unsigned ma = __ballot_sync(0xffffffffu, a < pinf && a == a4);
+    const unsigned mb = __ballot_sync(0xffffffffu, lane < 28 && b < pinf && b == b4);
+    has_tie = (ma | mb) != 0u;
+    tie = ma ? __shfl_sync(0xffffffffu, a, __ffs(ma) - 1) : __shfl_sync(0xffffffffu, b, mb ? __ffs(mb) - 1 : 0);
+  }
   if (m < 8) return false;
   float qlo = sorted64_get(a, b, (unsigned)(0.06f * (float)(m - 1)));
   float qhi = sorted64_get(a, b, (unsigned)(m - 1) - (unsigned)(0.06f * (float)(m - 1)));
@@ -296,15 +313,24 @@ struct SelPlan {
   int rq[3];               // range of pair q
   bool crowded[3];
   unsigned ncand;
+  // a heavily repeated value T (found in the 64-sample prefix, counted by vote in pass H): its ntie
+  // copies are not gathered; the range that holds T's fine bin merges them back by rank
+  int tie_range;           // -1: none
+  unsigned ntie;
+  float tie;
 };
 
 template <bool PACK16>
-__device__ __forceinline__ void sel_make_plan(const SelWarp& w, SelPlan& P) {
+__device__ __forceinline__ void sel_make_plan(const SelWarp& w, SelPlan& P, bool has_tie, float tie, int ftie,
+                                              unsigned ntie) {
   unsigned lex, ltot, un;
   fine_prefix<PACK16>(w, lex, ltot, un);
   P.n = (int)un;
   P.nr = 0;
   P.ncand = 0;
+  P.tie_range = -1;
+  P.ntie = 0;
+  P.tie = Math<float>::nan();
   if (P.n == 0) return;
   const double qs[3] = {16.0 / 100.0, 50.0 / 100.0, 84.0 / 100.0};                  // mcz.py:288
 #pragma unroll
@@ -334,15 +360,26 @@ __device__ __forceinline__ void sel_make_plan(const SelWarp& w, SelPlan& P) {
     P.rq[q] = nr - 1;
   }
   P.nr = nr;
-  // gather the ranges that fit in the 64-candidate list; the others are "crowded"
+  if (has_tie && ntie > 0u) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+      if (r < nr && ftie >= P.rlo[r] && ftie <= P.rhi[r]) { P.tie_range = r; P.ntie = ntie; P.tie = tie; }
+  }
+  // gather the ranges that fit in the 64-candidate list (not counting the copies of the tie value);
+  // the others are "crowded"
   unsigned ncand = 0;
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
     P.crowded[r] = false;
     if (r < nr) {
-      if (ncand + P.rM[r] <= 64u) ncand += P.rM[r];
+      const unsigned need = P.rM[r] - (r == P.tie_range ? P.ntie : 0u);
+      if (ncand + need <= 64u) ncand += need;
       else P.crowded[r] = true;
     }
+  }
+  if (P.tie_range >= 0) {
+    const bool cr = P.tie_range == 0 ? P.crowded[0] : (P.tie_range == 1 ? P.crowded[1] : P.crowded[2]);
+    if (cr) { P.tie_range = -1; P.ntie = 0; P.tie = Math<float>::nan(); }   // still crowded: ties stay members
   }
   P.ncand = ncand;
 }
@@ -379,14 +416,30 @@ __device__ __forceinline__ void sel_finish(const SelWarp& w, const SelPlan& P, c
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
       below[r] = acc;
-      if (r < P.nr && !P.crowded[r]) acc += P.rM[r];
+      if (r < P.nr && !P.crowded[r]) acc += P.rM[r] - (r == P.tie_range ? P.ntie : 0u);
+    }
+    // tie range: candidates below the tie value (the sorted list holds the range at [tb, tb + tm))
+    unsigned tless = 0, tb = 0, tm = 0;
+    if (P.tie_range >= 0) {
+      tb = P.tie_range == 0 ? below[0] : (P.tie_range == 1 ? below[1] : below[2]);
+      tm = (P.tie_range == 0 ? P.rM[0] : (P.tie_range == 1 ? P.rM[1] : P.rM[2])) - P.ntie;
+      const bool ina = (unsigned)lane - tb < tm && ca < P.tie;
+      const bool inb = (unsigned)(lane + 32) - tb < tm && cb < P.tie;
+      tless = __popc(__ballot_sync(0xffffffffu, ina)) + __popc(__ballot_sync(0xffffffffu, inb));
     }
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
       const int r = P.rq[i >> 1];
       const unsigned bl = r == 0 ? below[0] : (r == 1 ? below[1] : below[2]);
       const unsigned E = r == 0 ? P.rE[0] : (r == 1 ? P.rE[1] : P.rE[2]);
-      res[i] = sorted64_get(ca, cb, (bl + P.rk[i] - E) & 63u);
+      unsigned rho = P.rk[i] - E;                   // rank inside the range
+      bool is_tie = false;
+      if (r == P.tie_range) {
+        if (rho >= tless && rho < tless + P.ntie) is_tie = true;
+        else if (rho >= tless + P.ntie) rho -= P.ntie;
+      }
+      const float val = sorted64_get(ca, cb, (bl + rho) & 63u);
+      res[i] = is_tie ? P.tie : val;
     }
   }
   if (P.crowded[0] || P.crowded[1] || P.crowded[2]) {
@@ -441,23 +494,44 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
   pct[0] = pct[1] = pct[2] = nanf_;
   nvalid = 0;
   sel_count(SEL_TOTAL);
-  float scale, nLs;
-  if (!subsample_range(v, lane, scale, nLs)) {
+  float scale, nLs, tie;
+  bool has_tie;
+  unsigned ntie_total = 0;
+  if (!subsample_range(v, lane, scale, nLs, has_tie, tie)) {
     sel_count(SEL_NO_SUBSAMPLE);
+    has_tie = false;
     if (!exact_range(w, scale, nLs)) { status = ST_EMPTY; return; }                 // mcz.py:277-280
   }
   // ---- pass H: the 1024-bin histogram (out-of-range finite values land in the end bins)
   FH::zero(hist, lane);
+  if (!has_tie) {
 #pragma unroll 2
-  for (int s0 = 4 * lane; s0 < Npad; s0 += 128) {
-    const float4 x4 = *reinterpret_cast<const float4*>(v + s0);
-    const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+    for (int s0 = 4 * lane; s0 < Npad; s0 += 128) {
+      const float4 x4 = *reinterpret_cast<const float4*>(v + s0);
+      const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (finite_f(xs[j])) FH::add(hist, fine_index(xs[j], scale, nLs));            // mcz.py:273
+      for (int j = 0; j < 4; ++j)
+        if (finite_f(xs[j])) FH::add(hist, fine_index(xs[j], scale, nLs));          // mcz.py:273
+    }
+  } else {
+    int ntie = 0;
+    for (int s0 = 4 * lane; s0 < Npad; s0 += 128) {
+      const float4 x4 = *reinterpret_cast<const float4*>(v + s0);
+      const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool is_tie = xs[j] == tie;
+        ntie += is_tie ? 1 : 0;
+        if (finite_f(xs[j]) && !is_tie) FH::add(hist, fine_index(xs[j], scale, nLs));
+      }
+    }
+    ntie = __reduce_add_sync(0xffffffffu, ntie);
+    if (lane == 0 && ntie > 0) FH::add_n(hist, fine_index(tie, scale, nLs), (unsigned)ntie);
+    ntie_total = (unsigned)ntie;
   }
   SelPlan P;
-  sel_make_plan<PACK16>(w, P);
+  sel_make_plan<PACK16>(w, P, has_tie, tie, has_tie ? fine_index(tie, scale, nLs) : 0, ntie_total);
+  const float skip = P.tie;           // NaN unless a tie value is merged back by rank (never equal then)
   nvalid = P.n;
   if (P.n == 0) { sel_count(SEL_TRIVIAL); status = ST_EMPTY; return; }              // mcz.py:277-280
   // ---- pass G: gather the members of the uncrowded ranges, sum everything
@@ -485,7 +559,7 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
         const bool hit = ((unsigned)(f - tlo[0]) <= tsp[0]) || ((unsigned)(f - tlo[1]) <= tsp[1]) ||
                          ((unsigned)(f - tlo[2]) <= tsp[2]);
         sum += fin ? x : 0.0f;
-        if (hit && fin) w.clist[atomicAdd(w.ccount, 1u) & 63u] = x;
+        if (hit && fin && x != skip) w.clist[atomicAdd(w.ccount, 1u) & 63u] = x;
       }
     }
   } else {
@@ -510,7 +584,7 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
           const int f = fine_index(x, scale, nLs);
           const bool hit = ((unsigned)(f - tlo[0]) <= tsp[0]) || ((unsigned)(f - tlo[1]) <= tsp[1]) ||
                            ((unsigned)(f - tlo[2]) <= tsp[2]);
-          if (hit) w.clist[atomicAdd(w.ccount, 1u) & 63u] = x;
+          if (hit && x != skip) w.clist[atomicAdd(w.ccount, 1u) & 63u] = x;
           bool member = false;
 #pragma unroll
           for (int r = 0; r < 3; ++r)
