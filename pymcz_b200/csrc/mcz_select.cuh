@@ -9,11 +9,14 @@
 //   pass G  gather of the members of the (at most three) fine-index ranges that hold the target
 //           ranks -- a rank pair (k, k+1) always lies in one bin or in two bins with nothing in
 //           between -- followed by a 64-key bitonic sort in registers.
-// The first round uses a robust range from the first 64 samples, [q06 - 1.5w, q94 + 1.5w]; values
-// outside are clamped into the end bins.  A range that holds more than 64 samples (ties such as
-// the clamped E(B-V) = 1e-5, or an end bin full of outliers) is "crowded": pass G records the
-// exact min / max of its members and how many equal the min (a tie is then answered at once),
-// and select_in_interval() runs further rounds restricted to [min, max].  Every such round leaves
+// The first round uses a robust range from the first 64 samples, [q06 - 1.5w, q94 + 1.5w] cut to
+// that prefix's own [min, max]; values outside are clamped into the end bins.  Each of the (at
+// most three) target ranges may hold 64 candidates: one shared list and one sort when they fit in
+// 64 together, one list and one sort per range otherwise.  A value that repeats heavily in the
+// prefix (the clamped E(B-V) = 1e-5) is counted by vote, left out of the lists and merged back by
+// rank.  A range that still holds more than 64 samples is "crowded": pass G records the exact
+// min / max of its members and how many equal the min (a tie is then answered at once), and
+// select_in_interval() runs further rounds restricted to [min, max].  Every such round leaves
 // at least two non-empty bins, so the member count strictly decreases and the loop terminates.
 #pragma once
 
@@ -110,8 +113,12 @@ struct SelWarp {
   int nmine;               // members of the crowded ranges were compacted (nmine = this lane's count)
   unsigned* hist;          // FineHist<>::WORDS words
   unsigned* ccount;        // candidate counter
-  float* clist;            // 64 candidates
+  float* clist;            // 64 candidates (select_in_interval)
+  float* glist;            // 192 candidates of pass G; aliases hist, which the plan has consumed by then
   int lane;
+#ifdef MCZ_COLTIME_DUMP
+  mutable int dbg;
+#endif
 };
 
 __device__ __forceinline__ int fine_index(float x, float scale, float nLs) {
@@ -186,6 +193,9 @@ __device__ void select_in_interval(const SelWarp& w, float lo, float hi, unsigne
   bool haveA = false;
   for (;;) {
     sel_count(SEL_ROUNDS);
+#ifdef MCZ_COLTIME_DUMP
+    w.dbg += 256;
+#endif
     const float scale = (float)FB / (hi - lo), nLs = -lo * scale;
     if (!(hi > lo) || !finite_f(scale) || !finite_f(nLs)) {   // all equal (or denormal spacing)
       if (!haveA) outA = lo;
@@ -294,7 +304,14 @@ __device__ __forceinline__ bool subsample_range(const float* __restrict__ v, int
   if (!(qhi > qlo)) { qlo = sorted64_get(a, b, 0u); qhi = sorted64_get(a, b, (unsigned)(m - 1)); }
   if (!(qhi > qlo)) return false;
   const float ww = 1.5f * (qhi - qlo);
-  const float L = qlo - ww, H = qhi + ww;
+  float L = qlo - ww, H = qhi + ww;
+  if (m >= 48) {
+    // A target rank lies outside the prefix's own [min, max] with probability 0.84^m per column,
+    // so the index need not reach further: bimodal columns (two branches of a diagnostic) then
+    // keep bins fine enough for the 64-candidate lists.
+    L = fmaxf(L, sorted64_get(a, b, 0u));
+    H = fminf(H, sorted64_get(a, b, (unsigned)(m - 1)));
+  }
   scale = (float)FB / (H - L);
   nLs = -L * scale;
   return finite_f(scale) && finite_f(nLs);
@@ -311,7 +328,10 @@ struct SelPlan {
   int rlo[3], rhi[3];      // fine-index range
   unsigned rE[3], rM[3];   // samples below the range / inside it
   int rq[3];               // range of pair q
-  bool crowded[3];
+  bool crowded[3];         // more than 64 members: not gathered
+  unsigned need[3];        // members gathered for the range (0 if crowded)
+  unsigned loff[3];        // where its candidates start in the list
+  bool split;              // false: one list of <= 64 in all, one sort; true: one 64-list per range
   unsigned ncand;
   // a heavily repeated value T (found in the 64-sample prefix, counted by vote in pass H): its ntie
   // copies are not gathered; the range that holds T's fine bin merges them back by rank
@@ -365,15 +385,16 @@ __device__ __forceinline__ void sel_make_plan(const SelWarp& w, SelPlan& P, bool
     for (int r = 0; r < 3; ++r)
       if (r < nr && ftie >= P.rlo[r] && ftie <= P.rhi[r]) { P.tie_range = r; P.ntie = ntie; P.tie = tie; }
   }
-  // gather the ranges that fit in the 64-candidate list (not counting the copies of the tie value);
+  // a range is gathered if it has at most 64 members (not counting the copies of the tie value);
   // the others are "crowded"
   unsigned ncand = 0;
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
     P.crowded[r] = false;
+    P.need[r] = 0u;
     if (r < nr) {
       const unsigned need = P.rM[r] - (r == P.tie_range ? P.ntie : 0u);
-      if (ncand + need <= 64u) ncand += need;
+      if (need <= 64u) { P.need[r] = need; ncand += need; }
       else P.crowded[r] = true;
     }
   }
@@ -381,6 +402,10 @@ __device__ __forceinline__ void sel_make_plan(const SelWarp& w, SelPlan& P, bool
     const bool cr = P.tie_range == 0 ? P.crowded[0] : (P.tie_range == 1 ? P.crowded[1] : P.crowded[2]);
     if (cr) { P.tie_range = -1; P.ntie = 0; P.tie = Math<float>::nan(); }   // still crowded: ties stay members
   }
+  P.split = ncand > 64u;
+  P.loff[0] = 0u;
+  P.loff[1] = P.split ? 64u : P.need[0];
+  P.loff[2] = P.split ? 128u : P.need[0] + P.need[1];
   P.ncand = ncand;
 }
 
@@ -395,8 +420,8 @@ __device__ __forceinline__ void sel_tests(const SelPlan& P, bool gathered, int t
   }
 }
 
-// Stage "finish": the gathered candidates are in w.clist (P.ncand of them, any order); sort them,
-// read the order statistics, resolve crowded ranges, interpolate.
+// Stage "finish": the gathered candidates are in w.glist (range r at P.loff[r], P.need[r] of them,
+// any order); sort them, read the order statistics, resolve crowded ranges, interpolate.
 // For crowded ranges the caller supplies the min / max of their members and how many equal the
 // min, and has compacted those members to the front of each lane's slots (w.nmine, w.ngroups).
 template <bool PACK16>
@@ -405,24 +430,24 @@ __device__ __forceinline__ void sel_finish(const SelWarp& w, const SelPlan& P, c
   const float pinf = __int_as_float(0x7f800000);
   const int lane = w.lane;
   __syncwarp();
-  float ca = (unsigned)lane < P.ncand ? w.clist[lane] : pinf;
-  float cb = (unsigned)(lane + 32) < P.ncand ? w.clist[lane + 32] : pinf;
-  sort64_regs(ca, cb, lane);
   float res[6];
-  {
-    // candidates of lower gathered ranges come first in the sorted list
-    unsigned below[3];
-    unsigned acc = 0;
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      below[r] = acc;
-      if (r < P.nr && !P.crowded[r]) acc += P.rM[r] - (r == P.tie_range ? P.ntie : 0u);
-    }
+  for (int i = 0; i < 6; ++i) res[i] = pinf;
+  // one sort of the whole list (ranges are disjoint and ascending, so their candidates come out
+  // range after range), or one sort per range when the list is split
+  const int nsort = P.split ? P.nr : 1;
+#pragma unroll 1
+  for (int t = 0; t < nsort; ++t) {
+    const unsigned base = P.split ? 64u * (unsigned)t : 0u;
+    const unsigned cnt = P.split ? (t == 0 ? P.need[0] : (t == 1 ? P.need[1] : P.need[2])) : P.ncand;
+    float ca = (unsigned)lane < cnt ? w.glist[base + lane] : pinf;
+    float cb = (unsigned)(lane + 32) < cnt ? w.glist[base + lane + 32] : pinf;
+    sort64_regs(ca, cb, lane);
     // tie range: candidates below the tie value (the sorted list holds the range at [tb, tb + tm))
-    unsigned tless = 0, tb = 0, tm = 0;
-    if (P.tie_range >= 0) {
-      tb = P.tie_range == 0 ? below[0] : (P.tie_range == 1 ? below[1] : below[2]);
-      tm = (P.tie_range == 0 ? P.rM[0] : (P.tie_range == 1 ? P.rM[1] : P.rM[2])) - P.ntie;
+    unsigned tless = 0;
+    if (P.tie_range >= 0 && (!P.split || P.tie_range == t)) {
+      const unsigned tb = P.split ? 0u : (P.tie_range == 0 ? P.loff[0] : (P.tie_range == 1 ? P.loff[1] : P.loff[2]));
+      const unsigned tm = P.tie_range == 0 ? P.need[0] : (P.tie_range == 1 ? P.need[1] : P.need[2]);
       const bool ina = (unsigned)lane - tb < tm && ca < P.tie;
       const bool inb = (unsigned)(lane + 32) - tb < tm && cb < P.tie;
       tless = __popc(__ballot_sync(0xffffffffu, ina)) + __popc(__ballot_sync(0xffffffffu, inb));
@@ -430,7 +455,8 @@ __device__ __forceinline__ void sel_finish(const SelWarp& w, const SelPlan& P, c
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
       const int r = P.rq[i >> 1];
-      const unsigned bl = r == 0 ? below[0] : (r == 1 ? below[1] : below[2]);
+      if (P.split && r != t) continue;
+      const unsigned bl = P.split ? 0u : (r == 0 ? P.loff[0] : (r == 1 ? P.loff[1] : P.loff[2]));
       const unsigned E = r == 0 ? P.rE[0] : (r == 1 ? P.rE[1] : P.rE[2]);
       unsigned rho = P.rk[i] - E;                   // rank inside the range
       bool is_tie = false;
@@ -465,6 +491,15 @@ __device__ __forceinline__ void sel_finish(const SelWarp& w, const SelPlan& P, c
   pct[2] = np_lerp_f(res[4], res[5], P.gam[2]);       // 84th
 }
 
+// pass G: append a member of gathered range r (the one whose test f passes) to that range's list
+__device__ __forceinline__ void sel_put(const SelWarp& w, const SelPlan& P, int f, const int tlo[3],
+                                        const unsigned tsp[3], float x) {
+  const int r = ((unsigned)(f - tlo[0]) <= tsp[0]) ? 0 : (((unsigned)(f - tlo[1]) <= tsp[1]) ? 1 : 2);
+  const unsigned off = r == 0 ? P.loff[0] : (r == 1 ? P.loff[1] : P.loff[2]);
+  const unsigned pos = atomicAdd(w.ccount + r, 1u);
+  w.glist[(off + (pos & 63u)) & 255u] = x;
+}
+
 // Fine-index range of a column when the 64-sample estimate is not usable: the exact range.
 // Returns false for a column without finite values.
 __device__ __forceinline__ bool exact_range(const SelWarp& w, float& scale, float& nLs) {
@@ -490,6 +525,7 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
   w.v = v; w.Npad = Npad; w.hist = hist; w.lane = lane;
   w.ccount = reinterpret_cast<unsigned*>(cand);
   w.clist = cand + 32;
+  w.glist = reinterpret_cast<float*>(hist);
   const float nanf_ = Math<float>::nan();
   pct[0] = pct[1] = pct[2] = nanf_;
   nvalid = 0;
@@ -499,7 +535,6 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
   unsigned ntie_total = 0;
   if (!subsample_range(v, lane, scale, nLs, has_tie, tie)) {
     sel_count(SEL_NO_SUBSAMPLE);
-    has_tie = false;
     if (!exact_range(w, scale, nLs)) { status = ST_EMPTY; return; }                 // mcz.py:277-280
   }
   // ---- pass H: the 1024-bin histogram (out-of-range finite values land in the end bins)
@@ -538,7 +573,7 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
   int tlo[3];
   unsigned tsp[3];
   sel_tests(P, true, tlo, tsp);
-  if (lane == 0) *w.ccount = 0u;
+  if (lane < 3) w.ccount[lane] = 0u;
   __syncwarp();
   float sum = 0.0f;
   const float pinf = __int_as_float(0x7f800000), ninf = __int_as_float(0xff800000);
@@ -559,7 +594,7 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
         const bool hit = ((unsigned)(f - tlo[0]) <= tsp[0]) || ((unsigned)(f - tlo[1]) <= tsp[1]) ||
                          ((unsigned)(f - tlo[2]) <= tsp[2]);
         sum += fin ? x : 0.0f;
-        if (hit && fin && x != skip) w.clist[atomicAdd(w.ccount, 1u) & 63u] = x;
+        if (hit && fin && x != skip) sel_put(w, P, f, tlo, tsp, x);
       }
     }
   } else {
@@ -584,7 +619,7 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
           const int f = fine_index(x, scale, nLs);
           const bool hit = ((unsigned)(f - tlo[0]) <= tsp[0]) || ((unsigned)(f - tlo[1]) <= tsp[1]) ||
                            ((unsigned)(f - tlo[2]) <= tsp[2]);
-          if (hit && x != skip) w.clist[atomicAdd(w.ccount, 1u) & 63u] = x;
+          if (hit && x != skip) sel_put(w, P, f, tlo, tsp, x);
           bool member = false;
 #pragma unroll
           for (int r = 0; r < 3; ++r)
@@ -621,7 +656,14 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
   if (!(warp_sum((double)sum) > 0.0)) { sel_count(SEL_TRIVIAL); status = ST_NONPOS; return; }   // mcz.py:282-285
   status = ST_OK;
   sel_count(SEL_FAST);
+#ifdef MCZ_COLTIME_DUMP
+  w.dbg = (P.crowded[0] ? 1 : 0) | (P.crowded[1] ? 2 : 0) | (P.crowded[2] ? 4 : 0) | (P.tie_range >= 0 ? 8 : 0) |
+          (has_tie ? 16 : 0) | (P.nr << 5);
+#endif
   sel_finish<PACK16>(w, P, bmn, bmx, nmin, pct);
+#ifdef MCZ_COLTIME_DUMP
+  nvalid |= w.dbg << 16;
+#endif
 }
 
 }  // namespace mcz

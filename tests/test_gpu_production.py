@@ -90,8 +90,11 @@ def test_per_sample_values_vs_oracle(mds, dust, correlated, n):
     assert np.median(d) < 2e-5
 
 
-def test_percentile_table_is_exact_selection_of_own_columns():
-    sm, se = synthetic_table(30, config=4)
+@pytest.mark.parametrize("ngal", [30, 700])
+def test_percentile_table_is_exact_selection_of_own_columns(ngal):
+    # 700 galaxies x 17 columns reach every selection path many times: repeated values merged by
+    # rank, split candidate lists, crowded ranges with follow-up rounds, empty columns
+    sm, se = synthetic_table(ngal, config=4)
     meas, err = np.concatenate([EX_M, sm]), np.concatenate([EX_E, se])
     pct, nvalid, status, trips, ret, Z = run_prod(meas, err, 2200)
     for g in range(meas.shape[0]):
