@@ -51,6 +51,12 @@ template <bool PACK16> struct FineHist {
     if (PACK16) atomicAdd(h + (f >> 1), 1u << ((f & 1) << 4));
     else atomicAdd(h + f, 1u);
   }
+  // branch-free form for the streaming pass: a sample that is not counted adds 0 to a word of
+  // its lane's own bank, so the four samples of a 128-bit load keep independent instruction chains
+  static __device__ __forceinline__ void add_if(unsigned* h, int f, bool ok, int lane) {
+    if (PACK16) atomicAdd(h + (ok ? (f >> 1) : lane), ok ? (1u << ((f & 1) << 4)) : 0u);
+    else atomicAdd(h + (ok ? f : lane), ok ? 1u : 0u);
+  }
   static __device__ __forceinline__ void add_n(unsigned* h, int f, unsigned n) {      // n < 65536 when PACK16
     if (PACK16) atomicAdd(h + (f >> 1), n << ((f & 1) << 4));
     else atomicAdd(h + f, n);
@@ -121,8 +127,12 @@ struct SelWarp {
 #endif
 };
 
+// Monotone map of a value to a bin of [0, FB): round(x * scale + nLs), clamped.  The 2^23 bias
+// makes the FMA itself round to an integer that sits in the float's low mantissa bits, so no
+// float-to-int conversion (a quarter-rate instruction) is needed.  NaN maps to bin 0.
 __device__ __forceinline__ int fine_index(float x, float scale, float nLs) {
-  return __float2int_rz(fminf(fmaxf(fmaf(x, scale, nLs), 0.0f), (float)(FB - 1)));
+  const float t = fminf(fmaxf(fmaf(x, scale, nLs + 8388608.0f), 8388608.0f), 8388608.0f + (float)(FB - 1));
+  return __float_as_int(t) - 0x4B000000;
 }
 
 // After pass H: every lane gets its exclusive prefix over lanes (32 bins per lane) and its total.
@@ -546,7 +556,7 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
       const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        if (finite_f(xs[j])) FH::add(hist, fine_index(xs[j], scale, nLs));          // mcz.py:273
+        FH::add_if(hist, fine_index(xs[j], scale, nLs), finite_f(xs[j]), lane);     // mcz.py:273
     }
   } else {
     int ntie = 0;
@@ -557,7 +567,7 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
       for (int j = 0; j < 4; ++j) {
         const bool is_tie = xs[j] == tie;
         ntie += is_tie ? 1 : 0;
-        if (finite_f(xs[j]) && !is_tie) FH::add(hist, fine_index(xs[j], scale, nLs));
+        FH::add_if(hist, fine_index(xs[j], scale, nLs), finite_f(xs[j]) && !is_tie, lane);
       }
     }
     ntie = __reduce_add_sync(0xffffffffu, ntie);

@@ -3,6 +3,9 @@
 //  mode 1: warp-shared packed u16 counters, atomicAdd (ATOMS) on u32 words, 1024 bins, gaussian-ish bins
 //  mode 2: same as 1 but every lane hits the same bin (worst case)
 //  mode 3: __match_any_sync + leader RMW
+//  mode 8: per-lane private u8 counters, one bank per lane (word = (bin/4)*32 + lane), 64 bins
+//  mode 9: ATOMS without bank conflicts (word = (bin%16)*32 + lane)
+//  mode 10: per-lane private u8 counters, one bank per lane, 128 bins in two 64-bin halves (4 KB)
 #include <cstdio>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -39,6 +42,17 @@ __global__ void __launch_bounds__(576, 1) k(int mode, int iters, const float* __
         int b = min(max(__float2int_rz((x + 4.0f) * 128.0f), 0), 1023);
         unsigned addr = (unsigned)__cvta_generic_to_shared(hw + (b >> 1));
         asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(addr), "r"(1u << (16 * (b & 1))));
+      } else if (mode == 8) {
+        int b = min(max(__float2int_rz((x + 4.0f) * 8.0f), 0), 63);
+        unsigned char* h = hb + ((b >> 2) * 32 + lane) * 4 + (b & 3);
+        *h = (unsigned char)(*h + 1);
+      } else if (mode == 9) {
+        int b = min(max(__float2int_rz((x + 4.0f) * 128.0f), 0), 1023);
+        atomicAdd(hw + (b & 15) * 32 + lane, 1u);
+      } else if (mode == 10) {
+        int b = min(max(__float2int_rz((x + 4.0f) * 16.0f), 0), 127);
+        unsigned* h = hw2 + (b >> 2) * 32 + lane;
+        *h += 1u << ((b & 3) * 8);
       } else if (mode == 7) {
         int b = min(max(__float2int_rz((x + 4.0f) * 128.0f), 0), 1023);
         atomicAdd(hw + (b & 511), 1u << (16 * (b >> 9)));
@@ -65,7 +79,7 @@ int main() {
   cudaMalloc(&d, n * 4); cudaMemcpy(d, h, n * 4, cudaMemcpyHostToDevice);
   cudaMalloc(&o, nb * 8); cudaMalloc(&sink, 4);
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  for (int mode = 0; mode < 8; ++mode) {
+  for (int mode = 0; mode < 11; ++mode) {
     if (mode == 3) continue;
     const int iters = 20;
     k<<<nb, 576, 80 * 1024>>>(mode, 2, d, o, sink);
