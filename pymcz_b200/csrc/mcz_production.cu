@@ -599,7 +599,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
         p.pct[3 * o] = pc[0];
         p.pct[3 * o + 1] = pc[1];
         p.pct[3 * o + 2] = pc[2];
-#ifdef MCZ_COLTIME_DUMP
+#if defined(MCZ_COLTIME_DUMP) && MCZ_COLTIME_DUMP == 1
         p.pct[3 * o + 2] = (float)(clock64() - tc0);
 #endif
       }

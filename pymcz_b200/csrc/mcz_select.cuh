@@ -122,6 +122,7 @@ struct SelWarp {
   float* clist;            // 64 candidates (select_in_interval)
   float* glist;            // 192 candidates of pass G; aliases hist, which the plan has consumed by then
   int lane;
+  float scale, nLs;        // fine index of the first round
 #ifdef MCZ_COLTIME_DUMP
   mutable int dbg;
 #endif
@@ -319,8 +320,12 @@ __device__ __forceinline__ bool subsample_range(const float* __restrict__ v, int
     // A target rank lies outside the prefix's own [min, max] with probability 0.84^m per column,
     // so the index need not reach further: bimodal columns (two branches of a diagnostic) then
     // keep bins fine enough for the 64-candidate lists.
-    L = fmaxf(L, sorted64_get(a, b, 0u));
-    H = fminf(H, sorted64_get(a, b, (unsigned)(m - 1)));
+    // (two bins of margin: the end bins then hold only values outside the prefix's range, and
+    // NaN / inf, which index into them, are never members of a target range in practice)
+    const float pmin = sorted64_get(a, b, 0u), pmax = sorted64_get(a, b, (unsigned)(m - 1));
+    const float d = (pmax - pmin) * (2.0f / (float)(FB - 4));
+    L = fmaxf(L, pmin - d);
+    H = fminf(H, pmax + d);
   }
   scale = (float)FB / (H - L);
   nLs = -L * scale;
@@ -340,9 +345,9 @@ struct SelPlan {
   int rq[3];               // range of pair q
   bool crowded[3];         // more than 64 members: not gathered
   unsigned need[3];        // members gathered for the range (0 if crowded)
-  unsigned loff[3];        // where its candidates start in the list
-  bool split;              // false: one list of <= 64 in all, one sort; true: one 64-list per range
-  unsigned ncand;
+  unsigned loff[3];        // where its candidates start in the sorted list (when not split)
+  bool split;              // false: <= 64 candidates in all, one sort; true: one sort per range
+  unsigned ncand;          // candidates gathered in all (<= 192)
   // a heavily repeated value T (found in the 64-sample prefix, counted by vote in pass H): its ntie
   // copies are not gathered; the range that holds T's fine bin merges them back by rank
   int tie_range;           // -1: none
@@ -414,8 +419,8 @@ __device__ __forceinline__ void sel_make_plan(const SelWarp& w, SelPlan& P, bool
   }
   P.split = ncand > 64u;
   P.loff[0] = 0u;
-  P.loff[1] = P.split ? 64u : P.need[0];
-  P.loff[2] = P.split ? 128u : P.need[0] + P.need[1];
+  P.loff[1] = P.need[0];
+  P.loff[2] = P.need[0] + P.need[1];
   P.ncand = ncand;
 }
 
@@ -444,14 +449,36 @@ __device__ __forceinline__ void sel_finish(const SelWarp& w, const SelPlan& P, c
 #pragma unroll
   for (int i = 0; i < 6; ++i) res[i] = pinf;
   // one sort of the whole list (ranges are disjoint and ascending, so their candidates come out
-  // range after range), or one sort per range when the list is split
+  // range after range); when the list is split, the members of each range are first picked out
+  // of the (unordered) list into w.clist and sorted range by range
   const int nsort = P.split ? P.nr : 1;
+  const unsigned lt = (1u << lane) - 1u;
 #pragma unroll 1
   for (int t = 0; t < nsort; ++t) {
-    const unsigned base = P.split ? 64u * (unsigned)t : 0u;
-    const unsigned cnt = P.split ? (t == 0 ? P.need[0] : (t == 1 ? P.need[1] : P.need[2])) : P.ncand;
-    float ca = (unsigned)lane < cnt ? w.glist[base + lane] : pinf;
-    float cb = (unsigned)(lane + 32) < cnt ? w.glist[base + lane + 32] : pinf;
+    const float* src = w.glist;
+    unsigned cnt = P.ncand;
+    if (P.split) {
+      const int lo_t = t == 0 ? P.rlo[0] : (t == 1 ? P.rlo[1] : P.rlo[2]);
+      const unsigned sp_t = (unsigned)((t == 0 ? P.rhi[0] : (t == 1 ? P.rhi[1] : P.rhi[2])) - lo_t);
+      const bool cr_t = t == 0 ? P.crowded[0] : (t == 1 ? P.crowded[1] : P.crowded[2]);
+      unsigned c = 0;
+      if (!cr_t) {
+        for (unsigned i0 = 0; i0 < P.ncand; i0 += 32u) {
+          const unsigned i = i0 + (unsigned)lane;
+          const float x = w.glist[i & 255u];
+          const bool in = i < P.ncand && (unsigned)(fine_index(x, w.scale, w.nLs) - lo_t) <= sp_t;
+          const unsigned m = __ballot_sync(0xffffffffu, in);
+          if (in) w.clist[(c + __popc(m & lt)) & 63u] = x;
+          c += __popc(m);
+        }
+      }
+      __syncwarp();
+      src = w.clist;
+      cnt = c;
+    }
+    float ca = (unsigned)lane < cnt ? src[lane] : pinf;
+    float cb = (unsigned)(lane + 32) < cnt ? src[lane + 32] : pinf;
+    __syncwarp();
     sort64_regs(ca, cb, lane);
     // tie range: candidates below the tie value (the sorted list holds the range at [tb, tb + tm))
     unsigned tless = 0;
@@ -501,15 +528,6 @@ __device__ __forceinline__ void sel_finish(const SelWarp& w, const SelPlan& P, c
   pct[2] = np_lerp_f(res[4], res[5], P.gam[2]);       // 84th
 }
 
-// pass G: append a member of gathered range r (the one whose test f passes) to that range's list
-__device__ __forceinline__ void sel_put(const SelWarp& w, const SelPlan& P, int f, const int tlo[3],
-                                        const unsigned tsp[3], float x) {
-  const int r = ((unsigned)(f - tlo[0]) <= tsp[0]) ? 0 : (((unsigned)(f - tlo[1]) <= tsp[1]) ? 1 : 2);
-  const unsigned off = r == 0 ? P.loff[0] : (r == 1 ? P.loff[1] : P.loff[2]);
-  const unsigned pos = atomicAdd(w.ccount + r, 1u);
-  w.glist[(off + (pos & 63u)) & 255u] = x;
-}
-
 // Fine-index range of a column when the 64-sample estimate is not usable: the exact range.
 // Returns false for a column without finite values.
 __device__ __forceinline__ bool exact_range(const SelWarp& w, float& scale, float& nLs) {
@@ -517,6 +535,11 @@ __device__ __forceinline__ bool exact_range(const SelWarp& w, float& scale, floa
   column_minmax(w, qlo, qhi);
   if (!(qhi >= qlo)) return false;
   if (!(qhi > qlo)) { qlo -= 1.0f; qhi += 1.0f; }       // constant column: any range will do
+  else {                                                // keep the end bins for NaN / inf alone
+    const float d = (qhi - qlo) * (2.0f / (float)(FB - 4));
+    qlo -= d;
+    qhi += d;
+  }
   scale = (float)FB / (qhi - qlo);
   nLs = -qlo * scale;
   if (!finite_f(scale) || !finite_f(nLs)) { scale = (float)FB / (FLT_MAX * 0.5f); nLs = 0.5f * (float)FB; }
@@ -543,11 +566,22 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
   float scale, nLs, tie;
   bool has_tie;
   unsigned ntie_total = 0;
+#if defined(MCZ_COLTIME_DUMP) && MCZ_COLTIME_DUMP >= 2
+  const long long ts0 = clock64();
+#define MCZ_TS(v) const long long v = clock64()
+#else
+#define MCZ_TS(v)
+#endif
   if (!subsample_range(v, lane, scale, nLs, has_tie, tie)) {
     sel_count(SEL_NO_SUBSAMPLE);
     if (!exact_range(w, scale, nLs)) { status = ST_EMPTY; return; }                 // mcz.py:277-280
   }
-  // ---- pass H: the 1024-bin histogram (out-of-range finite values land in the end bins)
+  w.scale = scale;
+  w.nLs = nLs;
+  MCZ_TS(ts1);
+  // ---- pass H: the 1024-bin histogram (out-of-range finite values land in the end bins) and the
+  // sum of the column (the atomics bound this pass, so the extra arithmetic is free here)
+  float sum = 0.0f;
   FH::zero(hist, lane);
   if (!has_tie) {
 #pragma unroll 2
@@ -555,8 +589,11 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
       const float4 x4 = *reinterpret_cast<const float4*>(v + s0);
       const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        FH::add_if(hist, fine_index(xs[j], scale, nLs), finite_f(xs[j]), lane);     // mcz.py:273
+      for (int j = 0; j < 4; ++j) {
+        const bool fin = finite_f(xs[j]);
+        sum += fin ? xs[j] : 0.0f;
+        FH::add_if(hist, fine_index(xs[j], scale, nLs), fin, lane);                 // mcz.py:273
+      }
     }
   } else {
     int ntie = 0;
@@ -566,49 +603,78 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const bool is_tie = xs[j] == tie;
+        const bool fin = finite_f(xs[j]);
         ntie += is_tie ? 1 : 0;
-        FH::add_if(hist, fine_index(xs[j], scale, nLs), finite_f(xs[j]) && !is_tie, lane);
+        sum += fin ? xs[j] : 0.0f;
+        FH::add_if(hist, fine_index(xs[j], scale, nLs), fin && !is_tie, lane);
       }
     }
     ntie = __reduce_add_sync(0xffffffffu, ntie);
     if (lane == 0 && ntie > 0) FH::add_n(hist, fine_index(tie, scale, nLs), (unsigned)ntie);
     ntie_total = (unsigned)ntie;
   }
+  MCZ_TS(ts2);
   SelPlan P;
   sel_make_plan<PACK16>(w, P, has_tie, tie, has_tie ? fine_index(tie, scale, nLs) : 0, ntie_total);
   const float skip = P.tie;           // NaN unless a tie value is merged back by rank (never equal then)
   nvalid = P.n;
   if (P.n == 0) { sel_count(SEL_TRIVIAL); status = ST_EMPTY; return; }              // mcz.py:277-280
   // ---- pass G: gather the members of the uncrowded ranges, sum everything
+  MCZ_TS(ts3);
   int tlo[3];
   unsigned tsp[3];
   sel_tests(P, true, tlo, tsp);
-  if (lane < 3) w.ccount[lane] = 0u;
   __syncwarp();
-  float sum = 0.0f;
+  unsigned gcnt = 0;                             // candidates gathered so far (same in every lane)
+  const unsigned lt = (1u << lane) - 1u;
   const float pinf = __int_as_float(0x7f800000), ninf = __int_as_float(0xff800000);
   float bmn[3] = {pinf, pinf, pinf}, bmx[3] = {ninf, ninf, ninf};
   unsigned nmin[3] = {0u, 0u, 0u};
   w.ngroups = Npad / 128;
   w.nmine = Npad;
-  if (!(P.crowded[0] || P.crowded[1] || P.crowded[2])) {
-#pragma unroll 2
-    for (int s0 = 4 * lane; s0 < Npad; s0 += 128) {
-      const float4 x4 = *reinterpret_cast<const float4*>(v + s0);
-      const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+  bool general = P.crowded[0] || P.crowded[1] || P.crowded[2];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float x = xs[j];
-        const int f = fine_index(x, scale, nLs);
-        const bool fin = finite_f(x);
-        const bool hit = ((unsigned)(f - tlo[0]) <= tsp[0]) || ((unsigned)(f - tlo[1]) <= tsp[1]) ||
-                         ((unsigned)(f - tlo[2]) <= tsp[2]);
-        sum += fin ? x : 0.0f;
-        if (hit && fin && x != skip) sel_put(w, P, f, tlo, tsp, x);
+  for (int r = 0; r < 3; ++r)                    // NaN / inf index into the end bins
+    if (r < P.nr && (P.rlo[r] == 0 || P.rhi[r] == FB - 1)) general = true;
+  if (!general) {
+    // The streaming loop only records which samples are members (one bit each, six 128-sample
+    // groups per 24-bit mask); the few members are appended after each chunk with one shared
+    // atomic per lane that has any.
+    constexpr int CH = 6;
+    const int ngroups = Npad / 128;
+    if (lane == 0) *w.ccount = 0u;
+    __syncwarp();
+#pragma unroll 1
+    for (int g0 = 0; g0 < ngroups; g0 += CH) {
+      unsigned mask = 0u;
+#pragma unroll
+      for (int i = 0; i < CH; ++i) {
+        if (g0 + i < ngroups) {
+          const float4 x4 = *reinterpret_cast<const float4*>(v + 4 * lane + 128 * (g0 + i));
+          const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float x = xs[j];
+            const int f = fine_index(x, scale, nLs);            // non-finite x: an end bin, no member here
+            const bool hit = ((unsigned)(f - tlo[0]) <= tsp[0]) || ((unsigned)(f - tlo[1]) <= tsp[1]) ||
+                             ((unsigned)(f - tlo[2]) <= tsp[2]);
+            mask |= (hit && x != skip) ? (1u << (4 * i + j)) : 0u;
+          }
+        }
+      }
+      if (mask) {
+        unsigned pos = atomicAdd(w.ccount, (unsigned)__popc(mask));
+        do {
+          const int b = __ffs(mask) - 1;
+          mask &= mask - 1u;
+          w.glist[pos & 255u] = v[4 * lane + 128 * (g0 + (b >> 2)) + (b & 3)];
+          ++pos;
+        } while (mask);
       }
     }
   } else {
-    // Some range is crowded (ties, end bins).  Same pass, but the members of the crowded ranges
+    // Some range is crowded (ties) or reaches an end bin.  Same pass, but with the test for
+    // non-finite values, candidates appended by vote, and the members of the crowded ranges
     // are also (a) reduced to min / max / number equal to the min and (b) compacted, in place, to
     // the front of this lane's own slots: from here on the column is only needed for them, so
     // the follow-up rounds of select_in_interval scan a few groups instead of the whole column.
@@ -624,12 +690,15 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float x = xs[j];
-        if (finite_f(x)) {
-          sum += x;
-          const int f = fine_index(x, scale, nLs);
-          const bool hit = ((unsigned)(f - tlo[0]) <= tsp[0]) || ((unsigned)(f - tlo[1]) <= tsp[1]) ||
-                           ((unsigned)(f - tlo[2]) <= tsp[2]);
-          if (hit && x != skip) sel_put(w, P, f, tlo, tsp, x);
+        const bool fin = finite_f(x);
+        const int f = fine_index(x, scale, nLs);
+        const bool take = fin && x != skip &&
+                          (((unsigned)(f - tlo[0]) <= tsp[0]) || ((unsigned)(f - tlo[1]) <= tsp[1]) ||
+                           ((unsigned)(f - tlo[2]) <= tsp[2]));
+        const unsigned m = __ballot_sync(0xffffffffu, take);
+        if (take) w.glist[(gcnt + __popc(m & lt)) & 255u] = x;
+        gcnt += __popc(m);
+        if (fin) {
           bool member = false;
 #pragma unroll
           for (int r = 0; r < 3; ++r)
@@ -665,6 +734,7 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
   }
   if (!(warp_sum((double)sum) > 0.0)) { sel_count(SEL_TRIVIAL); status = ST_NONPOS; return; }   // mcz.py:282-285
   status = ST_OK;
+  MCZ_TS(ts4);
   sel_count(SEL_FAST);
 #ifdef MCZ_COLTIME_DUMP
   w.dbg = (P.crowded[0] ? 1 : 0) | (P.crowded[1] ? 2 : 0) | (P.crowded[2] ? 4 : 0) | (P.tie_range >= 0 ? 8 : 0) |
@@ -673,6 +743,11 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
   sel_finish<PACK16>(w, P, bmn, bmx, nmin, pct);
 #ifdef MCZ_COLTIME_DUMP
   nvalid |= w.dbg << 16;
+#endif
+#if defined(MCZ_COLTIME_DUMP) && MCZ_COLTIME_DUMP == 2
+  pct[0] = (float)(ts2 - ts0); pct[1] = (float)(ts3 - ts2); pct[2] = (float)(ts4 - ts3);   // range + pass H, plan, pass G
+#elif defined(MCZ_COLTIME_DUMP) && MCZ_COLTIME_DUMP == 3
+  pct[0] = (float)(ts1 - ts0); pct[1] = (float)(clock64() - ts4); pct[2] = (float)(clock64() - ts0);   // range, finish, total
 #endif
 }
 
