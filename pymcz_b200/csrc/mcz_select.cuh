@@ -67,11 +67,14 @@ template <bool PACK16> struct FineHist {
   }
   // sum of the 32 bins [32*lane, 32*lane+32)
   static __device__ __forceinline__ unsigned lane_total(const unsigned* h, int lane) {
+    // each lane starts at a different one of its 128-bit pieces so that the eight lanes of a
+    // shared-memory phase touch eight different bank groups
     const uint4* q = reinterpret_cast<const uint4*>(h + lane * (WORDS / 32));
+    const int rot = PACK16 ? (lane >> 1) : lane;
     unsigned acc = 0;
 #pragma unroll
     for (int i = 0; i < WORDS / 128; ++i) {
-      const uint4 w = q[i];
+      const uint4 w = q[(i + rot) & (WORDS / 128 - 1)];
       if (PACK16) acc += (w.x & 0xffffu) + (w.x >> 16) + (w.y & 0xffffu) + (w.y >> 16) + (w.z & 0xffffu) + (w.z >> 16) + (w.w & 0xffffu) + (w.w >> 16);
       else acc += w.x + w.y + w.z + w.w;
     }
@@ -171,6 +174,41 @@ __device__ __forceinline__ void fine_locate(const SelWarp& w, unsigned lane_excl
   f = 32 * ol + hl;
   excl = __shfl_sync(0xffffffffu, ex, hl);
   cnt = __shfl_sync(0xffffffffu, c, hl);
+}
+
+// Same for two consecutive ranks rA <= rB <= rA + 1: they share one scan when the same lane's 32
+// bins hold both (nearly always).  Returns the bins, the samples below fA and the samples up to
+// and including fB.
+template <bool PACK16>
+__device__ __forceinline__ void fine_locate_pair(const SelWarp& w, unsigned lane_excl, unsigned lane_tot,
+                                                 unsigned rA, unsigned rB, int& fA, unsigned& exA, int& fB,
+                                                 unsigned& endB) {
+  const unsigned ownA = __ballot_sync(0xffffffffu, lane_tot > 0 && rA >= lane_excl && rA < lane_excl + lane_tot);
+  const unsigned ownB = __ballot_sync(0xffffffffu, lane_tot > 0 && rB >= lane_excl && rB < lane_excl + lane_tot);
+  const int olA = ownA ? __ffs(ownA) - 1 : 31;
+  const int olB = ownB ? __ffs(ownB) - 1 : 31;
+  const unsigned base = __shfl_sync(0xffffffffu, lane_excl, olA);
+  const unsigned c = FineHist<PACK16>::get(w.hist, 32 * olA + w.lane);
+  unsigned inc = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (w.lane >= o) inc += t;
+  }
+  const unsigned ex = base + inc - c;
+  const unsigned hitA = __ballot_sync(0xffffffffu, c > 0 && rA >= ex && rA < ex + c);
+  const unsigned hitB = __ballot_sync(0xffffffffu, c > 0 && rB >= ex && rB < ex + c);
+  const int hlA = hitA ? __ffs(hitA) - 1 : 31;
+  const int hlB = hitB ? __ffs(hitB) - 1 : 31;
+  fA = 32 * olA + hlA;
+  exA = __shfl_sync(0xffffffffu, ex, hlA);
+  fB = 32 * olA + hlB;
+  endB = __shfl_sync(0xffffffffu, ex + c, hlB);
+  if (olB != olA) {                                 // rB starts the next non-empty group of bins
+    unsigned exB, cnB;
+    fine_locate<PACK16>(w, lane_excl, lane_tot, rB, fB, exB, cnB);
+    endB = exB + cnB;
+  }
 }
 
 // min / max of the finite values of the column
@@ -376,20 +414,21 @@ __device__ __forceinline__ void sel_make_plan(const SelWarp& w, SelPlan& P, bool
     P.rk[2 * q] = (unsigned)lo;
     P.rk[2 * q + 1] = min((unsigned)lo + 1u, (unsigned)(P.n - 1));
   }
-  int fi[6];
-  unsigned ex[6], cn[6];
+  int fa[3], fb[3];
+  unsigned exa[3], endb[3];
 #pragma unroll
-  for (int i = 0; i < 6; ++i) fine_locate<PACK16>(w, lex, ltot, P.rk[i], fi[i], ex[i], cn[i]);
-  // Merge the three pair ranges [fi[2q], fi[2q+1]] where they touch or overlap (small n, ties).
+  for (int q = 0; q < 3; ++q)
+    fine_locate_pair<PACK16>(w, lex, ltot, P.rk[2 * q], P.rk[2 * q + 1], fa[q], exa[q], fb[q], endb[q]);
+  // Merge the three pair ranges [fa, fb] where they touch or overlap (small n, ties).
   int nr = 0;
 #pragma unroll
   for (int q = 0; q < 3; ++q) {
-    const int a = fi[2 * q], b = fi[2 * q + 1];
-    const unsigned endcount = ex[2 * q + 1] + cn[2 * q + 1];      // samples with f <= b
+    const int a = fa[q], b = fb[q];
+    const unsigned endcount = endb[q];                            // samples with f <= b
     if (nr > 0 && a <= P.rhi[nr - 1]) {
       if (b > P.rhi[nr - 1]) { P.rhi[nr - 1] = b; P.rM[nr - 1] = endcount - P.rE[nr - 1]; }
     } else {
-      P.rlo[nr] = a; P.rhi[nr] = b; P.rE[nr] = ex[2 * q]; P.rM[nr] = endcount - ex[2 * q];
+      P.rlo[nr] = a; P.rhi[nr] = b; P.rE[nr] = exa[q]; P.rM[nr] = endcount - exa[q];
       ++nr;
     }
     P.rq[q] = nr - 1;
