@@ -103,6 +103,19 @@ __device__ __forceinline__ void sort64_regs(float& a, float& b, int lane) {
     }
   }
 }
+// ascending bitonic sort of 32 keys, one per lane
+__device__ __forceinline__ void sort32_regs(float& a, int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const float pa = __shfl_xor_sync(0xffffffffu, a, j);
+      const bool lower = (lane & j) == 0;
+      const bool up = (lane & k) == 0 || k == 32;
+      a = (lower == up) ? fminf(a, pa) : fmaxf(a, pa);
+    }
+  }
+}
 __device__ __forceinline__ float sorted64_get(float a, float b, unsigned i) {
   const float va = __shfl_sync(0xffffffffu, a, i & 31), vb = __shfl_sync(0xffffffffu, b, i & 31);
   return i < 32u ? va : vb;
@@ -518,7 +531,8 @@ __device__ __forceinline__ void sel_finish(const SelWarp& w, const SelPlan& P, c
     float ca = (unsigned)lane < cnt ? src[lane] : pinf;
     float cb = (unsigned)(lane + 32) < cnt ? src[lane + 32] : pinf;
     __syncwarp();
-    sort64_regs(ca, cb, lane);
+    if (cnt <= 32u) sort32_regs(ca, lane);          // the usual case: a handful of candidates (cb = +inf)
+    else sort64_regs(ca, cb, lane);
     // tie range: candidates below the tie value (the sorted list holds the range at [tb, tb + tm))
     unsigned tless = 0;
     if (P.tie_range >= 0 && (!P.split || P.tie_range == t)) {
