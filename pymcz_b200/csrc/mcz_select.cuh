@@ -82,23 +82,23 @@ template <bool PACK16> struct FineHist {
   }
 };
 
-// ascending bitonic sort of 64 keys held two per lane: key i<32 is `a` of lane i, key i>=32 is `b`
-// of lane i-32
+// ascending bitonic sort of 64 keys held two per lane: key i is `a` (i even) or `b` (i odd) of
+// lane i / 2, so the six distance-1 stages stay inside a lane and 15 stages need a shuffle
 __device__ __forceinline__ void sort64_regs(float& a, float& b, int lane) {
 #pragma unroll
   for (int k = 2; k <= 64; k <<= 1) {
+    const bool up = (lane & (k >> 1)) == 0 || k == 64;
 #pragma unroll
     for (int j = k >> 1; j > 0; j >>= 1) {
-      if (j == 32) {
+      if (j == 1) {
         const float lo = fminf(a, b), hi = fmaxf(a, b);
-        a = lo; b = hi;
+        a = up ? lo : hi;
+        b = up ? hi : lo;
       } else {
-        const float pa = __shfl_xor_sync(0xffffffffu, a, j), pb = __shfl_xor_sync(0xffffffffu, b, j);
-        const bool lower = (lane & j) == 0;
-        const bool up_a = (lane & k) == 0;
-        const bool up_b = ((lane + 32) & k) == 0;
-        a = (lower == up_a) ? fminf(a, pa) : fmaxf(a, pa);
-        b = (lower == up_b) ? fminf(b, pb) : fmaxf(b, pb);
+        const float pa = __shfl_xor_sync(0xffffffffu, a, j >> 1), pb = __shfl_xor_sync(0xffffffffu, b, j >> 1);
+        const bool lower = (lane & (j >> 1)) == 0;
+        a = (lower == up) ? fminf(a, pa) : fmaxf(a, pa);
+        b = (lower == up) ? fminf(b, pb) : fmaxf(b, pb);
       }
     }
   }
@@ -117,8 +117,8 @@ __device__ __forceinline__ void sort32_regs(float& a, int lane) {
   }
 }
 __device__ __forceinline__ float sorted64_get(float a, float b, unsigned i) {
-  const float va = __shfl_sync(0xffffffffu, a, i & 31), vb = __shfl_sync(0xffffffffu, b, i & 31);
-  return i < 32u ? va : vb;
+  const float va = __shfl_sync(0xffffffffu, a, (i >> 1) & 31), vb = __shfl_sync(0xffffffffu, b, (i >> 1) & 31);
+  return (i & 1u) ? vb : va;
 }
 
 // numpy.lib._function_base_impl._lerp in float64 on the float32 order statistics
@@ -353,10 +353,11 @@ __device__ __forceinline__ bool subsample_range(const float* __restrict__ v, int
   sort64_regs(a, b, lane);
   {
     // sorted[i] == sorted[i + 4]  <=>  at least five copies of that value
-    const float a4 = sorted64_get(a, b, (unsigned)lane + 4u);
-    const float b4 = sorted64_get(a, b, min((unsigned)lane + 36u, 63u));
-    const unsigned ma = __ballot_sync(0xffffffffu, a < pinf && a == a4);
-    const unsigned mb = __ballot_sync(0xffffffffu, lane < 28 && b < pinf && b == b4);
+    // (key i + 4 is the same register two lanes up)
+    const float a4 = __shfl_down_sync(0xffffffffu, a, 2);
+    const float b4 = __shfl_down_sync(0xffffffffu, b, 2);
+    const unsigned ma = __ballot_sync(0xffffffffu, lane < 30 && a < pinf && a == a4);
+    const unsigned mb = __ballot_sync(0xffffffffu, lane < 30 && b < pinf && b == b4);
     has_tie = (ma | mb) != 0u;
     tie = ma ? __shfl_sync(0xffffffffu, a, __ffs(ma) - 1) : __shfl_sync(0xffffffffu, b, mb ? __ffs(mb) - 1 : 0);
   }
@@ -531,15 +532,18 @@ __device__ __forceinline__ void sel_finish(const SelWarp& w, const SelPlan& P, c
     float ca = (unsigned)lane < cnt ? src[lane] : pinf;
     float cb = (unsigned)(lane + 32) < cnt ? src[lane + 32] : pinf;
     __syncwarp();
-    if (cnt <= 32u) sort32_regs(ca, lane);          // the usual case: a handful of candidates (cb = +inf)
+    const bool small = cnt <= 32u;                  // the usual case: a handful of candidates (cb = +inf)
+    if (small) sort32_regs(ca, lane);
     else sort64_regs(ca, cb, lane);
+    const unsigned ia = small ? (unsigned)lane : 2u * (unsigned)lane;        // sorted position of ca, cb
+    const unsigned ib = small ? 64u : 2u * (unsigned)lane + 1u;
     // tie range: candidates below the tie value (the sorted list holds the range at [tb, tb + tm))
     unsigned tless = 0;
     if (P.tie_range >= 0 && (!P.split || P.tie_range == t)) {
       const unsigned tb = P.split ? 0u : (P.tie_range == 0 ? P.loff[0] : (P.tie_range == 1 ? P.loff[1] : P.loff[2]));
       const unsigned tm = P.tie_range == 0 ? P.need[0] : (P.tie_range == 1 ? P.need[1] : P.need[2]);
-      const bool ina = (unsigned)lane - tb < tm && ca < P.tie;
-      const bool inb = (unsigned)(lane + 32) - tb < tm && cb < P.tie;
+      const bool ina = ia - tb < tm && ca < P.tie;
+      const bool inb = ib - tb < tm && cb < P.tie;
       tless = __popc(__ballot_sync(0xffffffffu, ina)) + __popc(__ballot_sync(0xffffffffu, inb));
     }
 #pragma unroll
@@ -554,7 +558,8 @@ __device__ __forceinline__ void sel_finish(const SelWarp& w, const SelPlan& P, c
         if (rho >= tless && rho < tless + P.ntie) is_tie = true;
         else if (rho >= tless + P.ntie) rho -= P.ntie;
       }
-      const float val = sorted64_get(ca, cb, (bl + rho) & 63u);
+      const unsigned at = bl + rho;
+      const float val = small ? __shfl_sync(0xffffffffu, ca, at & 31u) : sorted64_get(ca, cb, at & 63u);
       res[i] = is_tie ? P.tie : val;
     }
   }
