@@ -140,16 +140,25 @@ __device__ __forceinline__ float fast_rcp(float x) {
   return r;
 }
 
-struct SlotPut {
+// Column store.  In the shared-memory variant the 32-bit shared address of the thread's sample
+// is computed once and the store is issued as st.shared: through a generic pointer the compiler
+// re-derives the shared window base (S2UR / ULEA / IMAD) at every one of the 17 stores.
+template <bool SHARED> struct SlotPut {
   float* col;                 // &vals[0][s]
   const int* col_off;         // per key: float offset of its column (kernel parameter space)
+  uint32_t saddr;             // shared-space byte address of col (SHARED only)
   __device__ __forceinline__ void operator()(int key, float v) const {
     // every key the physics can emit under the launch's tokens owns a column, except the
     // constant-NaN M08_R23 (reference metscales.py:1013-1018), which is never stored
     if (key == K_M08_R23) return;
-    col[col_off[key]] = v;
+    if (SHARED) asm volatile("st.shared.f32 [%0], %1;" :: "r"(saddr + 4u * (unsigned)col_off[key]), "f"(v) : "memory");
+    else col[col_off[key]] = v;
   }
 };
+template <bool SHARED> __device__ __forceinline__ void store_f32(float* gptr, uint32_t saddr, float v) {
+  if (SHARED) asm volatile("st.shared.f32 [%0], %1;" :: "r"(saddr), "f"(v) : "memory");
+  else *gptr = v;
+}
 
 }  // namespace mcz
 #include "mcz_select.cuh"
@@ -207,6 +216,13 @@ production_kernel(const __grid_constant__ ProdParams p) {
     st1 = kd ? vals + p.col_off[K_KK04_R23] : st3;
     st2 = kd ? vals + p.col_off[K_KD02COMB] : st3;
   }
+  // (the mov hides where the address comes from, or the compiler re-derives it at every store)
+  uint32_t vals_sa = GLOBAL ? 0u : (uint32_t)__cvta_generic_to_shared(vals);
+  asm volatile("mov.u32 %0, %0;" : "+r"(vals_sa));
+  const uint32_t st0_sa = GLOBAL ? 0u : (uint32_t)__cvta_generic_to_shared(st0);
+  const uint32_t st1_sa = GLOBAL ? 0u : (uint32_t)__cvta_generic_to_shared(st1);
+  const uint32_t st2_sa = GLOBAL ? 0u : (uint32_t)__cvta_generic_to_shared(st2);
+  const uint32_t st3_sa = GLOBAL ? 0u : (uint32_t)__cvta_generic_to_shared(st3);
   unsigned* hist = reinterpret_cast<unsigned*>(work + (size_t)warp * HIST_BYTES);
   float* cand = reinterpret_cast<float*>(work + (size_t)PW * HIST_BYTES) + warp * CAND_FLOATS;
 
@@ -265,15 +281,15 @@ production_kernel(const __grid_constant__ ProdParams p) {
           e[2] = 0.027f * z[2];           // metscales.py:948
           e[3] = 0.024f * z[3];           // metscales.py:949
           e[4] = 0.012f * z[4];           // metscales.py:952
-          SlotPut put{vals + s, p.col_off};
+          SlotPut<!GLOBAL> put{vals + s, p.col_off, vals_sa + 4u * (unsigned)s};
           Carry<float> c;
           c.y = c.n2ha = c.x = 0.0f;
           c.aux = 0u;
           phase_a<float>(f, e, flags, p.tok, de, put, c);
-          st0[s] = c.y;
-          st1[s] = c.n2ha;
-          st2[s] = c.x;
-          st3[s] = __uint_as_float(c.aux);
+          store_f32<!GLOBAL>(st0 + s, st0_sa + 4u * (unsigned)s, c.y);
+          store_f32<!GLOBAL>(st1 + s, st1_sa + 4u * (unsigned)s, c.n2ha);
+          store_f32<!GLOBAL>(st2 + s, st2_sa + 4u * (unsigned)s, c.x);
+          store_f32<!GLOBAL>(st3 + s, st3_sa + 4u * (unsigned)s, __uint_as_float(c.aux));
         } else if (s < Npad) {
           for (int sl = 0; sl < p.nstore; ++sl) vals[(long long)sl * Npad + s] = Math<float>::nan();
         }
@@ -467,7 +483,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
         for (int i = 0; i < SLOTS; ++i) {
           const int s = i * PT + tid;
           if (s < N) {
-            SlotPut put{vals + s, p.col_off};
+            SlotPut<!GLOBAL> put{vals + s, p.col_off, vals_sa + 4u * (unsigned)s};
             const float kd = has_kd ? vals[sl_kd * Npad + s] : Math<float>::nan();
             const float m91 = vals[sl_m91 * Npad + s];
             IterState<float> st;
@@ -536,7 +552,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
           st.L1 = F[9ll * Npad + s]; st.Z1 = F[10ll * Npad + s]; st.Z2 = F[11ll * Npad + s];
           st.lq2 = F[13ll * Npad + s];
           st.aux = __float_as_uint(st3[s]);
-          SlotPut put{vals + s, p.col_off};
+          SlotPut<!GLOBAL> put{vals + s, p.col_off, vals_sa + 4u * (unsigned)s};
           const float kd = has_kd ? vals[(long long)sl_kd * Npad + s] : Math<float>::nan();
           const float m91 = vals[(long long)sl_m91 * Npad + s];
           phase_c<float>(st, pm, ii1 >= 100, ii2 >= 100, kd, m91, put);
@@ -628,13 +644,33 @@ static void build_slots(uint32_t tok, ProdParams& p) {
     p.slot_of_key[k] = -1;
     p.key_of_slot[k] = -1;
   }
-  for (int k = 0; k < NKEYS; ++k) {
-    if (!((pm >> k) & 1ull) || k == K_M08_R23) continue;
-    p.slot_of_key[k] = (signed char)n;
-    p.key_of_slot[n] = (signed char)k;
-    ++n;
-  }
+  int keys[NKEYS];
+  for (int k = 0; k < NKEYS; ++k)
+    if (((pm >> k) & 1ull) && k != K_M08_R23) keys[n++] = k;
   p.nstore = n;
+  // Slot s is selected by warp s % 18, and warps 0, 4, 8, 12, 16 share one SM sub-partition: with 17
+  // columns it is the only one that runs five selections at once.  Give it the columns that are
+  // most often empty (a diagnostic outside its validity range yields an all-NaN column, which
+  // costs almost nothing), so that it usually has four like the others.
+  static const int often_empty[] = {K_M13_O3N2, K_M08_O3O2, K_P10_ONS, K_P10_ON, K_KD02_N2O2, K_Z94, K_KK04_N2HA};
+  bool placed[NKEYS] = {false};
+  int pos = 0;
+  for (int k : often_empty) {
+    if (pos >= n || pos >= 18) break;
+    if (!((pm >> k) & 1ull) || k == K_M08_R23) continue;
+    p.slot_of_key[k] = (signed char)pos;
+    p.key_of_slot[pos] = (signed char)k;
+    placed[k] = true;
+    pos += 4;
+  }
+  int sl = 0;
+  for (int i = 0; i < n; ++i) {
+    const int k = keys[i];
+    if (placed[k]) continue;
+    while (p.key_of_slot[sl] >= 0) ++sl;
+    p.slot_of_key[k] = (signed char)sl;
+    p.key_of_slot[sl] = (signed char)k;
+  }
 }
 static void finish_slots(ProdParams& p) {
   for (int k = 0; k < NKEYS; ++k) p.col_off[k] = p.slot_of_key[k] >= 0 ? p.slot_of_key[k] * p.Npad : -1;
