@@ -230,16 +230,27 @@ production_kernel(const __grid_constant__ ProdParams p) {
   const int nsl = (Npad + PT - 1) / PT;     // Npad is a multiple of 128; [N, Npad) is NaN-filled
   int phase = 0;
 
+  // The next galaxy (queue ticket, its 22 input numbers, cleared flags) is fetched by the last warp
+  // while the block is busy with phase D, so the loop top costs one barrier and no global latency.
+  auto fetch_next = [&]() {
+    long long gn = 0;
+    if (lane == 0) gn = (long long)atomicAdd(p.counter, 1ull);
+    gn = __shfl_sync(0xffffffffu, gn, 0);
+    if (gn < p.G) {
+      if (lane < NLINES) ctrl->line[lane] = p.meas[gn * NLINES + lane];
+      else if (lane < 2 * NLINES) ctrl->line[lane] = p.err[gn * NLINES + (lane - NLINES)];
+    }
+    if (lane == 0) {
+      ctrl->g = gn;
+      ctrl->flags = 0u; ctrl->acc[0][0] = 0; ctrl->acc[0][1] = 0; ctrl->acc[0][2] = 0; ctrl->acc[0][3] = 0;
+    }
+  };
+  if (warp == PW - 1) fetch_next();
+
   for (;;) {
-    __syncthreads();
-    if (tid == 0) ctrl->g = (long long)atomicAdd(p.counter, 1ull);
     __syncthreads();
     const long long g = ctrl->g;
     if (g >= p.G) break;
-    if (tid < NLINES) ctrl->line[tid] = p.meas[g * NLINES + tid];
-    else if (tid < 2 * NLINES) ctrl->line[tid] = p.err[g * NLINES + (tid - NLINES)];
-    if (tid == 0) { ctrl->flags = 0u; ctrl->acc[0][0] = 0; ctrl->acc[0][1] = 0; ctrl->acc[0][2] = 0; ctrl->acc[0][3] = 0; }
-    __syncthreads();
     float lm[NUSED], le[NUSED];
     uint32_t assumed = 0u;
 #pragma unroll
@@ -592,6 +603,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
       p.trips[2 * g + 1] = ii2;
       if (p.ret) p.ret[g] = ok ? 0 : -1;
     }
+    if (warp == PW - 1) fetch_next();    // (the lines / ticket of this galaxy were read into registers in phase A)
     for (int sl = warp; sl < p.nstore; sl += PW) {
       const int k = p.key_of_slot[sl];
       if (!((pm >> k) & 1ull)) continue;
