@@ -195,7 +195,7 @@ __device__ __forceinline__ void fine_locate(const SelWarp& w, unsigned lane_excl
 template <bool PACK16>
 __device__ __forceinline__ void fine_locate_pair(const SelWarp& w, unsigned lane_excl, unsigned lane_tot,
                                                  unsigned rA, unsigned rB, int& fA, unsigned& exA, int& fB,
-                                                 unsigned& endB) {
+                                                 unsigned& endB, bool& redoB) {
   const unsigned ownA = __ballot_sync(0xffffffffu, lane_tot > 0 && rA >= lane_excl && rA < lane_excl + lane_tot);
   const unsigned ownB = __ballot_sync(0xffffffffu, lane_tot > 0 && rB >= lane_excl && rB < lane_excl + lane_tot);
   const int olA = ownA ? __ffs(ownA) - 1 : 31;
@@ -217,11 +217,7 @@ __device__ __forceinline__ void fine_locate_pair(const SelWarp& w, unsigned lane
   exA = __shfl_sync(0xffffffffu, ex, hlA);
   fB = 32 * olA + hlB;
   endB = __shfl_sync(0xffffffffu, ex + c, hlB);
-  if (olB != olA) {                                 // rB starts the next non-empty group of bins
-    unsigned exB, cnB;
-    fine_locate<PACK16>(w, lane_excl, lane_tot, rB, fB, exB, cnB);
-    endB = exB + cnB;
-  }
+  redoB = olB != olA;         // rB starts the next non-empty group of bins: the caller locates it alone
 }
 
 // min / max of the finite values of the column
@@ -430,9 +426,20 @@ __device__ __forceinline__ void sel_make_plan(const SelWarp& w, SelPlan& P, bool
   }
   int fa[3], fb[3];
   unsigned exa[3], endb[3];
+  bool redo[3];
 #pragma unroll
-  for (int q = 0; q < 3; ++q)
-    fine_locate_pair<PACK16>(w, lex, ltot, P.rk[2 * q], P.rk[2 * q + 1], fa[q], exa[q], fb[q], endb[q]);
+  for (int q = 0; q < 3; ++q)      // three independent chains of shuffles, no branch between them
+    fine_locate_pair<PACK16>(w, lex, ltot, P.rk[2 * q], P.rk[2 * q + 1], fa[q], exa[q], fb[q], endb[q], redo[q]);
+  if (redo[0] || redo[1] || redo[2]) {
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      if (redo[q]) {
+        unsigned exB, cnB;
+        fine_locate<PACK16>(w, lex, ltot, P.rk[2 * q + 1], fb[q], exB, cnB);
+        endb[q] = exB + cnB;
+      }
+    }
+  }
   // Merge the three pair ranges [fa, fb] where they touch or overlap (small n, ties).
   int nr = 0;
 #pragma unroll
