@@ -612,7 +612,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
 #ifdef MCZ_PHASE_TIMING
       const long long tc0 = clock64();
 #endif
-      warp_percentiles<PACK16>(vals + (long long)sl * Npad, Npad, hist, cand, pc, nv, stt);
+      warp_percentiles<PACK16, GLOBAL ? 0 : SLOTS * PT / 128>(vals + (long long)sl * Npad, Npad, hist, cand, pc, nv, stt);
 #ifdef MCZ_PHASE_TIMING
       if (lane == 0) {
         const unsigned long long dt = (unsigned long long)(clock64() - tc0);

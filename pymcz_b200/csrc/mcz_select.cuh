@@ -614,7 +614,8 @@ __device__ __forceinline__ bool exact_range(const SelWarp& w, float& scale, floa
 // Whole selection of one column by one warp (mcz.py:273-301); all 32 lanes participate.
 // v has Npad (multiple of 128) readable entries; entries in [N, Npad) are NaN.
 // hist: FineHist<PACK16>::WORDS words; cand: 128 floats.
-template <bool PACK16>
+// NG: number of 128-sample groups when it is known at compile time (Npad == 128 * NG), else 0.
+template <bool PACK16, int NG>
 __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned* hist, float* cand,
                                  float pct[3], int& nvalid, int& status) {
   typedef FineHist<PACK16> FH;
@@ -648,9 +649,10 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
   // sum of the column (the atomics bound this pass, so the extra arithmetic is free here)
   float sum = 0.0f;
   FH::zero(hist, lane);
+  const int nH = NG > 0 ? NG * 128 : Npad;      // (compile-time trip count when the length is known)
   if (!has_tie) {
 #pragma unroll 2
-    for (int s0 = 4 * lane; s0 < Npad; s0 += 128) {
+    for (int s0 = 4 * lane; s0 < nH; s0 += 128) {
       const float4 x4 = *reinterpret_cast<const float4*>(v + s0);
       const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
@@ -706,9 +708,50 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
     // groups per 24-bit mask); the few members are appended after each chunk with one shared
     // atomic per lane that has any.
     constexpr int CH = 6;
+    constexpr int NCH = (NG + CH - 1) / CH;
     const int ngroups = Npad / 128;
     if (lane == 0) *w.ccount = 0u;
     __syncwarp();
+    if constexpr (NG > 0 && NCH <= 4) {
+      // known column length: straight-line code, all masks kept, members appended once at the end
+      unsigned m[NCH];
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        unsigned mask = 0u;
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+          if (c * CH + i < NG) {
+            const float4 x4 = *reinterpret_cast<const float4*>(v + 4 * lane + 128 * (c * CH + i));
+            const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float x = xs[j];
+              const int f = fine_index(x, scale, nLs);
+              const bool hit = ((unsigned)(f - tlo[0]) <= tsp[0]) || ((unsigned)(f - tlo[1]) <= tsp[1]) ||
+                               ((unsigned)(f - tlo[2]) <= tsp[2]);
+              mask |= (hit && x != skip) ? (1u << (4 * i + j)) : 0u;
+            }
+          }
+        }
+        m[c] = mask;
+      }
+      unsigned mine = 0u;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) mine += (unsigned)__popc(m[c]);
+      if (mine) {
+        unsigned pos = atomicAdd(w.ccount, mine);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          unsigned mask = m[c];
+          while (mask) {
+            const int b = __ffs(mask) - 1;
+            mask &= mask - 1u;
+            w.glist[pos & 255u] = v[4 * lane + 128 * (c * CH + (b >> 2)) + (b & 3)];
+            ++pos;
+          }
+        }
+      }
+    } else
 #pragma unroll 1
     for (int g0 = 0; g0 < ngroups; g0 += CH) {
       unsigned mask = 0u;
