@@ -316,6 +316,9 @@ production_kernel(const __grid_constant__ ProdParams p) {
     const bool ok = minimum_ok(flags);
 
     MCZ_T(tB0);
+#ifdef MCZ_PHASE_TIMING
+    long long tBL0 = tB0, tBL1 = tB0;
+#endif
     // ---- phases B and C ----------------------------------------------------------------------
     int ii1 = 0, ii2 = 0;
     int executed1 = -1;       // N2Ha trips actually executed (differs from ii1 after a proven early exit)
@@ -380,6 +383,9 @@ production_kernel(const __grid_constant__ ProdParams p) {
         // reduced together, then the reference's loop conditions are replayed trip by trip.  If a
         // loop turns out to have ended after trip a, its state is put back to that point (logq of
         // trip a is kept; Z follows from it).
+#ifdef MCZ_PHASE_TIMING
+        tBL0 = clock64();
+#endif
         while (act1 || act2) {
           float sm4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
           unsigned nanb = 0u;
@@ -490,6 +496,9 @@ production_kernel(const __grid_constant__ ProdParams p) {
           }
         }
         if (executed1 < 0) executed1 = ii1;
+#ifdef MCZ_PHASE_TIMING
+        tBL1 = clock64();
+#endif
 #pragma unroll
         for (int i = 0; i < SLOTS; ++i) {
           const int s = i * PT + tid;
@@ -642,6 +651,9 @@ production_kernel(const __grid_constant__ ProdParams p) {
       MCZ_TADD(1, tB0 - tA0);
       MCZ_TADD(2, tD0 - tB0);
       MCZ_TADD(4, tD2 - tD0);
+      MCZ_TADD(5, tBL0 - tB0);        // B prologue (loop state, constants)
+      MCZ_TADD(6, tBL1 - tBL0);       // KK04 loops
+      MCZ_TADD(7, tD0 - tBL1);        // phase C
     }
 #endif
   }

@@ -651,7 +651,7 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
   FH::zero(hist, lane);
   const int nH = NG > 0 ? NG * 128 : Npad;      // (compile-time trip count when the length is known)
   if (!has_tie) {
-#pragma unroll 2
+#pragma unroll 3
     for (int s0 = 4 * lane; s0 < nH; s0 += 128) {
       const float4 x4 = *reinterpret_cast<const float4*>(v + s0);
       const float xs[4] = {x4.x, x4.y, x4.z, x4.w};

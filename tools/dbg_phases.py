@@ -22,6 +22,7 @@ print("galaxies %d, kernel %.2f ms" % (g, a.elapsed_time(b)))
 print("cycles per galaxy: A %.0f  B+C %.0f  D own(mean over warps) %.0f  D wall %.0f  total %.0f" % (o[1]/g, o[2]/g, o[3]/g, o[4]/g, (o[1]+o[2]+o[4])/g))
 L.mcz_debug_col_cycles(cc, 1)
 cc = list(cc)
+print("B prologue %.0f  KK04 loops %.0f  phase C %.0f" % (o[5]/g, o[6]/g, o[7]/g))
 print("sample-parallel stages (cycles per galaxy): D0 %.0f  D1 %.0f  D2 %.0f  D3 %.0f" % tuple(c / g for c in cc[:4]))
 for j, k in enumerate(sc.KEYS):
     if cc[j]:
