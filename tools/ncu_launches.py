@@ -1,0 +1,28 @@
+"""Summarise an ncu launch list (`--metrics gpu__time_duration.sum --csv --log-file X.csv`) per kernel:
+   python tools/ncu_launches.py gpurun_out/launches.csv "<command that was profiled>" > profiles/<tag>_launches_summary.txt"""
+import csv
+import sys
+from collections import defaultdict
+
+
+def main(path, cmd):
+    rows = [r for r in csv.reader(open(path, errors="replace")) if r and not r[0].startswith("==")]
+    hdr = rows[0]
+    ik, iv, iu = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    tot = defaultdict(lambda: [0, 0.0])
+    for r in rows[1:]:
+        if len(r) <= iv:
+            continue
+        v = float(r[iv].replace(",", ""))
+        v *= {"ns": 1.0, "us": 1e3, "ms": 1e6, "s": 1e9}.get(r[iu], 1.0)
+        tot[r[ik][:70]][0] += 1
+        tot[r[ik][:70]][1] += v
+    allns = sum(v[1] for v in tot.values())
+    print("ncu --metrics gpu__time_duration.sum --clock-control none: %s" % cmd)
+    print("kernel, launches, total ns, share, mean ms per launch")
+    for k, (n, ns) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
+        print("%s, %d, %.0f, %.4f, %.3f" % (k, n, ns, ns / allns, ns / n / 1e6))
+
+
+if __name__ == "__main__":
+    main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else "")

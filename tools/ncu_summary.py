@@ -41,7 +41,7 @@ def main(rep, galaxies, tag, n_draw=2200):
     def num(k):
         v, u = vals[k]
         f = float(v.replace(",", ""))
-        mult = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "ms": 1e-3, "us": 1e-6, "ns": 1e-9, "s": 1.0}.get(u, 1.0)
+        mult = {"Kbyte": 1e3, "Kbyte/block": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "ms": 1e-3, "us": 1e-6, "ns": 1e-9, "s": 1.0}.get(u, 1.0)
         return f * mult
     out = {
         "kernel": vals["Kernel Name"][0], "galaxies": int(galaxies), "n_draw": n_draw,
