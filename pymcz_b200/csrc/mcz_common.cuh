@@ -102,7 +102,9 @@ template <> struct Math<float> {
   // float32 is the production arithmetic: MUFU-backed log2/exp2 scaled to base 10.
   static MCZ_HD float log10(float x) {
 #if defined(__CUDA_ARCH__)
-    return __log2f(x) * 0.30102999566398120f;
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));   // MUFU.LG2 alone: no denormal rescaling (fluxes are O(1))
+    return r * 0.30102999566398120f;
 #else
     return ::log10f(x);
 #endif

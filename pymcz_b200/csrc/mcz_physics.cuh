@@ -180,7 +180,7 @@ template <typename R> struct IterState {
   uint32_t aux;               // bits 0-1: Z_init_guess class (0: 8.2, 1: 8.4, 2: 8.7); bit 2: logN2Ha > 0.8
 };
 
-enum : uint32_t { AUX_ZI_MASK = 3u, AUX_N2HA_GT08 = 4u };
+enum : uint32_t { AUX_ZI_MASK = 3u, AUX_N2HA_GT08 = 4u, AUX_KD_VALID = 8u /* KD02_N2O2 is not NaN */ };
 
 template <typename R> MCZ_HD R calclogq(const IterState<R>& st, R Z) {
   return Math<R>::div(st.num0 + Z * st.num1, st.den0 + Z * st.den1);
@@ -430,11 +430,10 @@ MCZ_HD void phase_a(const R* f, const R* e, uint32_t flags, uint32_t tok, int du
       kd = kd02_n2o2<R>(logN2O2);
       put(K_KD02_N2O2, kd);
     }
-    (void)kd;
     carry.y = y;
     carry.n2ha = logN2Ha;
     carry.x = x;
-    carry.aux = zi | ((logN2Ha > R(0.8)) ? AUX_N2HA_GT08 : 0u);
+    carry.aux = zi | ((logN2Ha > R(0.8)) ? AUX_N2HA_GT08 : 0u) | (M::isnan(kd) ? 0u : AUX_KD_VALID);
   }
 }
 

@@ -23,6 +23,7 @@ static constexpr int PT = 576;            // threads per block: 18 warps
 static constexpr int PW = PT / 32;
 static constexpr int CAND_FLOATS = 128;   // per-warp candidate area (counter + 64-entry list)
 static constexpr int CTRL_BYTES = 1024;
+static constexpr uint32_t SEEN_KD = 1u << 8;     // ctrl->flags bit above the eight line flags
 static constexpr int DIVERGENCE_CHECK_TRIP = 8;   // when to test a still-running N2Ha loop for provable divergence
 
 struct ProdParams {
@@ -268,6 +269,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
     MCZ_T(tA0);
     // ---- phase A (repeated once in the rare case the assumed flags were wrong) ----------------
     uint32_t flags = assumed;
+    bool anykd = false;
     for (;;) {
       const int de = effective_dust(p.dust, flags);
       uint32_t seen = 0u;
@@ -297,6 +299,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
           c.y = c.n2ha = c.x = 0.0f;
           c.aux = 0u;
           phase_a<float>(f, e, flags, p.tok, de, put, c);
+          if (c.aux & AUX_KD_VALID) seen |= SEEN_KD;
           store_f32<!GLOBAL>(st0 + s, st0_sa + 4u * (unsigned)s, c.y);
           store_f32<!GLOBAL>(st1 + s, st1_sa + 4u * (unsigned)s, c.n2ha);
           store_f32<!GLOBAL>(st2 + s, st2_sa + 4u * (unsigned)s, c.x);
@@ -308,9 +311,14 @@ production_kernel(const __grid_constant__ ProdParams p) {
       seen = __reduce_or_sync(0xffffffffu, seen);
       if (lane == 0 && seen) atomicOr(&ctrl->flags, seen);
       __syncthreads();
-      const uint32_t actual = ctrl->flags;
+      const uint32_t all = ctrl->flags;
+      const uint32_t actual = all & F_ALL;
+      anykd = (all & SEEN_KD) != 0u;          // some sample has a KD02_N2O2 value (start of the N2Ha loop)
       if (actual == flags) break;
       flags = actual;               // deterministic samples: the second pass reproduces `actual`
+      __syncthreads();              // (rare path) drop the KD bit of the discarded pass
+      if (tid == 0) ctrl->flags = actual;
+      __syncthreads();
     }
     const uint64_t pm = present_mask(flags, p.tok);
     const bool ok = minimum_ok(flags);
@@ -361,8 +369,9 @@ production_kernel(const __grid_constant__ ProdParams p) {
             tU0[i] = st.U0; tU1[i] = st.U1; tL0[i] = st.L0; tL1[i] = st.L1;
           }
         }
-        // (barrier: every thread has read its stash entries before the constants overwrite them)
-        const bool anykd = __syncthreads_or(any);
+        // (no barrier: a thread overwrites only the stash entries it has just read itself; whether
+        // any sample has a KD02_N2O2 value was collected with the line flags in phase A)
+        (void)any;
 #pragma unroll
         for (int i = 0; i < SLOTS; ++i) {
           const int s = i * PT + tid;
