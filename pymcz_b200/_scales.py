@@ -27,7 +27,7 @@ T_ALL = T_D02 | T_Z94 | T_M91 | T_PP04 | T_P10 | T_M08 | T_M13 | T_KD02
 
 _TOKEN_BITS = {
     'all': T_ALL, 'D02': T_D02, 'Z94': T_Z94, 'M91': T_M91, 'PP04': T_PP04, 'P10': T_P10,
-    'M08': T_M08, 'M13': T_M13, 'KD02': T_KD02, 'P05': T_P05, 'C01': T_C01, 'P01': T_P01,
+    'M08': T_M08, 'M08all': T_M08ALL, 'M13': T_M13, 'KD02': T_KD02, 'P05': T_P05, 'C01': T_C01, 'P01': T_P01,
     'DP00': T_DP00, 'D16': T_D16,
     # README.md:55-56 advertises "KD02comb"; the reference's dispatch matches nothing for it
     # (metallicity.py:251).  Documented deviation: treated as an alias of KD02.
@@ -35,8 +35,6 @@ _TOKEN_BITS = {
 }
 #: tokens whose arithmetic lives in third-party code the reference does not vendor
 THIRD_PARTY_TOKENS = ('D13', 'D13all', 'PM14')
-#: tokens recognised but not built yet
-UNBUILT_TOKENS = ('M08all',)
 
 DUST_NONE, DUST_ON, DUST_ON_IGNORING = 0, 1, 2
 ST_OK, ST_ABSENT, ST_EMPTY, ST_NONPOS, ST_NODIST = 0, 1, 2, 3, 4
@@ -53,9 +51,6 @@ def parse_md(mds: str):
             mask |= _TOKEN_BITS[tok]
         elif tok in THIRD_PARTY_TOKENS:
             third.append(tok)
-        elif tok in UNBUILT_TOKENS:
-            raise NotImplementedError(
-                "--md %s: the extra Maiolino+08 calibrators are not built yet (SURVEY.md 8 f-3)" % tok)
         else:
             unknown.append(tok)
     return mask, third, unknown

@@ -72,7 +72,6 @@ int mcz_forward_replay(const double* flux_d, const double* noise_d, long long G,
                        unsigned long long* present_d, int* trips_d, int* ret_d, void* scratch_d,
                        size_t scratch_bytes, void* stream) {
   if (!flux_d || !Z_d || !present_d || !trips_d || !ret_d) return set_error("mcz_forward_replay: null pointer");
-  if (tokens & T_M08ALL) return set_error("mcz_forward_replay: M08all is not built yet");
   if (precision != 0 && precision != 1) return set_error("mcz_forward_replay: precision must be 0 or 1");
   if ((tokens & (T_D02 | T_M13)) && !noise_d) return set_error("mcz_forward_replay: D02/M13 need noise_d");
   return launch_replay(flux_d, noise_d, G, N, tokens, dust, precision, Z_d, present_d, trips_d, ret_d,

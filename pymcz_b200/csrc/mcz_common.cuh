@@ -30,6 +30,10 @@ enum Key : int {
   NKEYS = 37
 };
 
+// keys that are present but NaN for every sample (the reference's `highZ is True` tests never hold
+// for a numpy.bool_, metscales.py:1013-1018, 1030-1047): never stored, reported as n = 0
+MCZ_HD bool const_nan_key(int k) { return k == K_M08_R23 || k == K_M08_O3HB || k == K_M08_O2HB; }
+
 // ---- input lines (mcz.py:45) ------------------------------------------------------------------
 enum Line : int {
   L_O2 = 0, L_HB, L_O34959, L_O3, L_O1, L_HA, L_N2, L_S2A, L_S2B, L_S39069, L_S39532, NLINES = 11

@@ -52,6 +52,10 @@ MCZ_HD uint64_t present_mask(uint32_t f, uint32_t tok) {
   set(K_M08_O3O2, m08 && o3o2);                                   // metscales.py:975
   set(K_M08_N2HA, m08 && n2 && ha);                               // metscales.py:993
   set(K_M08_R23, m08 && r23);                                     // metscales.py:1003-1009
+  const bool m08all = (tok & T_M08ALL) != 0;
+  set(K_M08_O3HB, m08all && o3hb);                                // metscales.py:1024 (logO3Hb is not None)
+  set(K_M08_O2HB, m08all && o2 && hb);                            // metscales.py:1036 (logO2Hb is not None)
+  set(K_M08_O3N2, m08all && o3 && n2);                            // metscales.py:1051
   set(K_M13_N2, (tok & T_M13) && ha && n2);                       // metscales.py:943-950
   set(K_M13_O3N2, (tok & T_M13) && ha && n2 && hb && o3);         // metscales.py:951
   set(K_KD02_N2O2, (tok & T_KD02) && n2 && o2 && ha && hb);       // metscales.py:1076
@@ -168,6 +172,37 @@ template <typename R> MCZ_HD R m08_o3o2(R y) {
   const R x = Math<R>::div(R(2.0) * cp, Math<R>::sqrt(D) + R(1.3881));
   const R Z = x + R(8.69);
   return (Z >= R(7.1) && Z <= R(9.4)) ? Z : Math<R>::nan();
+}
+
+// t(s) for the M08 [OIII]/[NII] cubic (metscales.py:1051-1057)
+template <typename R> MCZ_HD R rt_m08o3n2_t(R s) {
+  R t;
+  if (s < R(RT_M08O3N2_SEG0_HI)) {
+    const double c[] = {RT_M08O3N2_SEG0_POLY(MCZ_RT_X)};
+    t = horner_desc<R>(c, (s - R(RT_M08O3N2_SEG0_MID)) * R(RT_M08O3N2_SEG0_RHALF));
+  } else if (s < R(RT_M08O3N2_SEG1_HI)) {
+    const double c[] = {RT_M08O3N2_SEG1_POLY(MCZ_RT_X)};
+    t = horner_desc<R>(c, (s - R(RT_M08O3N2_SEG1_MID)) * R(RT_M08O3N2_SEG1_RHALF));
+  } else {
+    const double c[] = {RT_M08O3N2_SEG2_POLY(MCZ_RT_X)};
+    t = horner_desc<R>(c, (s - R(RT_M08O3N2_SEG2_MID)) * R(RT_M08O3N2_SEG2_RHALF));
+  }
+  return rt_polish<R>(t, s, RT_M08O3N2_H0, RT_M08O3N2_H1, RT_M08O3N2_H2);
+}
+
+// M08 [OIII]/[NII] of --md M08all (metscales.py:1051-1059): cubic 0.1347 x^3 - 0.7170 x^2 -
+// 2.6096 x + 0.4520 - y = 0, first root (np.roots order) with root+8.69 in [7.1, 9.4].  Inside the
+// window the cubic has one local maximum f0 at x0 = -1.325; its other extremum (x = 4.87) and the
+// largest root are far outside.  np.roots lists [largest, smallest, middle], so the smallest root
+// x0 + t(-s) wins once it is inside the window (y >= f(-1.59)), else the middle one x0 + t(+s)
+// (inside while y >= f(0.71)).  Non-finite y: constant coefficient zeroed -> root 0 -> 8.69.
+template <typename R> MCZ_HD R m08_o3n2(R y) {
+  if (!Math<R>::isfinite(y)) return R(0.0) + R(8.69);
+  const R d = R(RT_M08O3N2_F0) - y;
+  if (!(d >= R(0)) || y < R(RT_M08O3N2_F_HI)) return Math<R>::nan();
+  const R s = Math<R>::sqrt(d);
+  const R t = rt_m08o3n2_t<R>(y >= R(RT_M08O3N2_F_LO) ? -s : s);
+  return (R(RT_M08O3N2_X0) + t) + R(8.69);
 }
 
 // ---- per-sample state carried into the KK04 iterations ----------------------------------------
@@ -361,6 +396,12 @@ MCZ_HD void phase_a(const R* f, const R* e, uint32_t flags, uint32_t tok, int du
     if (o3o2) put(K_M08_O3O2, m08_o3o2<R>(logO35007O2));
     if (n2 && ha) put(K_M08_N2HA, m08_n2ha<R>(logN2Ha));
     if (r23ok) put(K_M08_R23, nan);            // `highZ is True` never holds for numpy.bool_ (:1013-1018)
+    if (tok & T_M08ALL) {                                                 // metscales.py:1024-1059
+      if (o3hb) put(K_M08_O3HB, nan);          // same dead `highZ is True / is False` tests (:1030, :1033)
+      if (o2 && hb) put(K_M08_O2HB, nan);      // (:1042, :1045)
+      // log10(O3/N2) MINUS the dust term: the reference adds dustcorrect() to the coefficient (:1054-1055)
+      if (o3 && n2) put(K_M08_O3N2, m08_o3n2<R>(lO3 - lN2 - a * R(MCZ_K_O35007 - MCZ_K_N2)));
+    }
   }
 
   if ((tok & T_M13) && ha && n2) {                                        // metscales.py:948-959

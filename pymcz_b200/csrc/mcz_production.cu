@@ -150,8 +150,8 @@ template <bool SHARED> struct SlotPut {
   uint32_t saddr;             // shared-space byte address of col (SHARED only)
   __device__ __forceinline__ void operator()(int key, float v) const {
     // every key the physics can emit under the launch's tokens owns a column, except the
-    // constant-NaN M08_R23 (reference metscales.py:1013-1018), which is never stored
-    if (key == K_M08_R23) return;
+    // constant-NaN ones (M08_R23, M08_O3Hb, M08_O2Hb: const_nan_key), which are never stored
+    if (const_nan_key(key)) return;
     if (SHARED) asm volatile("st.shared.f32 [%0], %1;" :: "r"(saddr + 4u * (unsigned)col_off[key]), "f"(v) : "memory");
     else col[col_off[key]] = v;
   }
@@ -679,7 +679,7 @@ static void build_slots(uint32_t tok, ProdParams& p) {
   }
   int keys[NKEYS];
   for (int k = 0; k < NKEYS; ++k)
-    if (((pm >> k) & 1ull) && k != K_M08_R23) keys[n++] = k;
+    if (((pm >> k) & 1ull) && !const_nan_key(k)) keys[n++] = k;
   p.nstore = n;
   // Slot s is selected by warp s % 18, and warps 0, 4, 8, 12, 16 share one SM sub-partition: with 17
   // columns it is the only one that runs five selections at once.  Give it the columns that are
@@ -690,7 +690,7 @@ static void build_slots(uint32_t tok, ProdParams& p) {
   int pos = 0;
   for (int k : often_empty) {
     if (pos >= n || pos >= 18) break;
-    if (!((pm >> k) & 1ull) || k == K_M08_R23) continue;
+    if (!((pm >> k) & 1ull) || const_nan_key(k)) continue;
     p.slot_of_key[k] = (signed char)pos;
     p.key_of_slot[pos] = (signed char)k;
     placed[k] = true;
@@ -816,7 +816,6 @@ int launch_production(const float* meas, const float* err, long long G, long lon
                       size_t scratch_bytes, cudaStream_t stream) {
   if (G <= 0) return 0;
   if (n_draw <= 0 || n_draw > 0x7fffffffll / 64) return set_error("mcz_forward_production: bad n_draw");
-  if (tok & T_M08ALL) return set_error("mcz_forward_production: M08all is not built yet");
   ProdParams p;
   build_slots(tok, p);
   const ProdPlan pl = make_plan(G, n_draw, p.nstore);

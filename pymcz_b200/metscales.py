@@ -206,8 +206,8 @@ class diagnostics:
         return self._run(sc.T_M13, _GROUP_KEYS[sc.T_M13])
 
     def calcM08(self, allM08=False):
-        if allM08:
-            raise NotImplementedError("M08all: the extra Maiolino+08 calibrators are not built yet")
+        if allM08:                                                         # metscales.py:1019-1059
+            return self._run(sc.T_M08ALL, _GROUP_KEYS[sc.T_M08] + ["M08_O3Hb", "M08_O2Hb", "M08_O3N2", "logR23"])
         return self._run(sc.T_M08, _GROUP_KEYS[sc.T_M08] + ["logR23"])
 
     def calcKD02_N2O2(self):

@@ -105,3 +105,20 @@ extern "C" void hostemu_philox(unsigned c0, unsigned c1, unsigned c2, unsigned c
   mcz::philox4x32_10(c0, c1, c2, c3, k0, k1, o);
   for (int i = 0; i < 4; ++i) out[i] = o[i];
 }
+
+// The closed-form root selections on their own: which = 0 KD02 [NII]/[OII], 1 M08 [NII]/Ha,
+// 2 M08 [OIII]/[OII], 3 M08 [OIII]/[NII] (M08all); y = the log ratio the reference subtracts from
+// the constant coefficient.
+extern "C" void hostemu_roots(int which, int use_float, const double* y, int n, double* out) {
+  using namespace mcz;
+  for (int i = 0; i < n; ++i) {
+    if (use_float) {
+      const float v = (float)y[i];
+      out[i] = which == 0 ? kd02_n2o2<float>(v) : which == 1 ? m08_n2ha<float>(v)
+               : which == 2 ? m08_o3o2<float>(v) : m08_o3n2<float>(v);
+    } else {
+      out[i] = which == 0 ? kd02_n2o2<double>(y[i]) : which == 1 ? m08_n2ha<double>(y[i])
+               : which == 2 ? m08_o3o2<double>(y[i]) : m08_o3n2<double>(y[i]);
+    }
+  }
+}

@@ -28,7 +28,7 @@ def measured_dict(meas_row, err_row, sample):
     return {k: meas_row[j] * np.ones(len(sample)) + err_row[j] * sample for j, k in enumerate(sc.LINES)}
 
 
-@pytest.mark.parametrize("mds,dust", [("all", True), ("all", False), ("KD02", True), ("D02,M13,PP04,P05,C01,D16", True)])
+@pytest.mark.parametrize("mds,dust", [("all", True), ("all", False), ("KD02", True), ("D02,M13,PP04,P05,C01,D16", True), ("M08all,Z94", True)])
 def test_calculation_matches_oracle_same_seed(mds, dust):
     sm, se = synthetic_table(6, config=4)
     meas, err = np.concatenate([EX_M, sm]), np.concatenate([EX_E, se])
@@ -85,6 +85,11 @@ def test_individual_calc_methods():
     for k in ("E(B-V)", "logR23", "Z94", "PP04_N2Ha", "PP04_O3N2", "KD02_N2O2", "KK04_N2Ha", "KK04_R23", "M91", "KD02comb"):
         assert np.allclose(s.mds[k], d.mds[k], rtol=0, atol=1e-8, equal_nan=True), k
     assert s.mds["D02"] is None
+    s.calcM08(allM08=True)                                    # metscales.py:969-1059
+    d2, _, _ = orc.calculation(flux.copy(), "M08all", True, False, "batched")
+    for k in ("M08_R23", "M08_N2Ha", "M08_O3O2", "M08_O3Hb", "M08_O2Hb", "M08_O3N2"):
+        assert np.allclose(s.mds[k], d2.mds[k], rtol=0, atol=1e-8, equal_nan=True), k
+    assert np.all(np.isnan(s.mds["M08_O3Hb"])) and np.isfinite(s.mds["M08_O3N2"]).any()
     assert s.calcpyqz() == -1 and s.calcPM14() == -1          # third-party scales: warn, stay None
 
 

@@ -68,7 +68,7 @@ def oracle_on_kernel_samples(meas, err, n, seed, goff, mds, dust, correlated):
 
 @pytest.mark.parametrize("mds,dust,correlated,n", [("all", True, False, 2200), ("all", False, True, 700),
                                                    ("KD02", True, False, 2304),
-                                                   ("P05,C01,P01,DP00,D16,all", True, False, 1000)])
+                                                   ("P05,C01,P01,DP00,D16,M08all,all", True, False, 1000)])
 def test_per_sample_values_vs_oracle(mds, dust, correlated, n):
     sm, se = synthetic_table(40, config=4)
     meas, err = np.concatenate([EX_M, sm]), np.concatenate([EX_E, se])

@@ -57,7 +57,7 @@ CASES = [("example_corr", EX_M, EX_E, 200, 200, "correlated", "all", True),
          ("example_shuf", EX_M, EX_E, 200, 201, "shuffled", "all", True),
          ("example_nodust", EX_M, EX_E, 200, 202, "correlated", "all", False),
          ("tokens", *synthetic_table(12, config=3), 100, 203, "shuffled",
-          "P05,C01,P01,DP00,D16,M08,KD02,D02,M13", True),
+          "P05,C01,P01,DP00,D16,M08all,KD02,D02,M13", True),
          ("kd02only", *synthetic_table(12, config=3), 100, 204, "correlated", "KD02", True),
          ("synth_all", *synthetic_table(96, config=4), 300, 205, "shuffled", "all", True)]
 

@@ -25,8 +25,7 @@ def test_parse_md_tokens():
     m, third, unk = sc.parse_md("KD02,D13,foo,P05")
     assert m == sc.T_KD02 | sc.T_P05 and third == ["D13"] and unk == ["foo"]
     assert sc.parse_md("KD02comb")[0] == sc.T_KD02          # documented alias (README.md:55-56)
-    with pytest.raises(NotImplementedError):
-        sc.parse_md("M08all")
+    assert sc.parse_md("M08all")[0] == sc.T_M08ALL            # metallicity.py:243-246
     # `all` omits P05 (metallicity.py:178) and the deprecated scales
     assert not (sc.T_ALL & (sc.T_P05 | sc.T_C01 | sc.T_P01 | sc.T_DP00 | sc.T_D16))
 

@@ -22,6 +22,7 @@ OUT = os.path.join(os.path.dirname(HERE), "pymcz_b200", "csrc", "mcz_root_tables
 
 N2O2 = ["1106.8660", "-532.15451", "96.373260", "-7.8106123", "0.23928247"]   # metscales.py:146,419
 M08_N2HA = ["-0.7732", "1.2357", "-0.2811", "-0.7201", "-0.3330"]             # metscales.py:62
+M08_O3N2 = ["0.4520", "-2.6096", "-0.7170", "0.1347", "0"]                    # metscales.py:66 (cubic)
 
 
 def as_double_exact(strs):
@@ -29,12 +30,16 @@ def as_double_exact(strs):
     return [mp.mpf(float(s)) for s in strs]
 
 
-def real_extremum(c):
+def real_extremum(c, window=None):
     d = [c[i] * i for i in range(1, 5)]
+    while d and d[-1] == 0:
+        d.pop()                                   # cubic padded to five coefficients
     roots = mp.polyroots(d[::-1], maxsteps=200, extraprec=200)
-    real = [r for r in roots if abs(mp.im(r)) < mp.mpf(10) ** -40]
+    real = [mp.re(r) for r in roots if abs(mp.im(r)) < mp.mpf(10) ** -40]
+    if window is not None:                        # a cubic has two extrema: take the one in the window
+        real = [r for r in real if window[0] <= r <= window[1]]
     assert len(real) == 1, roots
-    return mp.re(real[0])
+    return real[0]
 
 
 def recentre(c, x0):
@@ -80,9 +85,9 @@ def fit(d, sgn, s_lo, s_hi, deg):
     return mid, half, mono, np.max(np.abs(p64 - tg)), np.max(np.abs(acc.astype(np.float64) - tg))
 
 
-def emit(name, c_strs, lo_x, hi_x, breaks, deg):
+def emit(name, c_strs, lo_x, hi_x, breaks, deg, window=None):
     c = as_double_exact(c_strs)
-    x0 = real_extremum(c)
+    x0 = real_extremum(c, window)
     d = recentre(c, x0)
     sgn = 1 if d[2] > 0 else -1
     f0 = d[0]
@@ -121,7 +126,8 @@ def emit(name, c_strs, lo_x, hi_x, breaks, deg):
 def main():
     parts = ["// GENERATED by tools/gen_root_tables.py -- do not edit.",
              "// Closed-form root tables replacing np.roots for the KD02 [NII]/[OII] quartic",
-             "// (/root/reference/pyMCZ/metscales.py:419-423) and the M08 [NII]/Ha quartic (:995-999).",
+             "// (/root/reference/pyMCZ/metscales.py:419-423), the M08 [NII]/Ha quartic (:995-999) and the",
+             "// M08 [OIII]/[NII] cubic of --md M08all (:1051-1059).",
              "#pragma once", ""]
     # KD02_N2O2: valid |root| in [7.5, 9.4] (metscales.py:1086)
     parts.append(emit("rt_n2o2", N2O2, "7.5", "9.4", [0.55], 10))
@@ -130,6 +136,11 @@ def main():
     lo = mp.mpf(float("7.1")) - mp.mpf(float("8.69"))
     hi = mp.mpf(float("9.4")) - mp.mpf(float("8.69"))
     parts.append(emit("rt_m08n2", M08_N2HA, mp.nstr(lo, 25), mp.nstr(hi, 25), [-1.3, -1.0, -0.6], 10))
+    parts.append("")
+    # M08_O3N2 (M08all, metscales.py:1051-1059): cubic, local maximum inside the window; the other
+    # extremum (x = 4.87) and the third root (x ~ 7.4 .. 8) are far outside [7.1, 9.4] - 8.69
+    parts.append(emit("rt_m08o3n2", M08_O3N2, mp.nstr(lo, 25), mp.nstr(hi, 25), [0.6, 1.3], 10,
+                      window=(lo, hi)))
     parts.append("")
     open(OUT, "w").write("\n".join(parts))
     print("wrote", OUT)
