@@ -108,6 +108,15 @@ int mcz_forward_production(const float* meas_d, const float* err_d, long long G,
 int mcz_debug_counters(unsigned long long* out8, int reset) { return read_sel_counters(out8, reset); }
 
 // [0] galaxies, [1] N2Ha loop trips executed, [2] R23 loop trips executed, [3] proven-divergence early exits
+// test entry point (not part of the public header): the production kernel's warp selection on
+// caller-supplied float32 columns cols_d[ncols][N]; padded_d (ncols * roundup(N,128) floats) is
+// needed for N > 2304 only
+int mcz_debug_select_columns(const float* cols_d, long long ncols, long long N, float* pct_d, int* nvalid_d,
+                             signed char* status_d, float* padded_d, void* stream) {
+  if (!cols_d || !pct_d || !nvalid_d || !status_d) return set_error("mcz_debug_select_columns: null pointer");
+  return launch_select_columns(cols_d, ncols, N, pct_d, nvalid_d, status_d, padded_d, (cudaStream_t)stream);
+}
+
 int mcz_debug_trip_counters(unsigned long long* out4, int reset) { return read_trip_counters(out4, reset); }
 int mcz_debug_col_cycles(unsigned long long* out74, int reset) { return read_col_cycles(out74, reset); }
 int mcz_debug_phase_cycles(unsigned long long* out8, int reset) { return read_phase_cycles(out8, reset); }

@@ -22,6 +22,8 @@ int read_trip_counters(unsigned long long* out4, int reset);
 int read_col_cycles(unsigned long long* out, int reset);
 int read_phase_cycles(unsigned long long* out8, int reset);
 int read_sel_counters(unsigned long long* out8, int reset);
+int launch_select_columns(const float* cols_d, long long ncols, long long N, float* pct_d, int* nvalid_d,
+                          signed char* status_d, float* padded_d, cudaStream_t stream);
 size_t production_scratch_bytes(long long G, long long n_draw, uint32_t tok);
 int launch_production(const float* meas, const float* err, long long G, long long n_draw, uint32_t tok,
                       int dust, unsigned long long seed, unsigned long long galaxy_offset,

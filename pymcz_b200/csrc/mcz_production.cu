@@ -857,4 +857,58 @@ int launch_production(const float* meas, const float* err, long long G, long lon
   return check_cuda(cudaGetLastError(), "production_kernel launch");
 }
 
+// ---- selection on caller-supplied columns (test entry point) -----------------------------------
+// One warp per column, exactly the code phase D runs: cols[ncols][N] f32 in global memory are
+// staged into a shared-memory column of NG*128 floats (NaN padding) or, for longer columns, into a
+// padded global scratch, then warp_percentiles() is called.  Lets the tests feed the selection
+// with distributions the physics never produces (ties, outliers, two-point, sorted, denormals).
+template <int NG>
+__global__ void __launch_bounds__(128, 1)
+select_columns_kernel(const float* __restrict__ cols, int ncols, int N, int Npad, float* __restrict__ padded,
+                      float* __restrict__ pct, int* __restrict__ nvalid, signed char* __restrict__ status) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  constexpr bool SH = NG > 0;
+  typedef FineHist<SH> FH;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 4 + warp;
+  if (c >= ncols) return;
+  unsigned char* mine = smem + (size_t)warp * ((SH ? NG * 128 * 4 : 0) + FH::BYTES + 512);
+  float* col = SH ? reinterpret_cast<float*>(mine) : padded + (long long)c * Npad;
+  unsigned* hist = reinterpret_cast<unsigned*>(mine + (SH ? NG * 128 * 4 : 0));
+  float* cand = reinterpret_cast<float*>(mine + (SH ? NG * 128 * 4 : 0) + FH::BYTES);
+  for (int s = lane; s < Npad; s += 32) col[s] = s < N ? cols[(long long)c * N + s] : Math<float>::nan();
+  __syncwarp();
+  float pc[3];
+  int nv, st;
+  warp_percentiles<SH, NG>(col, Npad, hist, cand, pc, nv, st);
+  if (lane == 0) {
+    pct[3 * c] = pc[0]; pct[3 * c + 1] = pc[1]; pct[3 * c + 2] = pc[2];
+    nvalid[c] = nv;
+    status[c] = (signed char)st;
+  }
+}
+
+int launch_select_columns(const float* cols_d, long long ncols, long long N, float* pct_d, int* nvalid_d,
+                          signed char* status_d, float* padded_d, cudaStream_t stream) {
+  if (ncols <= 0 || N <= 0) return 0;
+  const int grid = (int)((ncols + 3) / 4);
+  if (N <= 18 * 128) {
+    const size_t sm = 4 * (size_t)(18 * 128 * 4 + FineHist<true>::BYTES + 512);
+    static bool done = false;
+    if (!done) {
+      const int rc = check_cuda(cudaFuncSetAttribute(select_columns_kernel<18>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm), "smem attribute");
+      if (rc) return rc;
+      done = true;
+    }
+    select_columns_kernel<18><<<grid, 128, sm, stream>>>(cols_d, (int)ncols, (int)N, 18 * 128, nullptr, pct_d, nvalid_d, status_d);
+  } else {
+    if (!padded_d) return set_error("mcz_debug_select_columns: columns longer than 2304 need the padded scratch");
+    const int Npad = (int)((N + 127) / 128 * 128);
+    const size_t sm = 4 * (size_t)(FineHist<false>::BYTES + 512);
+    select_columns_kernel<0><<<grid, 128, sm, stream>>>(cols_d, (int)ncols, (int)N, Npad, padded_d, pct_d, nvalid_d, status_d);
+  }
+  count_launch();
+  return check_cuda(cudaGetLastError(), "select_columns_kernel launch");
+}
+
 }  // namespace mcz

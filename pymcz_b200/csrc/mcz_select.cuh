@@ -16,8 +16,9 @@
 // prefix (the clamped E(B-V) = 1e-5) is counted by vote, left out of the lists and merged back by
 // rank.  A range that still holds more than 64 samples is "crowded": pass G records the exact
 // min / max of its members and how many equal the min (a tie is then answered at once), and
-// select_in_interval() runs further rounds restricted to [min, max].  Every such round leaves
-// at least two non-empty bins, so the member count strictly decreases and the loop terminates.
+// select_in_interval() runs further rounds restricted to [min, max] of the one bin that holds
+// both ranks (two ranks in different bins are the max of one and the min of the other), so the
+// interval shrinks by at least 1024x per round and the loop terminates.
 #pragma once
 
 namespace mcz {
@@ -241,6 +242,12 @@ __device__ __forceinline__ void column_minmax(const SelWarp& w, float& mn, float
   }
 }
 
+// Order-preserving image of a float in the unsigned integers (-0 and +0 coincide).
+__device__ __forceinline__ unsigned ordered_bits(float x) {
+  const int b = __float_as_int(x);
+  return b >= 0 ? (unsigned)b + 0x80000000u : 0x80000000u - ((unsigned)b & 0x7fffffffu);
+}
+
 // Exact order statistics inside an interval: 0-based ranks rA <= rB <= rA+1 among the finite
 // values x with lo <= x <= hi (there are more than rB of them).
 template <bool PACK16>
@@ -249,17 +256,23 @@ __device__ void select_in_interval(const SelWarp& w, float lo, float hi, unsigne
   typedef FineHist<PACK16> FH;
   const float pinf = __int_as_float(0x7f800000), ninf = __int_as_float(0xff800000);
   bool haveA = false;
-  for (;;) {
+  // (each round divides the bit-pattern span by >= 512, so 4 rounds always suffice; the cap only
+  // guards the GPU against a hang should that reasoning ever be wrong)
+  for (int round = 0; round < 16; ++round) {
     sel_count(SEL_ROUNDS);
 #ifdef MCZ_COLTIME_DUMP
     w.dbg += 256;
 #endif
-    const float scale = (float)FB / (hi - lo), nLs = -lo * scale;
-    if (!(hi > lo) || !finite_f(scale) || !finite_f(nLs)) {   // all equal (or denormal spacing)
+    // The index of these rounds is taken from the ordered bit patterns, (u(x) - u(lo)) >> shift with
+    // the shift that maps [lo, hi] onto < 1024 bins: monotone like the float index of the first
+    // round, but free of overflow whatever the spacing (denormals, values near FLT_MAX).
+    const unsigned ulo = ordered_bits(lo), uspan = ordered_bits(hi) - ulo;
+    if (!(hi > lo) || uspan == 0u) {                    // all equal
       if (!haveA) outA = lo;
       outB = lo;
       return;
     }
+    const int shift = max(0, 22 - __clz(uspan));       // uspan >> shift in [1, 1023]
     FH::zero(w.hist, w.lane);
     for (int g = 0; g < w.ngroups; ++g) {
       const float4 x4 = *reinterpret_cast<const float4*>(w.v + 4 * w.lane + 128 * g);
@@ -267,7 +280,7 @@ __device__ void select_in_interval(const SelWarp& w, float lo, float hi, unsigne
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float x = xs[j];
-        if (4 * g + j < w.nmine && x >= lo && x <= hi) FH::add(w.hist, fine_index(x, scale, nLs));   // NaN fails
+        if (4 * g + j < w.nmine && x >= lo && x <= hi) FH::add(w.hist, (int)((ordered_bits(x) - ulo) >> shift));   // NaN fails
       }
     }
     unsigned lex, ltot, n;
@@ -276,10 +289,37 @@ __device__ void select_in_interval(const SelWarp& w, float lo, float hi, unsigne
     unsigned ea, ca, eb, cb;
     fine_locate<PACK16>(w, lex, ltot, rA, fa, ea, ca);
     fine_locate<PACK16>(w, lex, ltot, rB, fb, eb, cb);
-    const unsigned m = (fa == fb) ? ca : ca + cb;        // nothing lies between two consecutive ranks
+    if (fa != fb) {
+      // Two consecutive ranks in different bins: nothing lies between them, so rA is the largest
+      // member of bin fa and rB the smallest member of bin fb.  (Narrowing to [min, max] of the
+      // two bins would not shrink the interval when they are its two ends.)
+      float mxA = ninf, mnB = pinf;
+      for (int g = 0; g < w.ngroups; ++g) {
+        const float4 x4 = *reinterpret_cast<const float4*>(w.v + 4 * w.lane + 128 * g);
+        const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float x = xs[j];
+          if (4 * g + j < w.nmine && x >= lo && x <= hi) {
+            const int f = (int)((ordered_bits(x) - ulo) >> shift);
+            if (f == fa) mxA = fmaxf(mxA, x);
+            if (f == fb) mnB = fminf(mnB, x);
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        mxA = fmaxf(mxA, __shfl_xor_sync(0xffffffffu, mxA, o));
+        mnB = fminf(mnB, __shfl_xor_sync(0xffffffffu, mnB, o));
+      }
+      if (!haveA) outA = mxA;
+      outB = mnB;
+      return;
+    }
+    const unsigned m = ca;                               // both ranks in bin fa
     if (w.lane == 0) *w.ccount = 0u;
     __syncwarp();
-    const unsigned span = (unsigned)(fb - fa);
+    const unsigned span = 0u;
     if (m <= 64u) {
       for (int g = 0; g < w.ngroups; ++g) {
         const float4 x4 = *reinterpret_cast<const float4*>(w.v + 4 * w.lane + 128 * g);
@@ -287,7 +327,7 @@ __device__ void select_in_interval(const SelWarp& w, float lo, float hi, unsigne
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float x = xs[j];
-          const unsigned d = (unsigned)(fine_index(x, scale, nLs) - fa);
+          const unsigned d = ((ordered_bits(x) - ulo) >> shift) - (unsigned)fa;
           if (4 * g + j < w.nmine && x >= lo && x <= hi && d <= span) w.clist[atomicAdd(w.ccount, 1u) & 63u] = x;
         }
       }
@@ -300,7 +340,8 @@ __device__ void select_in_interval(const SelWarp& w, float lo, float hi, unsigne
       __syncwarp();
       return;
     }
-    // crowded: narrow to the exact range of the members of [fa, fb]
+    // crowded: narrow to the exact range of the members of bin fa (at most 1/1024 of the interval,
+    // so the rounds terminate: the interval shrinks until it is a single value)
     float mn = pinf, mx = ninf;
     int neq = 0;
     for (int g = 0; g < w.ngroups; ++g) {
@@ -309,7 +350,7 @@ __device__ void select_in_interval(const SelWarp& w, float lo, float hi, unsigne
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float x = xs[j];
-        const unsigned d = (unsigned)(fine_index(x, scale, nLs) - fa);
+        const unsigned d = ((ordered_bits(x) - ulo) >> shift) - (unsigned)fa;
         if (4 * g + j < w.nmine && x >= lo && x <= hi && d <= span) {
           if (x < mn) { mn = x; neq = 1; }
           else if (x == mn) ++neq;
@@ -331,6 +372,8 @@ __device__ void select_in_interval(const SelWarp& w, float lo, float hi, unsigne
     lo = gm;
     hi = mx;
   }
+  if (!haveA) outA = lo;
+  outB = lo;
 }
 
 // Robust fine-index range of a column from its first 64 samples (i.i.d. draws: any fixed subset is
