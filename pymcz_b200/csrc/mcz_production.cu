@@ -550,31 +550,114 @@ production_kernel(const __grid_constant__ ProdParams p) {
             F[10ll * Npad + s] = z1;
           }
         }
+        // Two trips per barrier, as in the register variant: the ten constants of a sample are read
+        // once for both trips (this loop is bound by L2 bandwidth), logq after the first trip is
+        // kept in F[14], F[15] so that a loop that turns out to have ended there can be put back.
         while (act1 || act2) {
-          float s1 = 0.0f, s2 = 0.0f;
+          float sm4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+          unsigned nanb = 0u;
+#pragma unroll 2
           for (int s = tid; s < N; s += PT) {
-            IterState<float> st;
-            st.num0 = F[0ll * Npad + s]; st.num1 = F[1ll * Npad + s]; st.den0 = F[2ll * Npad + s];
-            st.den1 = F[3ll * Npad + s];
-            st.aux = __float_as_uint(st3[s]);
+            const float num0 = F[0ll * Npad + s], num1 = F[1ll * Npad + s], den0 = F[2ll * Npad + s];
+            const float den1 = F[3ll * Npad + s];
             if (act1) {
-              st.A = F[4ll * Npad + s]; st.B = F[5ll * Npad + s];
-              st.Z1 = F[10ll * Npad + s]; st.lq1 = F[12ll * Npad + s];
-              s1 += kk04_n2ha_trip<float>(st);
-              F[10ll * Npad + s] = st.Z1; F[12ll * Npad + s] = st.lq1;
+              const float cA = F[4ll * Npad + s], cB = F[5ll * Npad + s];
+              const float Z1 = F[10ll * Npad + s], lq1 = F[12ll * Npad + s];
+              const float lq = (num0 + Z1 * num1) * fast_rcp(den0 + Z1 * den1);        // metscales.py:1112-1118
+              const float z = cA - lq * cB;
+              float d = fabsf(lq - lq1);
+              nanb |= (d != d) ? 1u : 0u;
+              sm4[0] += d;
+              const float lqb = (num0 + z * num1) * fast_rcp(den0 + z * den1);
+              d = fabsf(lqb - lq);
+              nanb |= (d != d) ? 2u : 0u;
+              sm4[1] += d;
+              F[10ll * Npad + s] = cA - lqb * cB;
+              F[12ll * Npad + s] = lqb;
+              F[14ll * Npad + s] = lq;
             }
             if (act2) {
-              st.U0 = F[6ll * Npad + s]; st.U1 = F[7ll * Npad + s]; st.L0 = F[8ll * Npad + s];
-              st.L1 = F[9ll * Npad + s];
-              st.Z2 = F[11ll * Npad + s]; st.lq2 = F[13ll * Npad + s];
-              s2 += kk04_r23_trip<float>(st);
-              F[11ll * Npad + s] = st.Z2; F[13ll * Npad + s] = st.lq2;
+              const float u0 = F[6ll * Npad + s], u1 = F[7ll * Npad + s], l0 = F[8ll * Npad + s];
+              const float l1 = F[9ll * Npad + s];
+              const float Z2 = F[11ll * Npad + s], lq2 = F[13ll * Npad + s];
+              const bool lowz = (__float_as_uint(st3[s]) & AUX_ZI_MASK) <= 1u;
+              const float lq = (num0 + Z2 * num1) * fast_rcp(den0 + Z2 * den1);        // metscales.py:1167-1178
+              bool lower = lowz && (lq >= 6.7f) && (lq < 8.3f);
+              const float z = (lower ? l0 : u0) - lq * (lower ? l1 : u1);
+              float d = lq2 - lq;
+              nanb |= (d != d) ? 4u : 0u;
+              sm4[2] += d;
+              const float lqb = (num0 + z * num1) * fast_rcp(den0 + z * den1);
+              lower = lowz && (lqb >= 6.7f) && (lqb < 8.3f);
+              d = lq - lqb;
+              nanb |= (d != d) ? 8u : 0u;
+              sm4[3] += d;
+              F[11ll * Npad + s] = (lower ? l0 : u0) - lqb * (lower ? l1 : u1);
+              F[13ll * Npad + s] = lqb;
+              F[15ll * Npad + s] = lq;
             }
           }
-          block_sum2f(s1, s2, ctrl->redf, phase);
-          if (act1) { ++ii1; act1 = (s1 > tol1) && ii1 < 100; }            // metscales.py:1111,1117
-          if (act2) { ++ii2; act2 = (fabsf(s2) > tol2) && ii2 < 100; }     // metscales.py:1166,1177
+          // float block sums of the unclamped terms (columns of any length: the 16.16 fixed point of
+          // the register variant would overflow); NaN flags by vote as there
+          block_sum2f(sm4[0], sm4[1], ctrl->redf, phase);
+          block_sum2f(sm4[2], sm4[3], ctrl->redf, phase);
+          unsigned nb = 0u;
+          if (__syncthreads_or(nanb != 0u)) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) nb |= __syncthreads_or((nanb >> k) & 1u) ? (1u << k) : 0u;
+          }
+          if (act1) {                                                     // metscales.py:1111,1117
+            ++ii1;
+            if ((nb & 1u) || !(sm4[0] > tol1) || ii1 >= 100) {
+              act1 = false;       // ended after the first trip of the pair: put that state back
+              for (int s = tid; s < N; s += PT) {
+                const float lq = F[14ll * Npad + s];
+                F[12ll * Npad + s] = lq;
+                F[10ll * Npad + s] = F[4ll * Npad + s] - lq * F[5ll * Npad + s];
+              }
+            } else {
+              ++ii1;
+              act1 = !(nb & 2u) && (sm4[1] > tol1) && ii1 < 100;
+            }
+          }
+          if (act2) {                                                     // metscales.py:1166,1177
+            ++ii2;
+            if ((nb & 4u) || !(fabsf(sm4[2]) > tol2) || ii2 >= 100) {
+              act2 = false;
+              for (int s = tid; s < N; s += PT) {
+                const float lq = F[15ll * Npad + s];
+                const bool lower = ((__float_as_uint(st3[s]) & AUX_ZI_MASK) <= 1u) && (lq >= 6.7f) && (lq < 8.3f);
+                F[13ll * Npad + s] = lq;
+                F[11ll * Npad + s] = (lower ? F[8ll * Npad + s] : F[6ll * Npad + s]) -
+                                     lq * (lower ? F[9ll * Npad + s] : F[7ll * Npad + s]);
+              }
+            } else {
+              ++ii2;
+              act2 = !(nb & 8u) && (fabsf(sm4[3]) > tol2) && ii2 < 100;
+            }
+          }
+          if (act1 && ii1 == DIVERGENCE_CHECK_TRIP) {
+            // proven-divergence exit, as in the register variant above (same bound, same threshold)
+            float sm = 0.0f, unused = 0.0f;
+            for (int s = tid; s < N; s += PT) {
+              const float n0 = F[0ll * Npad + s], n1 = F[1ll * Npad + s], d0 = F[2ll * Npad + s];
+              const float d1 = F[3ll * Npad + s], A = F[4ll * Npad + s], B = F[5ll * Npad + s];
+              const float al = n0 + A * n1, be = B * n1, ga = d0 + A * d1, de = B * d1;
+              const float bg = be + ga, disc = bg * bg - 4.0f * al * de;
+              float m = 0.0f;
+              if (disc < 0.0f) {
+                const float r = __fsqrt_rn(al * de - be * ga), ide = fast_rcp(de);
+                const float u1 = (ga + r) * ide, u2 = (ga - r) * ide;
+                const float q1 = (de * u1 - bg) * u1 + al, q2 = (de * u2 - bg) * u2 + al;
+                m = fminf(fabsf(q1), fabsf(q2)) * fast_rcp(r);
+              }
+              sm += (m == m) ? fminf(m, 8.0f) : 0.0f;
+            }
+            block_sum2f(sm, unused, ctrl->redf, phase);
+            if (sm > 4.0f * tol1) { executed1 = ii1; ii1 = 100; act1 = false; }
+          }
         }
+        if (executed1 < 0) executed1 = ii1;
         for (int s = tid; s < N; s += PT) {
           IterState<float> st;
           st.U0 = F[6ll * Npad + s]; st.U1 = F[7ll * Npad + s]; st.L0 = F[8ll * Npad + s];
