@@ -44,6 +44,7 @@ struct ProdParams {
   int* ret;
   float* Z;
   int nstore;
+  int scap;                                // global variant: samples whose KK04 loop state lives in shared memory
   signed char slot_of_key[NKEYS];
   signed char key_of_slot[NKEYS];
   int col_off[NKEYS];                      // slot * Npad (float index of the column), -1 if not stored
@@ -182,7 +183,8 @@ __device__ unsigned long long g_col_cycles[2 * NKEYS];   // per key: cycles, max
 // ---- the kernel -------------------------------------------------------------------------------
 // SLOTS > 0: at most SLOTS samples per thread, loop state in registers, columns in shared memory.
 // SLOTS == 0: any N', columns / stash / loop state in the per-block global scratch.
-template <int SLOTS>
+// WIDE: 32-bit histogram counters (columns of 65536 samples or more); global variant only.
+template <int SLOTS, bool WIDE>
 __global__ void __launch_bounds__(PT, 1)
 production_kernel(const __grid_constant__ ProdParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -191,11 +193,12 @@ production_kernel(const __grid_constant__ ProdParams p) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = p.N, Npad = p.Npad;
 
-  constexpr bool PACK16 = !GLOBAL;        // shared-memory variant: columns of < 65536 samples
+  constexpr bool PACK16 = !WIDE;          // 16-bit packed histogram counters: columns of < 65536 samples
   constexpr size_t HIST_BYTES = FineHist<PACK16>::BYTES;
   float* vals;              // columns [nstore][Npad]
   float* st0; float* st1; float* st2; float* st3;   // four per-sample scratch arrays (phase-A carry, then R23 constants)
   float* giter = nullptr;   // global variant: loop state [16][Npad]
+  float* sstate = nullptr;  // global variant: Z1, Z2, logq1, logq2 of the first p.scap samples, in shared memory
   unsigned char* work;      // selection scratch: PW histograms, then PW candidate areas
   if (GLOBAL) {
     float* base = p.gscratch + (long long)blockIdx.x * p.gscratch_per_block;
@@ -204,6 +207,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
     st1 = st0 + Npad; st2 = st1 + Npad; st3 = st2 + Npad;
     giter = st3 + Npad;
     work = smem + CTRL_BYTES;
+    sstate = reinterpret_cast<float*>(work + (size_t)PW * (HIST_BYTES + CAND_FLOATS * sizeof(float)));
   } else {
     // Shared-memory variant (Npad == SLOTS*PT always).  The histograms are live from phase B on
     // (they are filled while the KK04 loops wait on their barriers), so the per-sample scratch
@@ -525,8 +529,13 @@ production_kernel(const __grid_constant__ ProdParams p) {
           }
         }
       } else {
-        // memory-backed loop state: fields [16][Npad] in the per-block global scratch
+        // memory-backed loop state: fields [16][Npad] in the per-block global scratch; the four
+        // fields that change every trip (10 Z1, 11 Z2, 12 logq1, 13 logq2) live in shared memory
+        // for the first p.scap samples (a multiple of the block size, so each pass of the sample
+        // loop is on one side) -- the loop is bound by L2 bandwidth
         float* F = giter;
+        const int scap = p.scap;
+#define LST(k, s) (*((s) < scap ? sstate + ((k) - 10) * scap + (s) : F + (long long)(k) * Npad + (s)))
         bool any = false;
         for (int s = tid; s < N; s += PT) {
           Carry<float> c;
@@ -539,15 +548,15 @@ production_kernel(const __grid_constant__ ProdParams p) {
           F[0ll * Npad + s] = st.num0; F[1ll * Npad + s] = st.num1; F[2ll * Npad + s] = st.den0;
           F[3ll * Npad + s] = st.den1; F[4ll * Npad + s] = st.A; F[5ll * Npad + s] = st.B;
           F[6ll * Npad + s] = st.U0; F[7ll * Npad + s] = st.U1; F[8ll * Npad + s] = st.L0;
-          F[9ll * Npad + s] = st.L1; F[10ll * Npad + s] = st.Z1; F[11ll * Npad + s] = st.Z2;
-          F[12ll * Npad + s] = st.lq1; F[13ll * Npad + s] = st.lq2;
+          F[9ll * Npad + s] = st.L1; LST(10, s) = st.Z1; LST(11, s) = st.Z2;
+          LST(12, s) = st.lq1; LST(13, s) = st.lq2;
         }
         const bool allnan = !__syncthreads_or(any);
         if (allnan || (has_kn && !o3o2)) {
           for (int s = tid; s < N; s += PT) {
-            float z1 = allnan ? 8.6f : F[10ll * Npad + s];
+            float z1 = allnan ? 8.6f : LST(10, s);
             if (has_kn && !o3o2) z1 = F[4ll * Npad + s] - 7.37177f * F[5ll * Npad + s];
-            F[10ll * Npad + s] = z1;
+            LST(10, s) = z1;
           }
         }
         // Two trips per barrier, as in the register variant: the ten constants of a sample are read
@@ -562,7 +571,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
             const float den1 = F[3ll * Npad + s];
             if (act1) {
               const float cA = F[4ll * Npad + s], cB = F[5ll * Npad + s];
-              const float Z1 = F[10ll * Npad + s], lq1 = F[12ll * Npad + s];
+              const float Z1 = LST(10, s), lq1 = LST(12, s);
               const float lq = (num0 + Z1 * num1) * fast_rcp(den0 + Z1 * den1);        // metscales.py:1112-1118
               const float z = cA - lq * cB;
               float d = fabsf(lq - lq1);
@@ -572,14 +581,14 @@ production_kernel(const __grid_constant__ ProdParams p) {
               d = fabsf(lqb - lq);
               nanb |= (d != d) ? 2u : 0u;
               sm4[1] += d;
-              F[10ll * Npad + s] = cA - lqb * cB;
-              F[12ll * Npad + s] = lqb;
+              LST(10, s) = cA - lqb * cB;
+              LST(12, s) = lqb;
               F[14ll * Npad + s] = lq;
             }
             if (act2) {
               const float u0 = F[6ll * Npad + s], u1 = F[7ll * Npad + s], l0 = F[8ll * Npad + s];
               const float l1 = F[9ll * Npad + s];
-              const float Z2 = F[11ll * Npad + s], lq2 = F[13ll * Npad + s];
+              const float Z2 = LST(11, s), lq2 = LST(13, s);
               const bool lowz = (__float_as_uint(st3[s]) & AUX_ZI_MASK) <= 1u;
               const float lq = (num0 + Z2 * num1) * fast_rcp(den0 + Z2 * den1);        // metscales.py:1167-1178
               bool lower = lowz && (lq >= 6.7f) && (lq < 8.3f);
@@ -592,8 +601,8 @@ production_kernel(const __grid_constant__ ProdParams p) {
               d = lq - lqb;
               nanb |= (d != d) ? 8u : 0u;
               sm4[3] += d;
-              F[11ll * Npad + s] = (lower ? l0 : u0) - lqb * (lower ? l1 : u1);
-              F[13ll * Npad + s] = lqb;
+              LST(11, s) = (lower ? l0 : u0) - lqb * (lower ? l1 : u1);
+              LST(13, s) = lqb;
               F[15ll * Npad + s] = lq;
             }
           }
@@ -612,8 +621,8 @@ production_kernel(const __grid_constant__ ProdParams p) {
               act1 = false;       // ended after the first trip of the pair: put that state back
               for (int s = tid; s < N; s += PT) {
                 const float lq = F[14ll * Npad + s];
-                F[12ll * Npad + s] = lq;
-                F[10ll * Npad + s] = F[4ll * Npad + s] - lq * F[5ll * Npad + s];
+                LST(12, s) = lq;
+                LST(10, s) = F[4ll * Npad + s] - lq * F[5ll * Npad + s];
               }
             } else {
               ++ii1;
@@ -627,8 +636,8 @@ production_kernel(const __grid_constant__ ProdParams p) {
               for (int s = tid; s < N; s += PT) {
                 const float lq = F[15ll * Npad + s];
                 const bool lower = ((__float_as_uint(st3[s]) & AUX_ZI_MASK) <= 1u) && (lq >= 6.7f) && (lq < 8.3f);
-                F[13ll * Npad + s] = lq;
-                F[11ll * Npad + s] = (lower ? F[8ll * Npad + s] : F[6ll * Npad + s]) -
+                LST(13, s) = lq;
+                LST(11, s) = (lower ? F[8ll * Npad + s] : F[6ll * Npad + s]) -
                                      lq * (lower ? F[9ll * Npad + s] : F[7ll * Npad + s]);
               }
             } else {
@@ -661,8 +670,8 @@ production_kernel(const __grid_constant__ ProdParams p) {
         for (int s = tid; s < N; s += PT) {
           IterState<float> st;
           st.U0 = F[6ll * Npad + s]; st.U1 = F[7ll * Npad + s]; st.L0 = F[8ll * Npad + s];
-          st.L1 = F[9ll * Npad + s]; st.Z1 = F[10ll * Npad + s]; st.Z2 = F[11ll * Npad + s];
-          st.lq2 = F[13ll * Npad + s];
+          st.L1 = F[9ll * Npad + s]; st.Z1 = LST(10, s); st.Z2 = LST(11, s);
+          st.lq2 = LST(13, s);
           st.aux = __float_as_uint(st3[s]);
           SlotPut<!GLOBAL> put{vals + s, p.col_off, vals_sa + 4u * (unsigned)s};
           const float kd = has_kd ? vals[(long long)sl_kd * Npad + s] : Math<float>::nan();
@@ -807,6 +816,8 @@ static uint32_t philox_calls(uint32_t tok, int correlated, int deterministic) {
 
 struct ProdPlan {
   bool global;
+  bool wide;      // global variant with 32-bit histogram counters (Npad >= 65536)
+  int scap;       // global variant: samples with their loop state in shared memory
   int Npad, grid;
   size_t smem;
   long long per_block_floats;
@@ -831,13 +842,22 @@ static ProdPlan make_plan(long long G, long long N, int nstore) {
                             (size_t)PW * (FineHist<true>::BYTES + CAND_FLOATS * sizeof(float)) +
                             (size_t)4 * PT * sizeof(float);
   pl.global = !(N <= 4ll * PT && smem_local <= 227ull * 1024);
+  pl.wide = false;
+  pl.scap = 0;
   if (!pl.global) {
     pl.Npad = 4 * PT;
     pl.smem = smem_local;
     pl.per_block_floats = 0;
   } else {
     pl.Npad = (int)((N + 127) / 128 * 128);
-    pl.smem = CTRL_BYTES + (size_t)PW * (FineHist<false>::BYTES + CAND_FLOATS * sizeof(float));
+    pl.wide = pl.Npad >= 65536;
+    const size_t base = CTRL_BYTES + (size_t)PW * ((pl.wide ? FineHist<false>::BYTES : FineHist<true>::BYTES) +
+                                                    CAND_FLOATS * sizeof(float));
+    // the rest of the 227 KB holds the per-trip loop state (16 B per sample) of as many samples as fit
+    const long long fit = (long long)((227ull * 1024 - base) / 16 / PT) * PT;
+    const long long need = (N + PT - 1) / PT * PT;
+    pl.scap = (int)(fit < need ? fit : need);
+    pl.smem = base + (size_t)pl.scap * 16;
     pl.per_block_floats = ((long long)nstore + 4 + 16) * pl.Npad;
   }
   const long long sms = num_sms();
@@ -904,7 +924,7 @@ int launch_production(const float* meas, const float* err, long long G, long lon
   const ProdPlan pl = make_plan(G, n_draw, p.nstore);
   if (scratch_bytes < production_scratch_bytes(G, n_draw, tok))
     return set_error("mcz_forward_production: scratch too small");
-  p.meas = meas; p.err = err; p.G = G; p.N = (int)n_draw; p.Npad = pl.Npad; p.tok = tok; p.dust = dust;
+  p.meas = meas; p.err = err; p.G = G; p.N = (int)n_draw; p.Npad = pl.Npad; p.scap = pl.scap; p.tok = tok; p.dust = dust;
   p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32); p.goff = galaxy_offset;
   p.correlated = sample_mode == 1; p.deterministic = deterministic != 0;
   p.calls = philox_calls(tok, p.correlated, p.deterministic);
@@ -918,23 +938,33 @@ int launch_production(const float* meas, const float* err, long long G, long lon
   if (!pl.global) {
     static bool attr_done = false;
     if (!attr_done) {
-      rc = check_cuda(cudaFuncSetAttribute(production_kernel<4>,
+      rc = check_cuda(cudaFuncSetAttribute(production_kernel<4, false>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
                       "smem attribute");
       if (rc) return rc;
       attr_done = true;
     }
-    production_kernel<4><<<pl.grid, PT, pl.smem, stream>>>(p);
+    production_kernel<4, false><<<pl.grid, PT, pl.smem, stream>>>(p);
+  } else if (!pl.wide) {
+    static bool attr_done = false;
+    if (!attr_done) {
+      rc = check_cuda(cudaFuncSetAttribute(production_kernel<0, false>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
+                      "smem attribute");
+      if (rc) return rc;
+      attr_done = true;
+    }
+    production_kernel<0, false><<<pl.grid, PT, pl.smem, stream>>>(p);
   } else {
     static bool attr_done = false;
     if (!attr_done) {
-      rc = check_cuda(cudaFuncSetAttribute(production_kernel<0>,
+      rc = check_cuda(cudaFuncSetAttribute(production_kernel<0, true>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
                       "smem attribute");
       if (rc) return rc;
       attr_done = true;
     }
-    production_kernel<0><<<pl.grid, PT, pl.smem, stream>>>(p);
+    production_kernel<0, true><<<pl.grid, PT, pl.smem, stream>>>(p);
   }
   count_launch();
   return check_cuda(cudaGetLastError(), "production_kernel launch");
@@ -945,13 +975,13 @@ int launch_production(const float* meas, const float* err, long long G, long lon
 // staged into a shared-memory column of NG*128 floats (NaN padding) or, for longer columns, into a
 // padded global scratch, then warp_percentiles() is called.  Lets the tests feed the selection
 // with distributions the physics never produces (ties, outliers, two-point, sorted, denormals).
-template <int NG>
+template <int NG, bool WIDE>
 __global__ void __launch_bounds__(128, 1)
 select_columns_kernel(const float* __restrict__ cols, int ncols, int N, int Npad, float* __restrict__ padded,
                       float* __restrict__ pct, int* __restrict__ nvalid, signed char* __restrict__ status) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr bool SH = NG > 0;
-  typedef FineHist<SH> FH;
+  typedef FineHist<!WIDE> FH;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = blockIdx.x * 4 + warp;
   if (c >= ncols) return;
@@ -963,7 +993,7 @@ select_columns_kernel(const float* __restrict__ cols, int ncols, int N, int Npad
   __syncwarp();
   float pc[3];
   int nv, st;
-  warp_percentiles<SH, NG>(col, Npad, hist, cand, pc, nv, st);
+  warp_percentiles<!WIDE, NG>(col, Npad, hist, cand, pc, nv, st);
   if (lane == 0) {
     pct[3 * c] = pc[0]; pct[3 * c + 1] = pc[1]; pct[3 * c + 2] = pc[2];
     nvalid[c] = nv;
@@ -979,16 +1009,21 @@ int launch_select_columns(const float* cols_d, long long ncols, long long N, flo
     const size_t sm = 4 * (size_t)(18 * 128 * 4 + FineHist<true>::BYTES + 512);
     static bool done = false;
     if (!done) {
-      const int rc = check_cuda(cudaFuncSetAttribute(select_columns_kernel<18>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm), "smem attribute");
+      const int rc = check_cuda(cudaFuncSetAttribute(select_columns_kernel<18, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm), "smem attribute");
       if (rc) return rc;
       done = true;
     }
-    select_columns_kernel<18><<<grid, 128, sm, stream>>>(cols_d, (int)ncols, (int)N, 18 * 128, nullptr, pct_d, nvalid_d, status_d);
+    select_columns_kernel<18, false><<<grid, 128, sm, stream>>>(cols_d, (int)ncols, (int)N, 18 * 128, nullptr, pct_d, nvalid_d, status_d);
   } else {
     if (!padded_d) return set_error("mcz_debug_select_columns: columns longer than 2304 need the padded scratch");
     const int Npad = (int)((N + 127) / 128 * 128);
-    const size_t sm = 4 * (size_t)(FineHist<false>::BYTES + 512);
-    select_columns_kernel<0><<<grid, 128, sm, stream>>>(cols_d, (int)ncols, (int)N, Npad, padded_d, pct_d, nvalid_d, status_d);
+    if (Npad < 65536) {           // the instantiations the production kernel uses for these lengths
+      const size_t sm = 4 * (size_t)(FineHist<true>::BYTES + 512);
+      select_columns_kernel<0, false><<<grid, 128, sm, stream>>>(cols_d, (int)ncols, (int)N, Npad, padded_d, pct_d, nvalid_d, status_d);
+    } else {
+      const size_t sm = 4 * (size_t)(FineHist<false>::BYTES + 512);
+      select_columns_kernel<0, true><<<grid, 128, sm, stream>>>(cols_d, (int)ncols, (int)N, Npad, padded_d, pct_d, nvalid_d, status_d);
+    }
   }
   count_launch();
   return check_cuda(cudaGetLastError(), "select_columns_kernel launch");

@@ -93,7 +93,7 @@ def adversarial_columns(N, rs):
     return np.stack(cols), names
 
 
-@pytest.mark.parametrize("N", [1, 2, 5, 63, 64, 65, 127, 128, 129, 700, 2199, 2200, 2304, 2305, 11000])
+@pytest.mark.parametrize("N", [1, 2, 5, 63, 64, 65, 127, 128, 129, 700, 2199, 2200, 2304, 2305, 11000, 70000])
 def test_selection_is_exact_on_adversarial_columns(N):
     rs = np.random.RandomState(1000 + N)
     cols, names = adversarial_columns(N, rs)
