@@ -529,48 +529,54 @@ production_kernel(const __grid_constant__ ProdParams p) {
           }
         }
       } else {
-        // memory-backed loop state: fields [16][Npad] in the per-block global scratch; the four
-        // fields that change every trip (10 Z1, 11 Z2, 12 logq1, 13 logq2) live in shared memory
-        // for the first p.scap samples (a multiple of the block size, so each pass of the sample
-        // loop is on one side) -- the loop is bound by L2 bandwidth
+        // Memory-backed loop state.  The ten per-sample constants of the two maps are recomputed
+        // from the four carry values (st0..st3: logO3O2, logN2Ha, logR23, flags) in every batch:
+        // ~35 FMAs against 40 bytes of L2 traffic per sample, and this loop is bound by L2
+        // bandwidth.  The four values that change every trip (Z1, Z2, logq1, logq2 = fields 10..13)
+        // live in shared memory for the first p.scap samples (a multiple of the block size, so
+        // each pass of the sample loop is on one side), in the global scratch beyond.
         float* F = giter;
         const int scap = p.scap;
 #define LST(k, s) (*((s) < scap ? sstate + ((k) - 10) * scap + (s) : F + (long long)(k) * Npad + (s)))
-        bool any = false;
-        for (int s = tid; s < N; s += PT) {
+        auto consts = [&](int s, IterState<float>& st) {
           Carry<float> c;
           c.y = st0[s]; c.n2ha = st1[s]; c.x = st2[s];
           c.aux = __float_as_uint(st3[s]);
+          make_iter<float>(c, 0.0f, st);
+        };
+        bool any = false;
+        for (int s = tid; s < N; s += PT) {
           const float kd = has_kd ? vals[(long long)sl_kd * Npad + s] : Math<float>::nan();
           IterState<float> st;
-          make_iter<float>(c, kd, st);
+          consts(s, st);
           any = any || !Math<float>::isnan(kd);
-          F[0ll * Npad + s] = st.num0; F[1ll * Npad + s] = st.num1; F[2ll * Npad + s] = st.den0;
-          F[3ll * Npad + s] = st.den1; F[4ll * Npad + s] = st.A; F[5ll * Npad + s] = st.B;
-          F[6ll * Npad + s] = st.U0; F[7ll * Npad + s] = st.U1; F[8ll * Npad + s] = st.L0;
-          F[9ll * Npad + s] = st.L1; LST(10, s) = st.Z1; LST(11, s) = st.Z2;
+          LST(10, s) = kd; LST(11, s) = st.Z2;
           LST(12, s) = st.lq1; LST(13, s) = st.lq2;
         }
         const bool allnan = !__syncthreads_or(any);
         if (allnan || (has_kn && !o3o2)) {
           for (int s = tid; s < N; s += PT) {
             float z1 = allnan ? 8.6f : LST(10, s);
-            if (has_kn && !o3o2) z1 = F[4ll * Npad + s] - 7.37177f * F[5ll * Npad + s];
+            if (has_kn && !o3o2) {
+              IterState<float> st;
+              consts(s, st);
+              z1 = st.A - 7.37177f * st.B;
+            }
             LST(10, s) = z1;
           }
         }
-        // Two trips per barrier, as in the register variant: the ten constants of a sample are read
-        // once for both trips (this loop is bound by L2 bandwidth), logq after the first trip is
-        // kept in F[14], F[15] so that a loop that turns out to have ended there can be put back.
+        // Two trips per barrier, as in the register variant; logq after the first trip is kept in
+        // F[14], F[15] so that a loop that turns out to have ended there can be put back.
         while (act1 || act2) {
           float sm4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
           unsigned nanb = 0u;
 #pragma unroll 2
           for (int s = tid; s < N; s += PT) {
-            const float num0 = F[0ll * Npad + s], num1 = F[1ll * Npad + s], den0 = F[2ll * Npad + s];
-            const float den1 = F[3ll * Npad + s];
+            IterState<float> k;
+            consts(s, k);
+            const float num0 = k.num0, num1 = k.num1, den0 = k.den0, den1 = k.den1;
             if (act1) {
-              const float cA = F[4ll * Npad + s], cB = F[5ll * Npad + s];
+              const float cA = k.A, cB = k.B;
               const float Z1 = LST(10, s), lq1 = LST(12, s);
               const float lq = (num0 + Z1 * num1) * fast_rcp(den0 + Z1 * den1);        // metscales.py:1112-1118
               const float z = cA - lq * cB;
@@ -586,10 +592,9 @@ production_kernel(const __grid_constant__ ProdParams p) {
               F[14ll * Npad + s] = lq;
             }
             if (act2) {
-              const float u0 = F[6ll * Npad + s], u1 = F[7ll * Npad + s], l0 = F[8ll * Npad + s];
-              const float l1 = F[9ll * Npad + s];
+              const float u0 = k.U0, u1 = k.U1, l0 = k.L0, l1 = k.L1;
               const float Z2 = LST(11, s), lq2 = LST(13, s);
-              const bool lowz = (__float_as_uint(st3[s]) & AUX_ZI_MASK) <= 1u;
+              const bool lowz = (k.aux & AUX_ZI_MASK) <= 1u;
               const float lq = (num0 + Z2 * num1) * fast_rcp(den0 + Z2 * den1);        // metscales.py:1167-1178
               bool lower = lowz && (lq >= 6.7f) && (lq < 8.3f);
               const float z = (lower ? l0 : u0) - lq * (lower ? l1 : u1);
@@ -620,9 +625,11 @@ production_kernel(const __grid_constant__ ProdParams p) {
             if ((nb & 1u) || !(sm4[0] > tol1) || ii1 >= 100) {
               act1 = false;       // ended after the first trip of the pair: put that state back
               for (int s = tid; s < N; s += PT) {
+                IterState<float> k;
+                consts(s, k);
                 const float lq = F[14ll * Npad + s];
                 LST(12, s) = lq;
-                LST(10, s) = F[4ll * Npad + s] - lq * F[5ll * Npad + s];
+                LST(10, s) = k.A - lq * k.B;
               }
             } else {
               ++ii1;
@@ -634,11 +641,12 @@ production_kernel(const __grid_constant__ ProdParams p) {
             if ((nb & 4u) || !(fabsf(sm4[2]) > tol2) || ii2 >= 100) {
               act2 = false;
               for (int s = tid; s < N; s += PT) {
+                IterState<float> k;
+                consts(s, k);
                 const float lq = F[15ll * Npad + s];
-                const bool lower = ((__float_as_uint(st3[s]) & AUX_ZI_MASK) <= 1u) && (lq >= 6.7f) && (lq < 8.3f);
+                const bool lower = ((k.aux & AUX_ZI_MASK) <= 1u) && (lq >= 6.7f) && (lq < 8.3f);
                 LST(13, s) = lq;
-                LST(11, s) = (lower ? F[8ll * Npad + s] : F[6ll * Npad + s]) -
-                                     lq * (lower ? F[9ll * Npad + s] : F[7ll * Npad + s]);
+                LST(11, s) = (lower ? k.L0 : k.U0) - lq * (lower ? k.L1 : k.U1);
               }
             } else {
               ++ii2;
@@ -649,8 +657,9 @@ production_kernel(const __grid_constant__ ProdParams p) {
             // proven-divergence exit, as in the register variant above (same bound, same threshold)
             float sm = 0.0f, unused = 0.0f;
             for (int s = tid; s < N; s += PT) {
-              const float n0 = F[0ll * Npad + s], n1 = F[1ll * Npad + s], d0 = F[2ll * Npad + s];
-              const float d1 = F[3ll * Npad + s], A = F[4ll * Npad + s], B = F[5ll * Npad + s];
+              IterState<float> k;
+              consts(s, k);
+              const float n0 = k.num0, n1 = k.num1, d0 = k.den0, d1 = k.den1, A = k.A, B = k.B;
               const float al = n0 + A * n1, be = B * n1, ga = d0 + A * d1, de = B * d1;
               const float bg = be + ga, disc = bg * bg - 4.0f * al * de;
               float m = 0.0f;
@@ -669,10 +678,9 @@ production_kernel(const __grid_constant__ ProdParams p) {
         if (executed1 < 0) executed1 = ii1;
         for (int s = tid; s < N; s += PT) {
           IterState<float> st;
-          st.U0 = F[6ll * Npad + s]; st.U1 = F[7ll * Npad + s]; st.L0 = F[8ll * Npad + s];
-          st.L1 = F[9ll * Npad + s]; st.Z1 = LST(10, s); st.Z2 = LST(11, s);
+          consts(s, st);
+          st.Z1 = LST(10, s); st.Z2 = LST(11, s);
           st.lq2 = LST(13, s);
-          st.aux = __float_as_uint(st3[s]);
           SlotPut<!GLOBAL> put{vals + s, p.col_off, vals_sa + 4u * (unsigned)s};
           const float kd = has_kd ? vals[(long long)sl_kd * Npad + s] : Math<float>::nan();
           const float m91 = vals[(long long)sl_m91 * Npad + s];
