@@ -122,7 +122,11 @@ int mcz_forward_production(const float* meas_d, const float* err_d, long long G,
 
 /* ---- host-buffer convenience (what run() would call once for the whole table) -----------------
  * Same as mcz_forward_production but with HOST pointers: uploads meas/err, runs, downloads the
- * tables, synchronises.  Device buffers and the pinned staging area live in the context.
+ * tables, synchronises.  Device buffers live in the context.  Tables of 32768 galaxies or more run
+ * as up to 8 launches over contiguous chunks, and each chunk's result tables are copied back on
+ * a second stream while the next chunk computes (results are identical: galaxies are independent
+ * and the random stream is keyed by the global galaxy index).  Pass pinned host memory for the
+ * copies to overlap.
  */
 typedef struct mcz_ctx mcz_ctx;
 mcz_ctx* mcz_ctx_create(int device);

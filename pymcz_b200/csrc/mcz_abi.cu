@@ -41,6 +41,8 @@ using namespace mcz;
 struct mcz_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;     // result tables go back chunk by chunk while the next chunk computes
+  cudaEvent_t chunk_done[16] = {};
   // device buffers (grown on demand)
   float *meas = nullptr, *err = nullptr, *pct = nullptr;
   int *nvalid = nullptr, *trips = nullptr, *ret = nullptr;
@@ -130,9 +132,16 @@ mcz_ctx* mcz_ctx_create(int device) {
   mcz_ctx* c = new mcz_ctx();
   c->device = device;
   cudaSetDevice(device);
-  if (check_cuda(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "stream create")) {
-    delete c;
+  if (check_cuda(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "stream create") ||
+      check_cuda(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking), "stream create")) {
+    mcz_ctx_destroy(c);
     return nullptr;
+  }
+  for (auto& e : c->chunk_done) {
+    if (check_cuda(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "event create")) {
+      mcz_ctx_destroy(c);
+      return nullptr;
+    }
   }
   return c;
 }
@@ -143,6 +152,8 @@ void mcz_ctx_destroy(mcz_ctx* c) {
   cudaFree(c->meas); cudaFree(c->err); cudaFree(c->pct); cudaFree(c->nvalid); cudaFree(c->trips);
   cudaFree(c->ret); cudaFree(c->status); cudaFree(c->scratch);
   if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  for (auto& e : c->chunk_done) if (e) cudaEventDestroy(e);
   delete c;
 }
 
@@ -176,19 +187,32 @@ int mcz_ctx_run_host(mcz_ctx* c, const float* meas_h, const float* err_h, long l
     c->cap_scratch = need;
   }
   const size_t g = (size_t)G;
-  cudaStream_t st = c->stream;
+  cudaStream_t st = c->stream, cp = c->copy_stream;
   if ((rc = check_cuda(cudaMemcpyAsync(c->meas, meas_h, g * NLINES * 4, cudaMemcpyHostToDevice, st), "H2D meas"))) return rc;
   if ((rc = check_cuda(cudaMemcpyAsync(c->err, err_h, g * NLINES * 4, cudaMemcpyHostToDevice, st), "H2D err"))) return rc;
-  rc = launch_production(c->meas, c->err, G, n_draw, tokens, dust, seed, galaxy_offset, sample_mode,
-                         deterministic, c->pct, c->nvalid, c->status, c->trips, c->ret, nullptr,
-                         c->scratch, c->cap_scratch, st);
-  if (rc) return rc;
-  if ((rc = check_cuda(cudaMemcpyAsync(pct_h, c->pct, g * NKEYS * 3 * 4, cudaMemcpyDeviceToHost, st), "D2H pct"))) return rc;
-  if ((rc = check_cuda(cudaMemcpyAsync(nvalid_h, c->nvalid, g * NKEYS * 4, cudaMemcpyDeviceToHost, st), "D2H nvalid"))) return rc;
-  if ((rc = check_cuda(cudaMemcpyAsync(status_h, c->status, g * NKEYS, cudaMemcpyDeviceToHost, st), "D2H status"))) return rc;
-  if (trips_h && (rc = check_cuda(cudaMemcpyAsync(trips_h, c->trips, g * 2 * 4, cudaMemcpyDeviceToHost, st), "D2H trips"))) return rc;
-  if (ret_h && (rc = check_cuda(cudaMemcpyAsync(ret_h, c->ret, g * 4, cudaMemcpyDeviceToHost, st), "D2H ret"))) return rc;
-  return check_cuda(cudaStreamSynchronize(st), "stream sync");
+  // Galaxies are independent and Philox is keyed by the global galaxy index, so the table is run
+  // as up to 8 launches over contiguous chunks (>= 16384 galaxies each): the result tables of a
+  // chunk (641 B per galaxy) go back over PCIe on the copy stream while the next chunk computes.
+  long long nchunk = G / 16384;
+  nchunk = nchunk < 1 ? 1 : (nchunk > 8 ? 8 : nchunk);
+  for (long long k = 0; k < nchunk; ++k) {
+    const long long lo = G * k / nchunk, hi = G * (k + 1) / nchunk, n = hi - lo;
+    rc = launch_production(c->meas + lo * NLINES, c->err + lo * NLINES, n, n_draw, tokens, dust, seed,
+                           galaxy_offset + (unsigned long long)lo, sample_mode, deterministic,
+                           c->pct + lo * NKEYS * 3, c->nvalid + lo * NKEYS, c->status + lo * NKEYS,
+                           c->trips + lo * 2, c->ret + lo, nullptr, c->scratch, c->cap_scratch, st);
+    if (rc) return rc;
+    if ((rc = check_cuda(cudaEventRecord(c->chunk_done[k], st), "event record"))) return rc;
+    if ((rc = check_cuda(cudaStreamWaitEvent(cp, c->chunk_done[k], 0), "stream wait"))) return rc;
+    const size_t m = (size_t)n;
+    if ((rc = check_cuda(cudaMemcpyAsync(pct_h + lo * NKEYS * 3, c->pct + lo * NKEYS * 3, m * NKEYS * 3 * 4, cudaMemcpyDeviceToHost, cp), "D2H pct"))) return rc;
+    if ((rc = check_cuda(cudaMemcpyAsync(nvalid_h + lo * NKEYS, c->nvalid + lo * NKEYS, m * NKEYS * 4, cudaMemcpyDeviceToHost, cp), "D2H nvalid"))) return rc;
+    if ((rc = check_cuda(cudaMemcpyAsync(status_h + lo * NKEYS, c->status + lo * NKEYS, m * NKEYS, cudaMemcpyDeviceToHost, cp), "D2H status"))) return rc;
+    if (trips_h && (rc = check_cuda(cudaMemcpyAsync(trips_h + lo * 2, c->trips + lo * 2, m * 2 * 4, cudaMemcpyDeviceToHost, cp), "D2H trips"))) return rc;
+    if (ret_h && (rc = check_cuda(cudaMemcpyAsync(ret_h + lo, c->ret + lo, m * 4, cudaMemcpyDeviceToHost, cp), "D2H ret"))) return rc;
+  }
+  if ((rc = check_cuda(cudaStreamSynchronize(st), "stream sync"))) return rc;
+  return check_cuda(cudaStreamSynchronize(cp), "copy stream sync");
 }
 
 }  // extern "C"

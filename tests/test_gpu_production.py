@@ -250,20 +250,22 @@ def test_deterministic_single_evaluation():
                 assert abs(Z[g, j, 0] - Zo[j, 0]) < 1e-4, (g, sc.KEYS[j])
 
 
-def test_host_buffer_entry_point():
-    """mcz_ctx_run_host (the call run() makes): same tables as the device-pointer entry point."""
+@pytest.mark.parametrize("ngal,n", [(50, 2200), (40000, 64)])     # one launch / three pipelined chunks
+def test_host_buffer_entry_point(ngal, n):
+    """mcz_ctx_run_host (the call run() makes): same tables as the device-pointer entry point,
+    also when the table is split into chunks whose results are copied back while the next runs."""
     import ctypes
     from pymcz_b200 import _lib
     L = _lib.lib()
-    meas, err = synthetic_table(50, config=4)
+    meas, err = synthetic_table(ngal, config=4)
     tok = sc.T_ALL
-    ref = run_prod(meas, err, 2200, samples=False)
+    ref = run_prod(meas, err, n, samples=False)
     ctx = L.mcz_ctx_create(0)
     assert ctx
     G = meas.shape[0]
     pct = np.empty((G, sc.NKEYS, 3), np.float32); nvalid = np.empty((G, sc.NKEYS), np.int32)
     status = np.empty((G, sc.NKEYS), np.int8); trips = np.empty((G, 2), np.int32); ret = np.empty(G, np.int32)
-    rc = L.mcz_ctx_run_host(ctx, meas.ctypes.data, err.ctypes.data, G, 2200, tok, sc.DUST_ON, 0xB200, 0, 0, 0,
+    rc = L.mcz_ctx_run_host(ctx, meas.ctypes.data, err.ctypes.data, G, n, tok, sc.DUST_ON, 0xB200, 0, 0, 0,
                             pct.ctypes.data, nvalid.ctypes.data, status.ctypes.data, trips.ctypes.data,
                             ret.ctypes.data)
     assert rc == 0, L.mcz_last_error()
