@@ -10,9 +10,11 @@ SURVEY.md section 8(d), sharded over galaxies.  Scaling is WEAK: every GPU gets 
 (at 8 GPUs that is the full 10^6 table), so N=1 runs the first 1/8 of the table.
 
 A "step" is one pass of the hot path over the rank's shard: one fused kernel launch from
-device-resident meas/err tables to device-resident percentile tables, plus (N>1) the NCCL
-all-gather of the per-rank tables.  `e2e` is the same step through the C-ABI host-buffer entry
-point (mcz_ctx_run_host): pinned host tables in, H2D, kernel, D2H, host tables out.
+device-resident meas/err tables to device-resident percentile tables; for N>1 the gather of the
+per-rank tables is part of the step and is fused into the kernel (every rank's kernel writes its
+result rows into all ranks' full tables over NVLink; --gather nccl uses NCCL all-gathers instead).
+`e2e` is the same step through the C-ABI host-buffer entry point (mcz_ctx_run_host): pinned host
+tables in, H2D, kernel, D2H, host tables out.
 """
 import argparse
 import json
@@ -188,16 +190,27 @@ def run_ours(args):
     meas = torch.from_numpy(meas_h).to(dev)
     err = torch.from_numpy(err_h).to(dev)
     ws = ops.ProductionWorkspace(G, N, tok, dev)
-    gath = None
+    # The path's only exchange is the gather of the per-rank result tables.  Default:
+    # fused into the kernel -- every rank's kernel writes its rows straight into all ranks' full
+    # tables over NVLink peer mappings (pymcz_b200.dist.GatheredTables), then one 4-byte
+    # all-reduce as the barrier.  --gather nccl: kernel, then three NCCL all-gathers.
+    gath = fused = None
     if world > 1:
-        gath = dict(pct=torch.empty((G_total, sc.NKEYS, 3), dtype=torch.float32, device=dev),
-                    nvalid=torch.empty((G_total, sc.NKEYS), dtype=torch.int32, device=dev),
-                    status=torch.empty((G_total, sc.NKEYS), dtype=torch.int8, device=dev))
+        if args.gather == "fused":
+            from pymcz_b200.dist import GatheredTables
+            fused = GatheredTables(G_total, dev)
+        else:
+            gath = dict(pct=torch.empty((G_total, sc.NKEYS, 3), dtype=torch.float32, device=dev),
+                        nvalid=torch.empty((G_total, sc.NKEYS), dtype=torch.int32, device=dev),
+                        status=torch.empty((G_total, sc.NKEYS), dtype=torch.int8, device=dev))
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
     def step():
-        ops.forward_production(meas, err, N, tok, sc.DUST_ON, seed=0xB200, galaxy_offset=lo, workspace=ws)
-        if world > 1:      # the path's only exchange: gather of the per-rank tables
+        ops.forward_production(meas, err, N, tok, sc.DUST_ON, seed=0xB200, galaxy_offset=lo, workspace=ws,
+                               gather=fused)
+        if fused is not None:
+            fused.wait()
+        elif world > 1:
             dist.all_gather_into_tensor(gath["pct"], ws.pct)
             dist.all_gather_into_tensor(gath["nvalid"], ws.nvalid)
             dist.all_gather_into_tensor(gath["status"], ws.status)
@@ -352,7 +365,10 @@ def run_ours(args):
                        "galaxies_total": G_total, "galaxies_per_gpu": args.galaxies_per_gpu,
                        "nsample": args.nsample, "n_draw": N, "md": "all", "dust": True,
                        "sampling": "independent per line (Philox4x32-10, seed 0xB200)",
-                       "parallelism": "galaxy-sharded x%d, one all-gather of the tables" % world,
+                       "parallelism": ("galaxy-sharded x%d; result tables gathered by %s" % (
+                           world, "the kernel itself (rows written into every rank's table over NVLink peer "
+                           "mappings, then a 4-byte all-reduce)" if args.gather == "fused" else "three NCCL all-gathers")
+                           if world > 1 else "single GPU"),
                        "l2": "256 MiB buffer written between timed steps (not timed); per-step CUDA events"},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -375,6 +391,8 @@ def main():
     ap.add_argument("--galaxies-per-gpu", type=int, default=GALAXIES_PER_GPU)
     ap.add_argument("--nsample", type=int, default=NSAMPLE)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
+                    help="N > 1: result tables gathered by the kernel's own peer writes (default) or by NCCL")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -120,6 +120,23 @@ int mcz_forward_production(const float* meas_d, const float* err_d, long long G,
                            int* ret_d, float* Z_d, void* scratch_d, size_t scratch_bytes,
                            void* stream);
 
+/* ---- multi-GPU: production launch fused with the gather of the result tables --------------------
+ * Replaces "Pool.map returns the per-galaxy results to the parent" (reference mcz.py:553-569) when
+ * the galaxies are sharded over the GPUs of one node.  Rank r runs its G galaxies (global indices
+ * galaxy_offset .. galaxy_offset + G) and the kernel writes each result row (641 B per galaxy)
+ * straight into rows [row0, row0 + G) of EVERY rank's full-size table: pct_tables[q], nvalid_tables[q],
+ * status_tables[q] are device pointers to rank q's tables as mapped into this process (NVLink peer
+ * mappings, e.g. torch symmetric memory; q = own rank is the local table).  No separate collective
+ * moves data; the tables are complete on every rank once every rank's launch has finished (one
+ * barrier).  trips_d / ret_d stay local ([G,2], [G]).
+ */
+int mcz_forward_production_gather(const float* meas_d, const float* err_d, long long G, long long n_draw,
+                                  unsigned tokens, int dust, unsigned long long seed,
+                                  unsigned long long galaxy_offset, int sample_mode, int deterministic,
+                                  int nranks, long long row0, void* const* pct_tables,
+                                  void* const* nvalid_tables, void* const* status_tables, int* trips_d,
+                                  int* ret_d, void* scratch_d, size_t scratch_bytes, void* stream);
+
 /* ---- host-buffer convenience (what run() would call once for the whole table) -----------------
  * Same as mcz_forward_production but with HOST pointers: uploads meas/err, runs, downloads the
  * tables, synchronises.  Device buffers live in the context.  Tables of 32768 galaxies or more run

@@ -104,6 +104,28 @@ int mcz_forward_production(const float* meas_d, const float* err_d, long long G,
                            scratch_bytes, (cudaStream_t)stream);
 }
 
+int mcz_forward_production_gather(const float* meas_d, const float* err_d, long long G, long long n_draw,
+                                  unsigned tokens, int dust, unsigned long long seed,
+                                  unsigned long long galaxy_offset, int sample_mode, int deterministic,
+                                  int nranks, long long row0, void* const* pct_tables,
+                                  void* const* nvalid_tables, void* const* status_tables, int* trips_d,
+                                  int* ret_d, void* scratch_d, size_t scratch_bytes, void* stream) {
+  if (!meas_d || !err_d || !pct_tables || !nvalid_tables || !status_tables || !trips_d || !scratch_d)
+    return set_error("mcz_forward_production_gather: null pointer");
+  if (nranks < 1 || nranks > 8) return set_error("mcz_forward_production_gather: 1 to 8 ranks");
+  ProdDst dst;
+  dst.n = nranks;
+  dst.row0 = row0;
+  for (int q = 0; q < nranks; ++q) {
+    dst.pct[q] = static_cast<float*>(pct_tables[q]);
+    dst.nvalid[q] = static_cast<int*>(nvalid_tables[q]);
+    dst.status[q] = static_cast<signed char*>(status_tables[q]);
+  }
+  return launch_production(meas_d, err_d, G, n_draw, tokens, dust, seed, galaxy_offset, sample_mode,
+                           deterministic, nullptr, nullptr, nullptr, trips_d, ret_d, nullptr, scratch_d,
+                           scratch_bytes, (cudaStream_t)stream, &dst);
+}
+
 // diagnostics (not part of the public header): selection-path counters since the last reset:
 // [0] columns, [1] fast path, [2] fallback: degenerate range, [3] fallback: target in an edge bin
 // or > 4 target bins, [4] fallback: > 64 candidates (ties), [5] empty / non-positive columns

@@ -25,10 +25,19 @@ int read_sel_counters(unsigned long long* out8, int reset);
 int launch_select_columns(const float* cols_d, long long ncols, long long N, float* pct_d, int* nvalid_d,
                           signed char* status_d, float* padded_d, cudaStream_t stream);
 size_t production_scratch_bytes(long long G, long long n_draw, uint32_t tok);
+// Destination tables of a launch when they are not the caller's own: the gathered tables of up
+// to 8 ranks (peer-mapped device pointers), rows [row0, row0 + G) of each.
+struct ProdDst {
+  int n;
+  long long row0;
+  float* pct[8];
+  int* nvalid[8];
+  signed char* status[8];
+};
 int launch_production(const float* meas, const float* err, long long G, long long n_draw, uint32_t tok,
                       int dust, unsigned long long seed, unsigned long long galaxy_offset,
                       int sample_mode, int deterministic, float* pct, int* nvalid,
                       signed char* status, int* trips, int* ret, float* Z, void* scratch,
-                      size_t scratch_bytes, cudaStream_t stream);
+                      size_t scratch_bytes, cudaStream_t stream, const ProdDst* dst = nullptr);
 
 }  // namespace mcz

@@ -23,6 +23,7 @@ static constexpr int PT = 576;            // threads per block: 18 warps
 static constexpr int PW = PT / 32;
 static constexpr int CAND_FLOATS = 128;   // per-warp candidate area (counter + 64-entry list)
 static constexpr int CTRL_BYTES = 1024;
+static constexpr int MAX_DST = 8;                 // ranks of one node
 static constexpr uint32_t SEEN_KD = 1u << 8;     // ctrl->flags bit above the eight line flags
 static constexpr int DIVERGENCE_CHECK_TRIP = 8;   // when to test a still-running N2Ha loop for provable divergence
 
@@ -37,9 +38,13 @@ struct ProdParams {
   unsigned long long goff;
   int correlated, deterministic;
   uint32_t calls;                          // bit c set: Philox call c is needed
-  float* pct;
-  int* nvalid;
-  signed char* status;
+  // result tables: ndst destinations (1 = the caller's local tables; > 1 = the gathered tables of
+  // every rank, written over NVLink peer mappings), rows start at row0 in each of them
+  int ndst;
+  long long row0;
+  float* pct[MAX_DST];
+  int* nvalid[MAX_DST];
+  signed char* status[MAX_DST];
   int* trips;
   int* ret;
   float* Z;
@@ -255,7 +260,10 @@ production_kernel(const __grid_constant__ ProdParams p) {
   for (;;) {
     __syncthreads();
     const long long g = ctrl->g;
-    if (g >= p.G) break;
+    if (g >= p.G) {
+      if (p.ndst > 1) __threadfence_system();    // result rows written into other GPUs' tables
+      break;
+    }
     float lm[NUSED], le[NUSED];
     uint32_t assumed = 0u;
 #pragma unroll
@@ -706,10 +714,12 @@ production_kernel(const __grid_constant__ ProdParams p) {
       const int k = tid, sl = p.slot_of_key[k];
       const bool pres = (pm >> k) & 1ull;
       if (!(pres && sl >= 0)) {
-        const long long o = g * NKEYS + k;
-        p.status[o] = pres ? ST_EMPTY : ST_ABSENT;     // present but constant-NaN (M08_R23): n = 0
-        p.nvalid[o] = 0;
-        p.pct[3 * o] = p.pct[3 * o + 1] = p.pct[3 * o + 2] = Math<float>::nan();
+        const long long o = (p.row0 + g) * NKEYS + k;
+        for (int q = 0; q < p.ndst; ++q) {
+          p.status[q][o] = pres ? ST_EMPTY : ST_ABSENT;     // present but constant-NaN (M08_R23): n = 0
+          p.nvalid[q][o] = 0;
+          p.pct[q][3 * o] = p.pct[q][3 * o + 1] = p.pct[q][3 * o + 2] = Math<float>::nan();
+        }
       }
     }
     if (tid == 0) {
@@ -739,14 +749,16 @@ production_kernel(const __grid_constant__ ProdParams p) {
       }
 #endif
       if (lane == 0) {
-        const long long o = g * NKEYS + k;
-        p.status[o] = (signed char)stt;
-        p.nvalid[o] = nv;
-        p.pct[3 * o] = pc[0];
-        p.pct[3 * o + 1] = pc[1];
-        p.pct[3 * o + 2] = pc[2];
+        const long long o = (p.row0 + g) * NKEYS + k;
+        for (int q = 0; q < p.ndst; ++q) {
+          p.status[q][o] = (signed char)stt;
+          p.nvalid[q][o] = nv;
+          p.pct[q][3 * o] = pc[0];
+          p.pct[q][3 * o + 1] = pc[1];
+          p.pct[q][3 * o + 2] = pc[2];
+        }
 #if defined(MCZ_COLTIME_DUMP) && MCZ_COLTIME_DUMP == 1
-        p.pct[3 * o + 2] = (float)(clock64() - tc0);
+        p.pct[0][3 * o + 2] = (float)(clock64() - tc0);
 #endif
       }
     }
@@ -924,7 +936,7 @@ int launch_production(const float* meas, const float* err, long long G, long lon
                       int dust, unsigned long long seed, unsigned long long galaxy_offset,
                       int sample_mode, int deterministic, float* pct, int* nvalid,
                       signed char* status, int* trips, int* ret, float* Z, void* scratch,
-                      size_t scratch_bytes, cudaStream_t stream) {
+                      size_t scratch_bytes, cudaStream_t stream, const ProdDst* dst) {
   if (G <= 0) return 0;
   if (n_draw <= 0 || n_draw > 0x7fffffffll / 64) return set_error("mcz_forward_production: bad n_draw");
   ProdParams p;
@@ -937,7 +949,20 @@ int launch_production(const float* meas, const float* err, long long G, long lon
   p.correlated = sample_mode == 1; p.deterministic = deterministic != 0;
   p.calls = philox_calls(tok, p.correlated, p.deterministic);
   finish_slots(p);
-  p.pct = pct; p.nvalid = nvalid; p.status = status; p.trips = trips; p.ret = ret; p.Z = Z;
+  if (dst && dst->n > 0) {
+    if (dst->n > MAX_DST) return set_error("mcz_forward_production: more than 8 destination tables");
+    p.ndst = dst->n;
+    p.row0 = dst->row0;
+    for (int q = 0; q < dst->n; ++q) {
+      p.pct[q] = dst->pct[q]; p.nvalid[q] = dst->nvalid[q]; p.status[q] = dst->status[q];
+      if (!p.pct[q] || !p.nvalid[q] || !p.status[q]) return set_error("mcz_forward_production: null destination table");
+    }
+  } else {
+    p.ndst = 1;
+    p.row0 = 0;
+    p.pct[0] = pct; p.nvalid[0] = nvalid; p.status[0] = status;
+  }
+  p.trips = trips; p.ret = ret; p.Z = Z;
   p.counter = reinterpret_cast<unsigned long long*>(scratch);
   p.gscratch = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(scratch) + 256);
   p.gscratch_per_block = pl.per_block_floats;

@@ -3,8 +3,10 @@
 Every galaxy is independent (the reference's loop body has no cross-galaxy state,
 /root/reference/pyMCZ/mcz.py:575), so ranks take contiguous galaxy ranges, the Philox
 sub-sequence is the GLOBAL galaxy index (results do not depend on the number of ranks) and the
-only exchange of the whole path is one all-gather of the per-rank result tables -- the analogue
-of the reference's Pool.map return (mcz.py:553-569).  One process per GPU under torchrun;
+only exchange of the whole path is the gather of the per-rank result tables -- the analogue
+of the reference's Pool.map return (mcz.py:553-569).  On NCCL it is fused into the kernel
+(GatheredTables: every rank's kernel writes its rows into all ranks' tables over NVLink peer
+mappings); the all-gather form remains for the per-sample output and for gloo.  One process per GPU under torchrun;
 ``torch.distributed`` (NCCL on GPUs, gloo in the CPU tests) is plumbing only.
 """
 from __future__ import annotations
@@ -53,6 +55,44 @@ def gather_tables(tables: dict, G: int, group=None) -> dict:
     return {k: (all_gather_rows(v, counts, group) if v is not None else None) for k, v in tables.items()}
 
 
+class GatheredTables:
+    """Full-size result tables (pct [G,37,3] f32, nvalid [G,37] i32, status [G,37] i8) on every rank,
+    allocated as torch symmetric memory so that every rank holds NVLink peer mappings of all of
+    them.  ops.forward_production(..., gather=self) makes the production kernel write each result
+    row into all of them as it is produced: the gather of the reference's Pool.map results
+    (mcz.py:553-569) is fused into the kernel and no collective moves data.  wait() is the one
+    barrier after which the tables are complete everywhere.  Needs an initialised NCCL group."""
+
+    def __init__(self, G_total: int, device, group=None):
+        import ctypes
+        import torch.distributed._symmetric_memory as symm
+        from ._scales import NKEYS
+        from .synth import shard_bounds as _sb
+        self.group = group if group is not None else td.group.WORLD
+        self.world = td.get_world_size(self.group)
+        self.rank = td.get_rank(self.group)
+        if self.world > 8:
+            raise ValueError("GatheredTables: at most 8 ranks (one node)")
+        self.G_total = int(G_total)
+        self.row0 = _sb(self.G_total, self.world, self.rank)[0]
+        rows = max(self.G_total, 1)
+        self.pct = symm.empty((rows, NKEYS, 3), dtype=torch.float32, device=device)
+        self.nvalid = symm.empty((rows, NKEYS), dtype=torch.int32, device=device)
+        self.status = symm.empty((rows, NKEYS), dtype=torch.int8, device=device)
+        self._handles = [symm.rendezvous(t, self.group) for t in (self.pct, self.nvalid, self.status)]
+        arr = ctypes.c_void_p * self.world
+        self.pct_ptrs = arr(*[int(p) for p in self._handles[0].buffer_ptrs])
+        self.nvalid_ptrs = arr(*[int(p) for p in self._handles[1].buffer_ptrs])
+        self.status_ptrs = arr(*[int(p) for p in self._handles[2].buffer_ptrs])
+        self._flag = torch.zeros(1, dtype=torch.int32, device=device)
+
+    def wait(self):
+        """Every rank's launch has finished, so every row of the local tables has been written.
+        (A 4-byte all-reduce enqueued after the kernel: it cannot complete on any rank before all
+        ranks have reached it.)"""
+        td.all_reduce(self._flag, group=self.group)
+
+
 def production_table(meas, err, n_draw, tokens, dust, seed, correlated=False, deterministic=False,
                      return_samples=False, device=None):
     """Run the fused production kernel over a whole host table, sharded over the ranks of the
@@ -75,6 +115,21 @@ def production_table(meas, err, n_draw, tokens, dust, seed, correlated=False, de
     lo, hi = shard_bounds(G, world, r)
     m = torch.from_numpy(meas[lo:hi]).to(device)
     e = torch.from_numpy(err[lo:hi]).to(device)
+    if world > 1 and not return_samples and td.get_backend() == "nccl":
+        # the gather is fused into the kernel: result rows go straight into every rank's tables
+        gt = GatheredTables(G, device)
+        if hi > lo:
+            _, _, _, trips, ret, _ = ops.forward_production(
+                m, e, n_draw, tokens, dust, seed, galaxy_offset=lo, correlated=correlated,
+                deterministic=deterministic, gather=gt)
+        else:
+            trips = torch.empty((0, 2), dtype=torch.int32, device=device)
+            ret = torch.empty((0,), dtype=torch.int32, device=device)
+        gt.wait()
+        small = gather_tables(dict(trips=trips, ret=ret), G)
+        torch.cuda.synchronize(device)
+        out = dict(pct=gt.pct, nvalid=gt.nvalid, status=gt.status, trips=small["trips"], ret=small["ret"], Z=None)
+        return {k: (v.cpu().numpy() if v is not None else None) for k, v in out.items()}
     if hi > lo:
         pct, nvalid, status, trips, ret, Z = ops.forward_production(
             m, e, n_draw, tokens, dust, seed, galaxy_offset=lo, correlated=correlated,

@@ -107,9 +107,15 @@ class ProductionWorkspace:
 
 
 def forward_production(meas, err, n_draw, tokens, dust=DUST_ON, seed=0xB200, galaxy_offset=0,
-                       correlated=False, deterministic=False, return_samples=False, workspace=None):
+                       correlated=False, deterministic=False, return_samples=False, workspace=None,
+                       gather=None):
     """meas, err [G,11] f32 (cuda) -> (pct [G,37,3] f32, nvalid [G,37] i32, status [G,37] i8,
-    trips [G,2] i32, ret [G] i32, Z [G,37,n_draw] f32 or None).  Enqueues on the current stream."""
+    trips [G,2] i32, ret [G] i32, Z [G,37,n_draw] f32 or None).  Enqueues on the current stream.
+
+    gather: a dist.GatheredTables.  The kernel then writes this rank's result rows straight into
+    every rank's full tables (rows gather.row0 ...) over NVLink peer mappings instead of the
+    workspace's local pct/nvalid/status, which are returned untouched; call gather.wait() before
+    reading the tables."""
     L = _lib.lib()
     _need_cuda(meas, "meas")
     _need_cuda(err, "err")
@@ -124,6 +130,20 @@ def forward_production(meas, err, n_draw, tokens, dust=DUST_ON, seed=0xB200, gal
         ws = ProductionWorkspace(G, n_draw, tokens, dev, return_samples)
     elif (ws.G, ws.n_draw, ws.tokens) != (G, int(n_draw), int(tokens)) or ws.device != dev:
         raise ValueError("workspace does not match this call")
+    if gather is not None:
+        if return_samples:
+            raise ValueError("return_samples is not available with gather")
+        with torch.cuda.device(dev):
+            rc = L.mcz_forward_production_gather(
+                meas.data_ptr(), err.data_ptr(), G, int(n_draw), int(tokens), int(dust), int(seed),
+                int(galaxy_offset), 1 if correlated else 0, 1 if deterministic else 0,
+                gather.world, int(gather.row0), gather.pct_ptrs, gather.nvalid_ptrs, gather.status_ptrs,
+                ws.trips.data_ptr(), ws.ret.data_ptr(), ws.scratch.data_ptr(), ws.scratch_bytes + 0,
+                _stream_ptr(dev))
+            _lib.check(rc, "mcz_forward_production_gather")
+            if workspace is None:
+                ws.scratch.record_stream(torch.cuda.current_stream(dev))
+        return ws.pct, ws.nvalid, ws.status, ws.trips, ws.ret, None
     with torch.cuda.device(dev):
         rc = L.mcz_forward_production(
             meas.data_ptr(), err.data_ptr(), G, int(n_draw), int(tokens), int(dust), int(seed),
