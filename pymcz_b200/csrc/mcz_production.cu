@@ -7,10 +7,13 @@
 //   C. KK04 validity masks and KD02comb (metscales.py:1127-1129, 1186, 1250-1261);
 //   D. per (galaxy, scale) finite filter, n, sum<=0 test and the 50/16/84th percentiles with
 //      numpy's linear interpolation (mcz.py:273-301), one warp per scale.
-// Layout: one thread block per galaxy (dynamic galaxy queue), per-scale sample columns staged in
-// shared memory [slot][sample] (conflict-free: consecutive threads own consecutive samples);
-// nothing but the 2x11 input floats and the percentile table touches HBM.  A second
-// instantiation keeps the columns in an L2-resident global scratch for N' too large for 227 KB.
+// Layout: one thread block per galaxy (dynamic galaxy queue; the next galaxy's ticket and inputs
+// are fetched by the 18th warp during phase D), per-scale sample columns staged in shared memory
+// [slot][sample] (conflict-free: consecutive threads own consecutive samples); nothing but the
+// 2x11 input floats and the percentile table touches HBM.  production_kernel<0, WIDE> keeps the
+// columns in an L2-resident global scratch for N' too large for 227 KB.  With several GPUs the
+// result rows are written into every rank's full table (ProdParams::ndst): the gather of the
+// path is fused into the kernel.
 #include <float.h>
 #include "mcz_physics.cuh"
 #include "mcz_philox.cuh"

@@ -4,11 +4,14 @@
 //
 // One "round" = two streaming passes over the column (128-bit loads, no branches in the hot loop):
 //   pass H  1024-bin histogram of a monotone "fine index" f(x) over a value range [L, H], counted
-//           with shared-memory atomics on 16-bit counters packed two per word (2 KB per warp; the
-//           update is one ATOMS per sample and is LSU-bound, measured ~3 samples/clk/SM);
+//           with shared-memory atomics on 16-bit counters packed two per word (2 KB per warp; one
+//           branch-free ATOMS per sample -- the pass is bound by the shared-atomic pipe, measured
+//           4.9 clk per warp-wide ATOMS with 17 warps at it, tools/microbench/atoms2.cu); the sum
+//           of the column rides along;
 //   pass G  gather of the members of the (at most three) fine-index ranges that hold the target
 //           ranks -- a rank pair (k, k+1) always lies in one bin or in two bins with nothing in
-//           between -- followed by a 64-key bitonic sort in registers.
+//           between -- recorded as one bit per sample and appended afterwards, followed by a
+//           32- or 64-key bitonic sort in registers.
 // The first round uses a robust range from the first 64 samples, [q06 - 1.5w, q94 + 1.5w] cut to
 // that prefix's own [min, max]; values outside are clamped into the end bins.  Each of the (at
 // most three) target ranges may hold 64 candidates: one shared list and one sort when they fit in
@@ -17,8 +20,9 @@
 // rank.  A range that still holds more than 64 samples is "crowded": pass G records the exact
 // min / max of its members and how many equal the min (a tie is then answered at once), and
 // select_in_interval() runs further rounds restricted to [min, max] of the one bin that holds
-// both ranks (two ranks in different bins are the max of one and the min of the other), so the
-// interval shrinks by at least 1024x per round and the loop terminates.
+// both ranks (two ranks in different bins are the max of one and the min of the other); those
+// rounds index by ordered bit patterns, so the interval shrinks by at least 512x per round
+// whatever the spacing of the values, and the loop terminates.
 #pragma once
 
 namespace mcz {
