@@ -197,9 +197,17 @@ def run_ours(args):
     gath = fused = None
     if world > 1:
         if args.gather == "fused":
-            from pymcz_b200.dist import GatheredTables
-            fused = GatheredTables(G_total, dev)
-        else:
+            try:
+                from pymcz_b200.dist import GatheredTables
+                fused = GatheredTables(G_total, dev)
+            except Exception as exc:        # no peer mappings on this box: measure the NCCL form and say so
+                sys.stderr.write("bench.py: fused gather unavailable (%s); using NCCL all-gathers\n" % (exc,))
+                args.gather = "nccl"
+            ok = torch.tensor([1 if fused is not None else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if not int(ok.item()):
+                fused, args.gather = None, "nccl"
+        if fused is None:
             gath = dict(pct=torch.empty((G_total, sc.NKEYS, 3), dtype=torch.float32, device=dev),
                         nvalid=torch.empty((G_total, sc.NKEYS), dtype=torch.int32, device=dev),
                         status=torch.empty((G_total, sc.NKEYS), dtype=torch.int8, device=dev))

@@ -115,9 +115,14 @@ def production_table(meas, err, n_draw, tokens, dust, seed, correlated=False, de
     lo, hi = shard_bounds(G, world, r)
     m = torch.from_numpy(meas[lo:hi]).to(device)
     e = torch.from_numpy(err[lo:hi]).to(device)
+    gt = None
     if world > 1 and not return_samples and td.get_backend() == "nccl":
         # the gather is fused into the kernel: result rows go straight into every rank's tables
-        gt = GatheredTables(G, device)
+        try:
+            gt = GatheredTables(G, device)
+        except Exception:           # no peer mappings on this system: kernel, then all-gathers (below)
+            gt = None
+    if gt is not None:
         if hi > lo:
             _, _, _, trips, ret, _ = ops.forward_production(
                 m, e, n_draw, tokens, dust, seed, galaxy_offset=lo, correlated=correlated,
