@@ -290,7 +290,7 @@ MCZ_HD void phase_a(const R* f, const R* e, uint32_t flags, uint32_t tok, int du
   // E(B-V) (metscales.py:389-390) and a = 0.4 E (metscales.py:277)
   R E, a;
   if (dust_eff == 0) {
-    E = (R(0.45636603312904175) + lHb - lHa) / R(0.4 * (MCZ_K_HA - MCZ_K_HB));   // log10(2.86)
+    E = M::div(R(0.45636603312904175) + lHb - lHa, R(0.4 * (MCZ_K_HA - MCZ_K_HB)));   // log10(2.86)
     if (E <= R(0)) E = R(1e-5);
     a = R(0.4) * E;
   } else {
