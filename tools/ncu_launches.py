@@ -10,6 +10,7 @@ def main(path, cmd):
     hdr = rows[0]
     ik, iv, iu = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
     tot = defaultdict(lambda: [0, 0.0])
+    durs = defaultdict(list)
     for r in rows[1:]:
         if len(r) <= iv:
             continue
@@ -17,11 +18,17 @@ def main(path, cmd):
         v *= {"ns": 1.0, "us": 1e3, "ms": 1e6, "s": 1e9}.get(r[iu], 1.0)
         tot[r[ik][:70]][0] += 1
         tot[r[ik][:70]][1] += v
+        durs[r[ik][:70]].append(v)
     allns = sum(v[1] for v in tot.values())
     print("ncu --metrics gpu__time_duration.sum --clock-control none: %s" % cmd)
-    print("kernel, launches, total ns, share, mean ms per launch")
+    print("kernel, launches, total ns, share, min / median / max ms per launch")
     for k, (n, ns) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
-        print("%s, %d, %.0f, %.4f, %.3f" % (k, n, ns, ns / allns, ns / n / 1e6))
+        d = sorted(durs[k])
+        print("%s, %d, %.0f, %.4f, %.3f / %.3f / %.3f" % (k, n, ns, ns / allns, d[0] / 1e6, d[len(d) // 2] / 1e6, d[-1] / 1e6))
+    big = [v for k, d in durs.items() if "production_kernel" in k for v in d if v > 20e6]
+    if big:
+        print("production_kernel launches over the whole 125000-galaxy shard (the timed `value` steps): %d, mean %.3f ms; "
+              "the shorter ones are the 8 chunk launches per step of the e2e leg (mcz_ctx_run_host)" % (len(big), sum(big) / len(big) / 1e6))
 
 
 if __name__ == "__main__":
