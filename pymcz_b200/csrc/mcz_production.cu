@@ -15,6 +15,8 @@
 // result rows are written into every rank's full table (ProdParams::ndst): the gather of the
 // path is fused into the kernel.
 #include <float.h>
+#include <stdlib.h>
+#include <cooperative_groups.h>
 #include "mcz_physics.cuh"
 #include "mcz_philox.cuh"
 #include "mcz_device_utils.cuh"
@@ -928,11 +930,20 @@ int read_sel_counters(unsigned long long* out8, int reset) {
   return rc;
 }
 
+static size_t wide_scratch_bytes(long long N, int nstore);
+static bool use_wide(long long G, long long N, const float* Z);
+static int launch_wide(ProdParams& p, void* scratch, cudaStream_t stream);
+
 size_t production_scratch_bytes(long long G, long long n_draw, uint32_t tok) {
   ProdParams p;
   build_slots(tok, p);
   const ProdPlan pl = make_plan(G, n_draw, p.nstore);
-  return 256 + (size_t)pl.grid * (size_t)pl.per_block_floats * sizeof(float);
+  size_t need = 256 + (size_t)pl.grid * (size_t)pl.per_block_floats * sizeof(float);
+  if (use_wide(G, n_draw, nullptr)) {            // (Z is not known here: reserve for the wide kernel too)
+    const size_t w = wide_scratch_bytes(n_draw, p.nstore);
+    if (w > need) need = w;
+  }
+  return need;
 }
 
 int launch_production(const float* meas, const float* err, long long G, long long n_draw, uint32_t tok,
@@ -966,6 +977,7 @@ int launch_production(const float* meas, const float* err, long long G, long lon
     p.pct[0] = pct; p.nvalid[0] = nvalid; p.status[0] = status;
   }
   p.trips = trips; p.ret = ret; p.Z = Z;
+  if (use_wide(G, n_draw, Z)) return launch_wide(p, scratch, stream);
   p.counter = reinterpret_cast<unsigned long long*>(scratch);
   p.gscratch = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(scratch) + 256);
   p.gscratch_per_block = pl.per_block_floats;
@@ -1004,6 +1016,498 @@ int launch_production(const float* meas, const float* err, long long G, long lon
   }
   count_launch();
   return check_cuda(cudaGetLastError(), "production_kernel launch");
+}
+
+// ---- wide kernel: one galaxy at a time, samples tiled across all thread blocks ------------------
+// For single-object runs (few galaxies, N' in the 10^5 .. 10^7 range) one thread block
+// per galaxy would leave all but a few SMs idle.  This cooperative kernel gives every block a
+// contiguous slice of the samples of the SAME galaxy; what the phases need from the whole sample
+// set goes through global memory and grid-wide barriers:
+//   A  has* flags: atomicOr;
+//   B  the two KK04 means per trip: fixed-point 64-bit atomics, one grid barrier per two trips;
+//   D  per-slice histograms merged with global atomics, the plan made redundantly by every block
+//      from the merged histogram, candidates appended to a global list, one block finishes.
+// Per-sample results are identical to the per-galaxy kernels (same Philox indexing, same device
+// functions); columns whose target ranges are crowded fall back to warp_percentiles() by one warp
+// over the whole column.
+struct WideCtl {
+  unsigned flags;                 // line flags | SEEN_KD
+  unsigned nan[3];                // NaN bits of the KK04 sums, rotating with sums[]
+  long long sums[3][4];           // 16.16 fixed point
+  long long divsum;
+  unsigned ccount[NKEYS];         // per slot: candidates appended
+  unsigned ntie[NKEYS];           // per slot: copies of the repeated value
+  unsigned slow[NKEYS];           // per slot: needs the one-warp fallback
+  double colsum[NKEYS];
+};
+static_assert(sizeof(WideCtl) <= 4096, "wide control block too large");
+
+__global__ void __launch_bounds__(PT, 1)
+wide_kernel(const __grid_constant__ ProdParams p) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ __align__(16) unsigned char smem[];
+  typedef FineHist<false> FH;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nb = gridDim.x, b = blockIdx.x;
+  const int N = p.N, Npad = p.Npad, ngroups = Npad / 128;
+  // this block's slice: whole 128-sample groups
+  const int g_lo = (int)((long long)ngroups * b / nb), g_hi = (int)((long long)ngroups * (b + 1) / nb);
+  const int s_lo = g_lo * 128, s_hi = g_hi * 128;
+  unsigned* hist = reinterpret_cast<unsigned*>(smem) + (size_t)warp * FB;
+
+  unsigned char* base = reinterpret_cast<unsigned char*>(p.gscratch);
+  WideCtl* ctl = reinterpret_cast<WideCtl*>(base);
+  float* vals = reinterpret_cast<float*>(base + 4096);
+  float* st0 = vals + (long long)p.nstore * Npad;
+  float* st1 = st0 + Npad; float* st2 = st1 + Npad; float* st3 = st2 + Npad;
+  float* F = st3 + Npad;                                   // fields 0..5: Z1, Z2, lq1, lq2, lq1a, lq2a
+  unsigned* ghist = reinterpret_cast<unsigned*>(F + 6ll * Npad);     // [4 rounds][nstore][6 targets][256]
+  const int used2line[NUSED] = {L_HA, L_HB, L_O2, L_O3, L_N2, L_S2A, L_S2B, L_S39069};
+
+  for (long long g = 0; g < p.G; ++g) {
+    // ---- reset the control block and the merged histograms ------------------------------------
+    if (b == 0) {
+      for (int i = tid; i < (int)(sizeof(WideCtl) / 4); i += PT) reinterpret_cast<unsigned*>(ctl)[i] = 0u;
+    }
+    for (long long i = (long long)b * PT + tid; i < 4ll * p.nstore * 6 * 256; i += (long long)nb * PT) ghist[i] = 0u;
+    grid.sync();
+    float lm[NUSED], le[NUSED];
+    uint32_t assumed = 0u;
+#pragma unroll
+    for (int u = 0; u < NUSED; ++u) {
+      lm[u] = p.meas[g * NLINES + used2line[u]];
+      le[u] = p.deterministic ? 0.0f : p.err[g * NLINES + used2line[u]];
+      const float thr = (u >= U_S2B) ? 1e-9f : 0.0f;
+      bool a = finite_f(lm[u]) && finite_f(le[u]);
+      if (a && le[u] == 0.0f) a = lm[u] > thr;
+      if (a) assumed |= 1u << u;
+    }
+    const unsigned long long gg = p.goff + (unsigned long long)g;
+    // ---- phase A ------------------------------------------------------------------------------
+    uint32_t flags = assumed;
+    bool anykd = false;
+    for (;;) {
+      const int de = effective_dust(p.dust, flags);
+      uint32_t seen = 0u;
+      for (int s = s_lo + tid; s < s_hi; s += PT) {
+        if (s < N) {
+          float z[16];
+          draw_normals((uint32_t)s, gg, p, z);
+          float f[NUSED], e[5];
+#pragma unroll
+          for (int u = 0; u < NUSED; ++u) {
+            float v = fmaf(le[u], p.correlated ? z[5] : z[5 + u], lm[u]);
+            if (!finite_f(v)) v = 0.0f;
+            if (v < 0.0f) v = 0.0f;
+            f[u] = v;
+            const bool pos = (u >= U_S2B) ? (v > 1e-9f) : (v > 0.0f);
+            if (pos) seen |= 1u << u;
+          }
+          e[0] = 0.05f * z[0]; e[1] = 0.1f * z[1]; e[2] = 0.027f * z[2]; e[3] = 0.024f * z[3]; e[4] = 0.012f * z[4];
+          SlotPut<false> put{vals + s, p.col_off, 0u};
+          Carry<float> c;
+          c.y = c.n2ha = c.x = 0.0f;
+          c.aux = 0u;
+          phase_a<float>(f, e, flags, p.tok, de, put, c);
+          if (c.aux & AUX_KD_VALID) seen |= SEEN_KD;
+          st0[s] = c.y; st1[s] = c.n2ha; st2[s] = c.x; st3[s] = __uint_as_float(c.aux);
+        } else {
+          for (int sl = 0; sl < p.nstore; ++sl) vals[(long long)sl * Npad + s] = Math<float>::nan();
+        }
+      }
+      seen = __reduce_or_sync(0xffffffffu, seen);
+      if (lane == 0 && seen) atomicOr(&ctl->flags, seen);
+      grid.sync();
+      const uint32_t all = *reinterpret_cast<volatile unsigned*>(&ctl->flags);
+      const uint32_t actual = all & F_ALL;
+      anykd = (all & SEEN_KD) != 0u;
+      if (actual == flags) break;
+      flags = actual;
+      grid.sync();                                   // everyone has read the flags of the discarded pass
+      if (b == 0 && tid == 0) ctl->flags = actual;
+      grid.sync();
+    }
+    const uint64_t pm = present_mask(flags, p.tok);
+    const bool ok = minimum_ok(flags);
+
+    // ---- phases B and C -----------------------------------------------------------------------
+    int ii1 = 0, ii2 = 0;
+    if ((p.tok & T_KD02) && ok) {
+      const bool has_kd = (pm >> K_KD02_N2O2) & 1ull;
+      const bool has_kn = (pm >> K_KK04_N2HA) & 1ull, has_kr = (pm >> K_KK04_R23) & 1ull;
+      const bool o3o2 = (flags & F_O2) && (flags & F_O3);
+      const int sl_kd = p.slot_of_key[K_KD02_N2O2], sl_m91 = p.slot_of_key[K_M91];
+      bool act1 = has_kn && o3o2, act2 = has_kr;
+      const long long itol1 = (long long)(1.0e-3 * (double)N * 65536.0), itol2 = (long long)(1.0e-4 * (double)N * 65536.0);
+      auto consts = [&](int s, IterState<float>& st) {
+        Carry<float> c;
+        c.y = st0[s]; c.n2ha = st1[s]; c.x = st2[s];
+        c.aux = __float_as_uint(st3[s]);
+        make_iter<float>(c, 0.0f, st);
+      };
+      for (int s = s_lo + tid; s < s_hi && s < N; s += PT) {
+        IterState<float> st;
+        consts(s, st);
+        float z1 = has_kd ? vals[(long long)sl_kd * Npad + s] : Math<float>::nan();
+        if (!anykd) z1 = 8.6f;                                             // metscales.py:1097-1103
+        if (has_kn && !o3o2) z1 = st.A - 7.37177f * st.B;                  // metscales.py:1122-1126
+        F[0ll * Npad + s] = z1; F[1ll * Npad + s] = st.Z2;
+        F[2ll * Npad + s] = st.lq1; F[3ll * Npad + s] = st.lq2;
+      }
+      int ph = 0;
+      // fixed-point block -> grid sums of (up to) four terms; returns the four totals and NaN bits
+      auto grid_sums = [&](const float sm4[4], unsigned nanb, long long t4[4], unsigned& nb) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int q = __reduce_add_sync(0xffffffffu, __float2int_rn(sm4[k] * 65536.0f));
+          if (lane == 0 && q) atomicAdd(reinterpret_cast<unsigned long long*>(&ctl->sums[ph][k]), (unsigned long long)(long long)q);
+        }
+        nanb = __reduce_or_sync(0xffffffffu, nanb);
+        if (lane == 0 && nanb) atomicOr(&ctl->nan[ph], nanb);
+        const int nx = ph == 2 ? 0 : ph + 1;
+        if (b == 0 && tid < 4) ctl->sums[nx][tid] = 0;
+        if (b == 0 && tid == 4) ctl->nan[nx] = 0u;
+        grid.sync();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) t4[k] = *reinterpret_cast<volatile long long*>(&ctl->sums[ph][k]);
+        nb = *reinterpret_cast<volatile unsigned*>(&ctl->nan[ph]);
+        ph = nx;
+      };
+      while (act1 || act2) {
+        float sm4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        unsigned nanb = 0u;
+        for (int s = s_lo + tid; s < s_hi && s < N; s += PT) {
+          IterState<float> k;
+          consts(s, k);
+          const float num0 = k.num0, num1 = k.num1, den0 = k.den0, den1 = k.den1;
+          if (act1) {
+            const float Z1 = F[0ll * Npad + s], lq1 = F[2ll * Npad + s];
+            const float lq = (num0 + Z1 * num1) * fast_rcp(den0 + Z1 * den1);
+            const float z = k.A - lq * k.B;
+            float d = fabsf(lq - lq1);
+            nanb |= (d != d) ? 1u : 0u;
+            sm4[0] += fminf(d, 8.0f);
+            const float lqb = (num0 + z * num1) * fast_rcp(den0 + z * den1);
+            d = fabsf(lqb - lq);
+            nanb |= (d != d) ? 2u : 0u;
+            sm4[1] += fminf(d, 8.0f);
+            F[0ll * Npad + s] = k.A - lqb * k.B;
+            F[2ll * Npad + s] = lqb;
+            F[4ll * Npad + s] = lq;
+          }
+          if (act2) {
+            const float Z2 = F[1ll * Npad + s], lq2 = F[3ll * Npad + s];
+            const bool lowz = (k.aux & AUX_ZI_MASK) <= 1u;
+            const float lq = (num0 + Z2 * num1) * fast_rcp(den0 + Z2 * den1);
+            bool lower = lowz && (lq >= 6.7f) && (lq < 8.3f);
+            const float z = (lower ? k.L0 : k.U0) - lq * (lower ? k.L1 : k.U1);
+            float d = lq2 - lq;
+            nanb |= (d != d) ? 4u : 0u;
+            sm4[2] += fminf(fmaxf(d, -8.0f), 8.0f);
+            const float lqb = (num0 + z * num1) * fast_rcp(den0 + z * den1);
+            lower = lowz && (lqb >= 6.7f) && (lqb < 8.3f);
+            d = lq - lqb;
+            nanb |= (d != d) ? 8u : 0u;
+            sm4[3] += fminf(fmaxf(d, -8.0f), 8.0f);
+            F[1ll * Npad + s] = (lower ? k.L0 : k.U0) - lqb * (lower ? k.L1 : k.U1);
+            F[3ll * Npad + s] = lqb;
+            F[5ll * Npad + s] = lq;
+          }
+        }
+        long long t4[4];
+        unsigned nb;
+        grid_sums(sm4, nanb, t4, nb);
+        if (act1) {
+          ++ii1;
+          if ((nb & 1u) || !(t4[0] > itol1) || ii1 >= 100) {
+            act1 = false;
+            for (int s = s_lo + tid; s < s_hi && s < N; s += PT) {
+              IterState<float> k;
+              consts(s, k);
+              const float lq = F[4ll * Npad + s];
+              F[2ll * Npad + s] = lq;
+              F[0ll * Npad + s] = k.A - lq * k.B;
+            }
+          } else {
+            ++ii1;
+            act1 = !(nb & 2u) && (t4[1] > itol1) && ii1 < 100;
+          }
+        }
+        if (act2) {
+          ++ii2;
+          if ((nb & 4u) || !((t4[2] < 0 ? -t4[2] : t4[2]) > itol2) || ii2 >= 100) {
+            act2 = false;
+            for (int s = s_lo + tid; s < s_hi && s < N; s += PT) {
+              IterState<float> k;
+              consts(s, k);
+              const float lq = F[5ll * Npad + s];
+              const bool lower = ((k.aux & AUX_ZI_MASK) <= 1u) && (lq >= 6.7f) && (lq < 8.3f);
+              F[3ll * Npad + s] = lq;
+              F[1ll * Npad + s] = (lower ? k.L0 : k.U0) - lq * (lower ? k.L1 : k.U1);
+            }
+          } else {
+            ++ii2;
+            act2 = !(nb & 8u) && ((t4[3] < 0 ? -t4[3] : t4[3]) > itol2) && ii2 < 100;
+          }
+        }
+        if (act1 && ii1 == DIVERGENCE_CHECK_TRIP) {      // proven-divergence exit (see production_kernel)
+          float sm[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+          for (int s = s_lo + tid; s < s_hi && s < N; s += PT) {
+            IterState<float> k;
+            consts(s, k);
+            const float al = k.num0 + k.A * k.num1, be = k.B * k.num1, ga = k.den0 + k.A * k.den1, de = k.B * k.den1;
+            const float bg = be + ga, disc = bg * bg - 4.0f * al * de;
+            float m = 0.0f;
+            if (disc < 0.0f) {
+              const float r = __fsqrt_rn(al * de - be * ga), ide = fast_rcp(de);
+              const float u1 = (ga + r) * ide, u2 = (ga - r) * ide;
+              const float q1 = (de * u1 - bg) * u1 + al, q2 = (de * u2 - bg) * u2 + al;
+              m = fminf(fabsf(q1), fabsf(q2)) * fast_rcp(r);
+            }
+            sm[0] += (m == m) ? fminf(m, 8.0f) : 0.0f;
+          }
+          long long t4b[4];
+          unsigned nbb;
+          grid_sums(sm, 0u, t4b, nbb);
+          if (t4b[0] > 4 * itol1) { ii1 = 100; act1 = false; }
+        }
+      }
+      for (int s = s_lo + tid; s < s_hi && s < N; s += PT) {
+        IterState<float> st;
+        consts(s, st);
+        st.Z1 = F[0ll * Npad + s]; st.Z2 = F[1ll * Npad + s]; st.lq2 = F[3ll * Npad + s];
+        SlotPut<false> put{vals + s, p.col_off, 0u};
+        const float kd = has_kd ? vals[(long long)sl_kd * Npad + s] : Math<float>::nan();
+        const float m91 = vals[(long long)sl_m91 * Npad + s];
+        phase_c<float>(st, pm, ii1 >= 100, ii2 >= 100, kd, m91, put);
+      }
+    }
+    grid.sync();          // all columns final
+
+    // ---- phase D: distributed selection -------------------------------------------------------
+    if (b == 0 && tid < NKEYS) {
+      const int k = tid, sl = p.slot_of_key[k];
+      const bool pres = (pm >> k) & 1ull;
+      if (!(pres && sl >= 0)) {
+        const long long o = (p.row0 + g) * NKEYS + k;
+        for (int q = 0; q < p.ndst; ++q) {
+          p.status[q][o] = pres ? ST_EMPTY : ST_ABSENT;
+          p.nvalid[q][o] = 0;
+          p.pct[q][3 * o] = p.pct[q][3 * o + 1] = p.pct[q][3 * o + 2] = Math<float>::nan();
+        }
+      }
+    }
+    if (b == 0 && tid == 0) {
+      p.trips[2 * g] = ii1;
+      p.trips[2 * g + 1] = ii2;
+      if (p.ret) p.ret[g] = ok ? 0 : -1;
+    }
+    // MSB radix select on the order-preserving bit patterns of the floats, 8 bits per round, for the
+    // six ranks np.percentile interpolates between: exact whatever the distribution (ties end in
+    // one bit pattern), no gather, no sort.  Per round every block histograms its slice (shared
+    // memory, 16-bit counters), merges into the global table, and after the grid barrier every
+    // block locates the six ranks in the merged table (redundantly, identically).
+    unsigned tpre[2][6];        // per slot (this warp handles slots warp, warp + PW): prefix of each target
+    unsigned trk[2][6];         // rank of each target inside its prefix
+    double gam[2][3];
+    int nfin[2] = {0, 0};
+    bool live[2] = {false, false};
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int sl = warp + h * PW;
+      live[h] = sl < p.nstore && ((pm >> p.key_of_slot[sl < p.nstore ? sl : 0]) & 1ull);
+#pragma unroll
+      for (int t = 0; t < 6; ++t) { tpre[h][t] = 0u; trk[h][t] = 0u; }
+    }
+    unsigned short* rh = reinterpret_cast<unsigned short*>(hist);      // [6][256] 16-bit counters
+#pragma unroll 1
+    for (int round = 0; round < 4; ++round) {
+      const int shift = 24 - 8 * round;
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        if (!live[h]) continue;
+        const int sl = warp + h * PW;
+        const float* col = vals + (long long)sl * Npad;
+        // distinct prefixes among the six targets (ascending ranks -> non-decreasing prefixes)
+        unsigned uq[6];
+        int nu = 0;
+#pragma unroll
+        for (int t = 0; t < 6; ++t)
+          if (nu == 0 || tpre[h][t] != uq[nu - 1 < 0 ? 0 : nu - 1]) { uq[nu] = tpre[h][t]; ++nu; }
+        for (int i = lane; i < 6 * 128; i += 32) hist[i] = 0u;
+        __syncwarp();
+        float sum = 0.0f;
+        for (int g0 = g_lo; g0 < g_hi; ++g0) {
+          const float4 x4 = *reinterpret_cast<const float4*>(col + 4 * lane + 128 * g0);
+          const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float x = xs[j];
+            if (!finite_f(x)) continue;
+            if (round == 0) sum += x;
+            const unsigned u = ordered_bits(x);
+            const unsigned pre = round == 0 ? 0u : (u >> (shift + 8));
+            int which = -1;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) if (i < nu && uq[i] == pre) which = i;
+            if (which >= 0) {
+              const unsigned bin = (u >> shift) & 255u;
+              const unsigned idx = (unsigned)which * 256u + bin;
+              atomicAdd(hist + (idx >> 1), 1u << ((idx & 1u) << 4));
+            }
+          }
+        }
+        __syncwarp();
+        unsigned* gh = ghist + (((long long)round * p.nstore + sl) * 6) * 256;
+        for (int i = lane; i < nu * 256; i += 32) {
+          const unsigned c = rh[i];
+          if (c) atomicAdd(gh + i, c);
+        }
+        if (round == 0) {
+          const double tot = warp_sum((double)sum);
+          if (lane == 0) atomicAdd(&ctl->colsum[sl], tot);
+        }
+        __syncwarp();
+      }
+      grid.sync();
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        if (!live[h]) continue;
+        const int sl = warp + h * PW;
+        const unsigned* gh = ghist + (((long long)round * p.nstore + sl) * 6) * 256;
+        unsigned uq[6];
+        int nu = 0;
+#pragma unroll
+        for (int t = 0; t < 6; ++t)
+          if (nu == 0 || tpre[h][t] != uq[nu - 1 < 0 ? 0 : nu - 1]) { uq[nu] = tpre[h][t]; ++nu; }
+        if (round == 0) {
+          unsigned c = 0;
+          for (int i = lane; i < 256; i += 32) c += __ldcg(gh + i);
+          nfin[h] = (int)__reduce_add_sync(0xffffffffu, c);
+          if (nfin[h] == 0) { live[h] = false; continue; }
+          const double qs[3] = {16.0 / 100.0, 50.0 / 100.0, 84.0 / 100.0};              // mcz.py:288
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            const double vi = (double)(nfin[h] - 1) * qs[q];
+            const double lo = floor(vi);
+            gam[h][q] = vi - lo;
+            trk[h][2 * q] = (unsigned)lo;
+            trk[h][2 * q + 1] = min((unsigned)lo + 1u, (unsigned)(nfin[h] - 1));
+          }
+        }
+#pragma unroll
+        for (int t = 0; t < 6; ++t) {
+          int which = 0;
+#pragma unroll
+          for (int i = 0; i < 6; ++i) if (i < nu && uq[i] == tpre[h][t]) which = i;
+          // lane holds bins [8 lane, 8 lane + 8) of the target's table
+          unsigned c8[8], tot = 0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { c8[i] = __ldcg(gh + which * 256 + 8 * lane + i); tot += c8[i]; }
+          unsigned inc = tot;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+          }
+          const unsigned ex = inc - tot, r = trk[h][t];
+          const unsigned own = __ballot_sync(0xffffffffu, tot > 0 && r >= ex && r < ex + tot);
+          const int ol = own ? __ffs(own) - 1 : 0;
+          // inside the owning lane: which of its 8 bins
+          unsigned run = ex, bin = 0, before = ex;
+          bool found = false;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (!found && r < run + c8[i]) { bin = (unsigned)i; before = run; found = true; }
+            run += c8[i];
+          }
+          const unsigned gbin = __shfl_sync(0xffffffffu, 8u * (unsigned)lane + bin, ol);
+          const unsigned gbefore = __shfl_sync(0xffffffffu, before, ol);
+          tpre[h][t] = (tpre[h][t] << 8) | gbin;
+          trk[h][t] = r - gbefore;
+        }
+      }
+    }
+    // ---- results: block 0, lane 0 of each warp --------------------------------------------------
+    for (int h = 0; h < 2; ++h) {
+      const int sl = warp + h * PW;
+      if (sl >= p.nstore || b != 0) continue;
+      const int k = p.key_of_slot[sl];
+      if (!((pm >> k) & 1ull)) continue;
+      float pc[3] = {Math<float>::nan(), Math<float>::nan(), Math<float>::nan()};
+      int stt = ST_EMPTY;
+      if (nfin[h] > 0) {
+        const double tot = *reinterpret_cast<volatile double*>(&ctl->colsum[sl]);
+        if (!(tot > 0.0)) {
+          stt = ST_NONPOS;
+        } else {
+          float val[6];
+#pragma unroll
+          for (int t = 0; t < 6; ++t) {
+            const unsigned u = tpre[h][t];
+            val[t] = __uint_as_float(u >= 0x80000000u ? u - 0x80000000u : ((0x80000000u - u) | 0x80000000u));
+          }
+          pc[0] = np_lerp_f(val[2], val[3], gam[h][1]);       // median
+          pc[1] = np_lerp_f(val[0], val[1], gam[h][0]);       // 16th
+          pc[2] = np_lerp_f(val[4], val[5], gam[h][2]);       // 84th
+          stt = ST_OK;
+        }
+      }
+      if (lane == 0) {
+        const long long o = (p.row0 + g) * NKEYS + k;
+        for (int q = 0; q < p.ndst; ++q) {
+          p.status[q][o] = (signed char)stt;
+          p.nvalid[q][o] = nfin[h];
+          p.pct[q][3 * o] = pc[0]; p.pct[q][3 * o + 1] = pc[1]; p.pct[q][3 * o + 2] = pc[2];
+        }
+      }
+    }
+    grid.sync();          // the scratch is reused by the next galaxy
+  }
+  if (p.ndst > 1) __threadfence_system();
+}
+
+
+static size_t wide_scratch_bytes(long long N, int nstore) {
+  const long long Npad = (N + 127) / 128 * 128;
+  return 4096 + (size_t)((long long)nstore + 4 + 6) * Npad * sizeof(float) + (size_t)4 * nstore * 6 * 256 * sizeof(unsigned);
+}
+
+// Few galaxies with very many samples each (single-object runs): the cooperative wide kernel.
+static bool use_wide(long long G, long long N, const float* Z) {
+  const char* force = getenv("MCZ_WIDE");              // "1": always (tests), "0": never
+  if (Z) return false;
+  if (force && force[0] == '0') return false;
+  if ((N + 127) / 128 * 128 / num_sms() >= 65536) return false;      // 16-bit slice histograms
+  if (force && force[0] == '1') return true;
+  return G <= 8 && N >= 32768;
+}
+
+static int launch_wide(ProdParams& p, void* scratch, cudaStream_t stream) {
+  p.Npad = (int)((p.N + 127ll) / 128 * 128);
+  finish_slots(p);
+  p.gscratch = reinterpret_cast<float*>(scratch);
+  const size_t smem = (size_t)PW * FineHist<false>::BYTES;
+  static int max_blocks = 0;
+  if (!max_blocks) {
+    int rc = check_cuda(cudaFuncSetAttribute(wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attribute");
+    if (rc) return rc;
+    int per_sm = 0;
+    rc = check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wide_kernel, PT, smem), "occupancy");
+    if (rc) return rc;
+    if (per_sm < 1) return set_error("wide_kernel does not fit on an SM");
+    max_blocks = per_sm * num_sms();
+  }
+  int grid = max_blocks < num_sms() ? max_blocks : num_sms();
+  const int ngroups = p.Npad / 128;
+  if (grid > ngroups) grid = ngroups;
+  void* args[] = {&p};
+  const int rc = check_cuda(cudaLaunchCooperativeKernel((void*)wide_kernel, dim3(grid), dim3(PT), args, smem, stream),
+                            "wide_kernel launch");
+  if (rc) return rc;
+  count_launch();
+  return 0;
 }
 
 // ---- selection on caller-supplied columns (test entry point) -----------------------------------
