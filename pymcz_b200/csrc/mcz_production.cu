@@ -939,7 +939,7 @@ size_t production_scratch_bytes(long long G, long long n_draw, uint32_t tok) {
   build_slots(tok, p);
   const ProdPlan pl = make_plan(G, n_draw, p.nstore);
   size_t need = 256 + (size_t)pl.grid * (size_t)pl.per_block_floats * sizeof(float);
-  if (use_wide(G, n_draw, nullptr)) {            // (Z is not known here: reserve for the wide kernel too)
+  if (use_wide(G, n_draw, nullptr)) {
     const size_t w = wide_scratch_bytes(n_draw, p.nstore);
     if (w > need) need = w;
   }
@@ -1284,6 +1284,14 @@ wide_kernel(const __grid_constant__ ProdParams p) {
       }
     }
     grid.sync();          // all columns final
+    if (p.Z) {            // optional per-sample output (pickle / --asciidistrib path): this block's slice
+      for (int k = 0; k < NKEYS; ++k) {
+        const int sl = p.slot_of_key[k];
+        const bool livek = ((pm >> k) & 1ull) && sl >= 0;
+        float* dst = p.Z + ((long long)g * NKEYS + k) * N;
+        for (int s = s_lo + tid; s < s_hi && s < N; s += PT) dst[s] = livek ? vals[(long long)sl * Npad + s] : Math<float>::nan();
+      }
+    }
 
     // ---- phase D: distributed selection -------------------------------------------------------
     if (b == 0 && tid < NKEYS) {
@@ -1477,7 +1485,7 @@ static size_t wide_scratch_bytes(long long N, int nstore) {
 // Few galaxies with very many samples each (single-object runs): the cooperative wide kernel.
 static bool use_wide(long long G, long long N, const float* Z) {
   const char* force = getenv("MCZ_WIDE");              // "1": always (tests), "0": never
-  if (Z) return false;
+  (void)Z;
   if (force && force[0] == '0') return false;
   if ((N + 127) / 128 * 128 / num_sms() >= 65536) return false;      // 16-bit slice histograms
   if (force && force[0] == '1') return true;

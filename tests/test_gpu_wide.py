@@ -21,12 +21,12 @@ EX_E = np.array([[0.1005, 0.0435, 0.028, 0.0245, 0.00, 0.069, 0.0335, 0.0345, 0.
                  [0.053, 0.032, 0.00, 0.029, 0.0205, 0.0255, 0.022, 0.0205, 0.0185, 0.00, 0.00]], dtype=np.float32)
 
 
-def run(meas, err, n, tok, wide, dust=sc.DUST_ON, correlated=False, deterministic=False):
+def run(meas, err, n, tok, wide, dust=sc.DUST_ON, correlated=False, deterministic=False, samples=False):
     old = os.environ.get("MCZ_WIDE")
     os.environ["MCZ_WIDE"] = "1" if wide else "0"
     try:
         out = ops.forward_production(torch.from_numpy(meas).cuda(), torch.from_numpy(err).cuda(), n, tok, dust,
-                                     0xB200, 3, correlated, deterministic)
+                                     0xB200, 3, correlated, deterministic, samples)
         torch.cuda.synchronize()
     finally:
         if old is None:
@@ -70,6 +70,20 @@ def test_wide_kernel_equals_per_galaxy_kernel(n, mds):
     rest = [j for j in range(sc.NKEYS) if j not in it]
     assert np.array_equal(a[:, rest].view(np.int32), b[:, rest].view(np.int32))
     assert np.allclose(a[:, it], b[:, it], rtol=0, atol=4e-6, equal_nan=True), np.nanmax(np.abs(a[:, it] - b[:, it]))
+
+
+def test_wide_kernel_per_sample_output():
+    """Z[G,37,N'] (pickle / --asciidistrib product) from the wide kernel equals the per-galaxy kernel's,
+    bit for bit outside the KK04 iteration."""
+    meas, err = tables()
+    meas, err = meas[:12], err[:12]
+    ref = run(meas, err, 5000, sc.T_ALL, wide=False, samples=True)
+    wid = run(meas, err, 5000, sc.T_ALL, wide=True, samples=True)
+    same = np.all(ref[3] == wid[3], axis=1)
+    it = [sc.KEY_INDEX[k] for k in ("KK04_N2Ha", "KK04_R23", "KD02comb")]
+    rest = [j for j in range(sc.NKEYS) if j not in it]
+    assert np.array_equal(ref[5][:, rest].view(np.int32), wid[5][:, rest].view(np.int32))
+    assert np.allclose(ref[5][same][:, it], wid[5][same][:, it], rtol=0, atol=4e-6, equal_nan=True)
 
 
 def test_wide_kernel_is_chosen_for_single_object_runs():
