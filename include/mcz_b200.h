@@ -137,6 +137,28 @@ int mcz_forward_production_gather(const float* meas_d, const float* err_d, long 
                                   void* const* nvalid_tables, void* const* status_tables, int* trips_d,
                                   int* ret_d, void* scratch_d, size_t scratch_bytes, void* stream);
 
+/* ---- multi-GPU, single-object runs: ONE galaxy's samples sharded over the GPUs --------------------
+ * For runs with few measurements and very many samples each (the reference's per-galaxy vectors,
+ * mcz.py:509-519, in the 10^6 .. 10^8 range).  Every rank passes the SAME meas/err table and gets the
+ * SAME result tables; rank r draws and evaluates samples [N' r / nranks, N' (r+1) / nranks) (Philox is
+ * indexed by the global sample number, so results do not depend on nranks) and everything the
+ * reference takes over the whole sample vector -- the has* flags (metscales.py:287-378), the KK04 loop
+ * means per trip (:1111, :1166), the order statistics (mcz.py:288) -- is reduced across ranks inside the
+ * kernel through the shared regions: shared_regions[q] is rank q's region of
+ * mcz_samples_shared_bytes(tokens) bytes as mapped into this process (NVLink peer mapping; q = rank is
+ * the local one).  The caller zeroes its region, synchronises, and makes sure every rank has done so
+ * (one host-side barrier) before any rank calls this; all ranks must call it together.
+ * nranks = 1 is the single-GPU form (mcz_forward_production picks it by itself for G <= 8, N' >= 32768).
+ */
+size_t mcz_samples_shared_bytes(unsigned tokens);
+size_t mcz_samples_scratch_bytes(long long n_draw, unsigned tokens);   /* private scratch_d of each rank */
+int mcz_forward_production_samples(const float* meas_d, const float* err_d, long long G, long long n_draw,
+                                   unsigned tokens, int dust, unsigned long long seed,
+                                   unsigned long long galaxy_offset, int sample_mode, int deterministic,
+                                   int nranks, int rank, void* const* shared_regions, float* pct_d,
+                                   int* nvalid_d, signed char* status_d, int* trips_d, int* ret_d,
+                                   void* scratch_d, size_t scratch_bytes, void* stream);
+
 /* ---- host-buffer convenience (what run() would call once for the whole table) -----------------
  * Same as mcz_forward_production but with HOST pointers: uploads meas/err, runs, downloads the
  * tables, synchronises.  Device buffers live in the context.  Tables of 32768 galaxies or more run

@@ -47,6 +47,13 @@ SIGNATURES = {
         ctypes.c_int, ctypes.c_ulonglong, ctypes.c_ulonglong, ctypes.c_int, ctypes.c_int,
         ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "mcz_samples_shared_bytes": (ctypes.c_size_t, [ctypes.c_uint]),
+    "mcz_samples_scratch_bytes": (ctypes.c_size_t, [ctypes.c_longlong, ctypes.c_uint]),
+    "mcz_forward_production_samples": (ctypes.c_int, [
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_uint,
+        ctypes.c_int, ctypes.c_ulonglong, ctypes.c_ulonglong, ctypes.c_int, ctypes.c_int,
+        ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "mcz_ctx_create": (ctypes.c_void_p, [ctypes.c_int]),
     "mcz_ctx_destroy": (None, [ctypes.c_void_p]),
     "mcz_ctx_run_host": (ctypes.c_int, [

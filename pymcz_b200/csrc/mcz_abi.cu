@@ -126,6 +126,28 @@ int mcz_forward_production_gather(const float* meas_d, const float* err_d, long 
                            scratch_bytes, (cudaStream_t)stream, &dst);
 }
 
+size_t mcz_samples_shared_bytes(unsigned tokens) { return wide_shared_bytes(tokens); }
+size_t mcz_samples_scratch_bytes(long long n_draw, unsigned tokens) { return wide_private_bytes(n_draw, tokens); }
+
+int mcz_forward_production_samples(const float* meas_d, const float* err_d, long long G, long long n_draw,
+                                   unsigned tokens, int dust, unsigned long long seed,
+                                   unsigned long long galaxy_offset, int sample_mode, int deterministic,
+                                   int nranks, int rank, void* const* shared_regions, float* pct_d,
+                                   int* nvalid_d, signed char* status_d, int* trips_d, int* ret_d,
+                                   void* scratch_d, size_t scratch_bytes, void* stream) {
+  if (!meas_d || !err_d || !shared_regions || !pct_d || !nvalid_d || !status_d || !trips_d || !scratch_d)
+    return set_error("mcz_forward_production_samples: null pointer");
+  if (nranks < 1 || nranks > 8 || rank < 0 || rank >= nranks)
+    return set_error("mcz_forward_production_samples: 1 to 8 ranks, 0 <= rank < nranks");
+  WideShare ws;
+  ws.rank = rank;
+  ws.world = nranks;
+  for (int q = 0; q < nranks; ++q) ws.shared[q] = shared_regions[q];
+  return launch_production(meas_d, err_d, G, n_draw, tokens, dust, seed, galaxy_offset, sample_mode,
+                           deterministic, pct_d, nvalid_d, status_d, trips_d, ret_d, nullptr, scratch_d,
+                           scratch_bytes, (cudaStream_t)stream, nullptr, nranks > 1 ? &ws : nullptr);
+}
+
 // diagnostics (not part of the public header): selection-path counters since the last reset:
 // [0] columns, [1] fast path, [2] fallback: degenerate range, [3] fallback: target in an edge bin
 // or > 4 target bins, [4] fallback: > 64 candidates (ties), [5] empty / non-positive columns

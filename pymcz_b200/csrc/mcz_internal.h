@@ -34,10 +34,19 @@ struct ProdDst {
   int* nvalid[8];
   signed char* status[8];
 };
+// One object's samples sharded over the GPUs of a node (wide kernel): rank, world and every rank's
+// shared region (control block, merged histograms, barrier counter) as mapped into this process.
+struct WideShare {
+  int rank, world;
+  void* shared[8];
+};
 int launch_production(const float* meas, const float* err, long long G, long long n_draw, uint32_t tok,
                       int dust, unsigned long long seed, unsigned long long galaxy_offset,
                       int sample_mode, int deterministic, float* pct, int* nvalid,
                       signed char* status, int* trips, int* ret, float* Z, void* scratch,
-                      size_t scratch_bytes, cudaStream_t stream, const ProdDst* dst = nullptr);
+                      size_t scratch_bytes, cudaStream_t stream, const ProdDst* dst = nullptr,
+                      const struct WideShare* ws = nullptr);
+size_t wide_shared_bytes(uint32_t tok);
+size_t wide_private_bytes(long long N, uint32_t tok);
 
 }  // namespace mcz

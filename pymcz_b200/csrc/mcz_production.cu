@@ -58,6 +58,10 @@ struct ProdParams {
   signed char slot_of_key[NKEYS];
   signed char key_of_slot[NKEYS];
   int col_off[NKEYS];                      // slot * Npad (float index of the column), -1 if not stored
+  // wide kernel: the galaxy's samples may also be sharded over the GPUs of a node; wshared[q] is rank
+  // q's control block + merged histograms + barrier counter as mapped into this process
+  int wrank, wworld;
+  void* wshared[MAX_DST];
   unsigned long long* counter;
   float* gscratch;                         // global variant: per-block columns + stash + loop state
   long long gscratch_per_block;            // floats
@@ -932,7 +936,7 @@ int read_sel_counters(unsigned long long* out8, int reset) {
 
 static size_t wide_scratch_bytes(long long N, int nstore);
 static bool use_wide(long long G, long long N, const float* Z);
-static int launch_wide(ProdParams& p, void* scratch, cudaStream_t stream);
+static int launch_wide(ProdParams& p, void* scratch, cudaStream_t stream, const WideShare* ws);
 
 size_t production_scratch_bytes(long long G, long long n_draw, uint32_t tok) {
   ProdParams p;
@@ -950,13 +954,13 @@ int launch_production(const float* meas, const float* err, long long G, long lon
                       int dust, unsigned long long seed, unsigned long long galaxy_offset,
                       int sample_mode, int deterministic, float* pct, int* nvalid,
                       signed char* status, int* trips, int* ret, float* Z, void* scratch,
-                      size_t scratch_bytes, cudaStream_t stream, const ProdDst* dst) {
+                      size_t scratch_bytes, cudaStream_t stream, const ProdDst* dst, const WideShare* ws) {
   if (G <= 0) return 0;
   if (n_draw <= 0 || n_draw > 0x7fffffffll / 64) return set_error("mcz_forward_production: bad n_draw");
   ProdParams p;
   build_slots(tok, p);
   const ProdPlan pl = make_plan(G, n_draw, p.nstore);
-  if (scratch_bytes < production_scratch_bytes(G, n_draw, tok))
+  if (scratch_bytes < ((ws && ws->world > 1) ? wide_private_bytes(n_draw, tok) : production_scratch_bytes(G, n_draw, tok)))
     return set_error("mcz_forward_production: scratch too small");
   p.meas = meas; p.err = err; p.G = G; p.N = (int)n_draw; p.Npad = pl.Npad; p.scap = pl.scap; p.tok = tok; p.dust = dust;
   p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32); p.goff = galaxy_offset;
@@ -977,7 +981,7 @@ int launch_production(const float* meas, const float* err, long long G, long lon
     p.pct[0] = pct; p.nvalid[0] = nvalid; p.status[0] = status;
   }
   p.trips = trips; p.ret = ret; p.Z = Z;
-  if (use_wide(G, n_draw, Z)) return launch_wide(p, scratch, stream);
+  if ((ws && ws->world > 1) || use_wide(G, n_draw, Z)) return launch_wide(p, scratch, stream, ws);
   p.counter = reinterpret_cast<unsigned long long*>(scratch);
   p.gscratch = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(scratch) + 256);
   p.gscratch_per_block = pl.per_block_floats;
@@ -1051,18 +1055,42 @@ wide_kernel(const __grid_constant__ ProdParams p) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nb = gridDim.x, b = blockIdx.x;
   const int N = p.N, Npad = p.Npad, ngroups = Npad / 128;
-  // this block's slice: whole 128-sample groups
-  const int g_lo = (int)((long long)ngroups * b / nb), g_hi = (int)((long long)ngroups * (b + 1) / nb);
+  // this rank's share of the 128-sample groups, and this block's slice of it
+  const int rg_lo = (int)((long long)ngroups * p.wrank / p.wworld), rg_hi = (int)((long long)ngroups * (p.wrank + 1) / p.wworld);
+  const int g_lo = rg_lo + (int)((long long)(rg_hi - rg_lo) * b / nb), g_hi = rg_lo + (int)((long long)(rg_hi - rg_lo) * (b + 1) / nb);
   const int s_lo = g_lo * 128, s_hi = g_hi * 128;
   unsigned* hist = reinterpret_cast<unsigned*>(smem) + (size_t)warp * FB;
 
+  // shared part (this rank's copy; every rank's copy receives every rank's atomics)
+  const int W = p.wworld, R = p.wrank;
+  unsigned char* shl = reinterpret_cast<unsigned char*>(p.wshared[R]);
+  WideCtl* ctl = reinterpret_cast<WideCtl*>(shl);
+  unsigned* ghist = reinterpret_cast<unsigned*>(shl + 4096);             // [4 rounds][nstore][6 targets][256]
+  const size_t ghist_bytes = (size_t)4 * p.nstore * 6 * 256 * sizeof(unsigned);
+  unsigned* xbar = reinterpret_cast<unsigned*>(shl + 4096 + ghist_bytes);   // cross-rank barrier counter
+  auto peer = [&](void* local, int q) -> void* {
+    return reinterpret_cast<unsigned char*>(p.wshared[q]) + (reinterpret_cast<unsigned char*>(local) - shl);
+  };
+  unsigned xepoch = 0;
+  // grid barrier; with several ranks also a barrier across them (every rank's atomics have landed)
+  auto xsync = [&]() {
+    if (W > 1) __threadfence_system();
+    grid.sync();
+    if (W > 1) {
+      ++xepoch;
+      if (b == 0 && tid == 0) {
+        for (int q = 0; q < W; ++q) atomicAdd_system(reinterpret_cast<unsigned*>(peer(xbar, q)), 1u);
+        while (*reinterpret_cast<volatile unsigned*>(xbar) < xepoch * (unsigned)W) { }
+        __threadfence_system();
+      }
+      grid.sync();
+    }
+  };
   unsigned char* base = reinterpret_cast<unsigned char*>(p.gscratch);
-  WideCtl* ctl = reinterpret_cast<WideCtl*>(base);
-  float* vals = reinterpret_cast<float*>(base + 4096);
+  float* vals = reinterpret_cast<float*>(base);
   float* st0 = vals + (long long)p.nstore * Npad;
   float* st1 = st0 + Npad; float* st2 = st1 + Npad; float* st3 = st2 + Npad;
   float* F = st3 + Npad;                                   // fields 0..5: Z1, Z2, lq1, lq2, lq1a, lq2a
-  unsigned* ghist = reinterpret_cast<unsigned*>(F + 6ll * Npad);     // [4 rounds][nstore][6 targets][256]
   const int used2line[NUSED] = {L_HA, L_HB, L_O2, L_O3, L_N2, L_S2A, L_S2B, L_S39069};
 
   for (long long g = 0; g < p.G; ++g) {
@@ -1071,7 +1099,7 @@ wide_kernel(const __grid_constant__ ProdParams p) {
       for (int i = tid; i < (int)(sizeof(WideCtl) / 4); i += PT) reinterpret_cast<unsigned*>(ctl)[i] = 0u;
     }
     for (long long i = (long long)b * PT + tid; i < 4ll * p.nstore * 6 * 256; i += (long long)nb * PT) ghist[i] = 0u;
-    grid.sync();
+    xsync();
     float lm[NUSED], le[NUSED];
     uint32_t assumed = 0u;
 #pragma unroll
@@ -1117,16 +1145,17 @@ wide_kernel(const __grid_constant__ ProdParams p) {
         }
       }
       seen = __reduce_or_sync(0xffffffffu, seen);
-      if (lane == 0 && seen) atomicOr(&ctl->flags, seen);
-      grid.sync();
+      if (lane == 0 && seen)
+        for (int q = 0; q < W; ++q) atomicOr_system(reinterpret_cast<unsigned*>(peer(&ctl->flags, q)), seen);
+      xsync();
       const uint32_t all = *reinterpret_cast<volatile unsigned*>(&ctl->flags);
       const uint32_t actual = all & F_ALL;
       anykd = (all & SEEN_KD) != 0u;
       if (actual == flags) break;
       flags = actual;
-      grid.sync();                                   // everyone has read the flags of the discarded pass
+      xsync();                                       // everyone has read the flags of the discarded pass
       if (b == 0 && tid == 0) ctl->flags = actual;
-      grid.sync();
+      xsync();
     }
     const uint64_t pm = present_mask(flags, p.tok);
     const bool ok = minimum_ok(flags);
@@ -1161,14 +1190,17 @@ wide_kernel(const __grid_constant__ ProdParams p) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const int q = __reduce_add_sync(0xffffffffu, __float2int_rn(sm4[k] * 65536.0f));
-          if (lane == 0 && q) atomicAdd(reinterpret_cast<unsigned long long*>(&ctl->sums[ph][k]), (unsigned long long)(long long)q);
+          if (lane == 0 && q)
+            for (int r = 0; r < W; ++r)
+              atomicAdd_system(reinterpret_cast<unsigned long long*>(peer(&ctl->sums[ph][k], r)), (unsigned long long)(long long)q);
         }
         nanb = __reduce_or_sync(0xffffffffu, nanb);
-        if (lane == 0 && nanb) atomicOr(&ctl->nan[ph], nanb);
+        if (lane == 0 && nanb)
+          for (int r = 0; r < W; ++r) atomicOr_system(reinterpret_cast<unsigned*>(peer(&ctl->nan[ph], r)), nanb);
         const int nx = ph == 2 ? 0 : ph + 1;
         if (b == 0 && tid < 4) ctl->sums[nx][tid] = 0;
         if (b == 0 && tid == 4) ctl->nan[nx] = 0u;
-        grid.sync();
+        xsync();
 #pragma unroll
         for (int k = 0; k < 4; ++k) t4[k] = *reinterpret_cast<volatile long long*>(&ctl->sums[ph][k]);
         nb = *reinterpret_cast<volatile unsigned*>(&ctl->nan[ph]);
@@ -1370,15 +1402,17 @@ wide_kernel(const __grid_constant__ ProdParams p) {
         unsigned* gh = ghist + (((long long)round * p.nstore + sl) * 6) * 256;
         for (int i = lane; i < nu * 256; i += 32) {
           const unsigned c = rh[i];
-          if (c) atomicAdd(gh + i, c);
+          if (c)
+            for (int r = 0; r < W; ++r) atomicAdd_system(reinterpret_cast<unsigned*>(peer(gh + i, r)), c);
         }
         if (round == 0) {
           const double tot = warp_sum((double)sum);
-          if (lane == 0) atomicAdd(&ctl->colsum[sl], tot);
+          if (lane == 0)
+            for (int r = 0; r < W; ++r) atomicAdd_system(reinterpret_cast<double*>(peer(&ctl->colsum[sl], r)), tot);
         }
         __syncwarp();
       }
-      grid.sync();
+      xsync();
 #pragma unroll 1
       for (int h = 0; h < 2; ++h) {
         if (!live[h]) continue;
@@ -1477,9 +1511,22 @@ wide_kernel(const __grid_constant__ ProdParams p) {
 }
 
 
+static size_t wide_shared_bytes_n(int nstore) {
+  return 4096 + (size_t)4 * nstore * 6 * 256 * sizeof(unsigned) + 256;
+}
 static size_t wide_scratch_bytes(long long N, int nstore) {
   const long long Npad = (N + 127) / 128 * 128;
-  return 4096 + (size_t)((long long)nstore + 4 + 6) * Npad * sizeof(float) + (size_t)4 * nstore * 6 * 256 * sizeof(unsigned);
+  return wide_shared_bytes_n(nstore) + (size_t)((long long)nstore + 4 + 6) * Npad * sizeof(float);
+}
+size_t wide_private_bytes(long long N, uint32_t tok) {
+  ProdParams p;
+  build_slots(tok, p);
+  return wide_scratch_bytes(N, p.nstore);
+}
+size_t wide_shared_bytes(uint32_t tok) {
+  ProdParams p;
+  build_slots(tok, p);
+  return wide_shared_bytes_n(p.nstore);
 }
 
 // Few galaxies with very many samples each (single-object runs): the cooperative wide kernel.
@@ -1492,10 +1539,28 @@ static bool use_wide(long long G, long long N, const float* Z) {
   return G <= 8 && N >= 32768;
 }
 
-static int launch_wide(ProdParams& p, void* scratch, cudaStream_t stream) {
+static int launch_wide(ProdParams& p, void* scratch, cudaStream_t stream, const WideShare* ws) {
   p.Npad = (int)((p.N + 127ll) / 128 * 128);
   finish_slots(p);
-  p.gscratch = reinterpret_cast<float*>(scratch);
+  const size_t shb = wide_shared_bytes_n(p.nstore);
+  if (ws && ws->world > 1) {
+    if (ws->world > MAX_DST || ws->rank < 0 || ws->rank >= ws->world) return set_error("wide kernel: bad rank / world");
+    if (p.Z) return set_error("wide kernel: per-sample output is not available when one object is sharded over GPUs");
+    p.wworld = ws->world; p.wrank = ws->rank;
+    for (int q = 0; q < ws->world; ++q) {
+      if (!ws->shared[q]) return set_error("wide kernel: null shared region");
+      p.wshared[q] = ws->shared[q];
+    }
+    p.gscratch = reinterpret_cast<float*>(scratch);
+    // the cross-rank barrier counter starts at 0 (the caller makes sure every rank has done this
+    // before any rank launches: one host-side barrier)
+  } else {
+    p.wworld = 1; p.wrank = 0;
+    p.wshared[0] = scratch;
+    p.gscratch = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(scratch) + shb);
+    const int rc = check_cuda(cudaMemsetAsync(reinterpret_cast<unsigned char*>(scratch) + shb - 256, 0, 256, stream), "barrier memset");
+    if (rc) return rc;
+  }
   const size_t smem = (size_t)PW * FineHist<false>::BYTES;
   static int max_blocks = 0;
   if (!max_blocks) {
@@ -1509,7 +1574,8 @@ static int launch_wide(ProdParams& p, void* scratch, cudaStream_t stream) {
   }
   int grid = max_blocks < num_sms() ? max_blocks : num_sms();
   const int ngroups = p.Npad / 128;
-  if (grid > ngroups) grid = ngroups;
+  const int mine = (int)((long long)ngroups * (p.wrank + 1) / p.wworld - (long long)ngroups * p.wrank / p.wworld);
+  if (grid > mine) grid = mine > 0 ? mine : 1;
   void* args[] = {&p};
   const int rc = check_cuda(cudaLaunchCooperativeKernel((void*)wide_kernel, dim3(grid), dim3(PT), args, smem, stream),
                             "wide_kernel launch");

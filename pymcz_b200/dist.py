@@ -93,6 +93,54 @@ class GatheredTables:
         td.all_reduce(self._flag, group=self.group)
 
 
+def production_table_sample_sharded(meas, err, n_draw, tokens, dust, seed, correlated=False, group=None,
+                                    device=None):
+    """Single-object runs: the samples of every galaxy sharded over the ranks.
+
+    Every rank passes the same small table; rank r evaluates samples [N' r / W, N' (r+1) / W) of each
+    galaxy and the reductions over the whole sample vector (has* flags, KK04 loop means per trip,
+    order statistics) go through NVLink inside the kernel.  Returns the same dict of host arrays as
+    production_table (without Z) on every rank; results do not depend on the number of ranks."""
+    import ctypes
+    import torch.distributed._symmetric_memory as symm
+    from . import _lib
+    from ._scales import NKEYS
+    L = _lib.lib()
+    group = group if group is not None else td.group.WORLD
+    world, r = td.get_world_size(group), td.get_rank(group)
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    meas = torch.from_numpy(np.ascontiguousarray(meas, dtype=np.float32)).to(device)
+    err = torch.from_numpy(np.ascontiguousarray(err, dtype=np.float32)).to(device)
+    G = int(meas.shape[0])
+    shared = symm.empty(int(L.mcz_samples_shared_bytes(int(tokens))), dtype=torch.uint8, device=device)
+    shared.zero_()
+    handle = symm.rendezvous(shared, group)
+    ptrs = (ctypes.c_void_p * world)(*[int(p) for p in handle.buffer_ptrs])
+    scratch = torch.empty(int(L.mcz_samples_scratch_bytes(int(n_draw), int(tokens))), dtype=torch.uint8, device=device)
+    pct = torch.empty((G, NKEYS, 3), dtype=torch.float32, device=device)
+    nvalid = torch.empty((G, NKEYS), dtype=torch.int32, device=device)
+    status = torch.empty((G, NKEYS), dtype=torch.int8, device=device)
+    trips = torch.empty((G, 2), dtype=torch.int32, device=device)
+    ret = torch.empty((G,), dtype=torch.int32, device=device)
+    torch.cuda.synchronize(device)
+    td.barrier(group)                       # every rank's shared region is zeroed before any kernel starts
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    with torch.cuda.device(device):
+        rc = L.mcz_forward_production_samples(
+            meas.data_ptr(), err.data_ptr(), G, int(n_draw), int(tokens), int(dust), int(seed), 0,
+            1 if correlated else 0, 0, world, r, ptrs, pct.data_ptr(), nvalid.data_ptr(), status.data_ptr(),
+            trips.data_ptr(), ret.data_ptr(), scratch.data_ptr(), scratch.numel(),
+            torch.cuda.current_stream(device).cuda_stream)
+        _lib.check(rc, "mcz_forward_production_samples")
+    ev1.record()
+    torch.cuda.synchronize(device)
+    td.barrier(group)
+    return dict(pct=pct.cpu().numpy(), nvalid=nvalid.cpu().numpy(), status=status.cpu().numpy(),
+                trips=trips.cpu().numpy(), ret=ret.cpu().numpy(), Z=None, kernel_ms=ev0.elapsed_time(ev1))
+
+
 def production_table(meas, err, n_draw, tokens, dust, seed, correlated=False, deterministic=False,
                      return_samples=False, device=None):
     """Run the fused production kernel over a whole host table, sharded over the ranks of the
