@@ -1375,10 +1375,15 @@ wide_kernel(const __grid_constant__ ProdParams p) {
 #pragma unroll
         for (int t = 0; t < 6; ++t)
           if (nu == 0 || tpre[h][t] != uq[nu - 1 < 0 ? 0 : nu - 1]) { uq[nu] = tpre[h][t]; ++nu; }
+        float sum = 0.0f;
+        unsigned* gh = ghist + (((long long)round * p.nstore + sl) * 6) * 256;
+        // (16-bit counters: the slice is taken 480 groups = 61440 samples at a time)
+#pragma unroll 1
+        for (int gc = g_lo; gc < g_hi; gc += 480) {
+        const int gce = gc + 480 < g_hi ? gc + 480 : g_hi;
         for (int i = lane; i < 6 * 128; i += 32) hist[i] = 0u;
         __syncwarp();
-        float sum = 0.0f;
-        for (int g0 = g_lo; g0 < g_hi; ++g0) {
+        for (int g0 = gc; g0 < gce; ++g0) {
           const float4 x4 = *reinterpret_cast<const float4*>(col + 4 * lane + 128 * g0);
           const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
@@ -1399,11 +1404,12 @@ wide_kernel(const __grid_constant__ ProdParams p) {
           }
         }
         __syncwarp();
-        unsigned* gh = ghist + (((long long)round * p.nstore + sl) * 6) * 256;
         for (int i = lane; i < nu * 256; i += 32) {
           const unsigned c = rh[i];
           if (c)
             for (int r = 0; r < W; ++r) atomicAdd_system(reinterpret_cast<unsigned*>(peer(gh + i, r)), c);
+        }
+        __syncwarp();
         }
         if (round == 0) {
           const double tot = warp_sum((double)sum);
@@ -1534,7 +1540,6 @@ static bool use_wide(long long G, long long N, const float* Z) {
   const char* force = getenv("MCZ_WIDE");              // "1": always (tests), "0": never
   (void)Z;
   if (force && force[0] == '0') return false;
-  if ((N + 127) / 128 * 128 / num_sms() >= 65536) return false;      // 16-bit slice histograms
   if (force && force[0] == '1') return true;
   return G <= 8 && N >= 32768;
 }
