@@ -148,7 +148,8 @@ int mcz_forward_production_gather(const float* meas_d, const float* err_d, long 
  * mcz_samples_shared_bytes(tokens) bytes as mapped into this process (NVLink peer mapping; q = rank is
  * the local one).  The caller zeroes its region, synchronises, and makes sure every rank has done so
  * (one host-side barrier) before any rank calls this; all ranks must call it together.
- * nranks = 1 is the single-GPU form (mcz_forward_production picks it by itself for G <= 8, N' >= 32768).
+ * nranks = 1 is the single-GPU form (mcz_forward_production picks it by itself for few galaxies with
+ * N' >= 32768 samples each).
  */
 size_t mcz_samples_shared_bytes(unsigned tokens);
 size_t mcz_samples_scratch_bytes(long long n_draw, unsigned tokens);   /* private scratch_d of each rank */
