@@ -211,7 +211,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
   constexpr size_t HIST_BYTES = FineHist<PACK16>::BYTES;
   float* vals;              // columns [nstore][Npad]
   float* st0; float* st1; float* st2; float* st3;   // four per-sample scratch arrays (phase-A carry, then R23 constants)
-  float* giter = nullptr;   // global variant: loop state [16][Npad]
+  float* giter = nullptr;   // global variant: loop state, fields 10..15 of [..][Npad]
   float* sstate = nullptr;  // global variant: Z1, Z2, logq1, logq2 of the first p.scap samples, in shared memory
   unsigned char* work;      // selection scratch: PW histograms, then PW candidate areas
   if (GLOBAL) {
@@ -552,7 +552,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
         // bandwidth.  The four values that change every trip (Z1, Z2, logq1, logq2 = fields 10..13)
         // live in shared memory for the first p.scap samples (a multiple of the block size, so
         // each pass of the sample loop is on one side), in the global scratch beyond.
-        float* F = giter;
+        float* F = giter - 10ll * Npad;          // only fields 10..15 exist (the constants are recomputed)
         const int scap = p.scap;
 #define LST(k, s) (*((s) < scap ? sstate + ((k) - 10) * scap + (s) : F + (long long)(k) * Npad + (s)))
         auto consts = [&](int s, IterState<float>& st) {
@@ -887,7 +887,7 @@ static ProdPlan make_plan(long long G, long long N, int nstore) {
     const long long need = (N + PT - 1) / PT * PT;
     pl.scap = (int)(fit < need ? fit : need);
     pl.smem = base + (size_t)pl.scap * 16;
-    pl.per_block_floats = ((long long)nstore + 4 + 16) * pl.Npad;
+    pl.per_block_floats = ((long long)nstore + 4 + 6) * pl.Npad;
   }
   const long long sms = num_sms();
   pl.grid = (int)(G < sms ? (G > 0 ? G : 1) : sms);
