@@ -160,6 +160,16 @@ def production_table(meas, err, n_draw, tokens, dust, seed, correlated=False, de
     world, r = world_size(), rank()
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device())
+    if (world > 1 and G < world and n_draw >= 262144 and not return_samples and not deterministic
+            and td.get_backend() == "nccl"):
+        # single-object run: fewer galaxies than GPUs, very many samples each -> shard the samples
+        try:
+            out = production_table_sample_sharded(meas, err, n_draw, tokens, dust, seed, correlated=correlated,
+                                                  device=device)
+            out.pop("kernel_ms", None)
+            return out
+        except (ImportError, AttributeError):
+            pass                        # no symmetric memory in this torch: galaxy shards below
     lo, hi = shard_bounds(G, world, r)
     m = torch.from_numpy(meas[lo:hi]).to(device)
     e = torch.from_numpy(err[lo:hi]).to(device)
