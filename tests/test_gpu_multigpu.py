@@ -29,7 +29,7 @@ def test_sample_sharded_single_object_run():
     """One object's samples over two GPUs (reductions inside the kernel over NVLink) == one GPU."""
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
            "--master-addr", "127.0.0.1", "--master-port", "29542",
-           os.path.join(ROOT, "tests", "multigpu", "check_sample_sharded.py"), "150001"]
+           os.path.join(ROOT, "tests", "multigpu", "check_sample_sharded.py"), "300001"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "== single GPU: True" in out.stdout
