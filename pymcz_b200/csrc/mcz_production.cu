@@ -304,8 +304,8 @@ production_kernel(const __grid_constant__ ProdParams p) {
 #pragma unroll
           for (int u = 0; u < NUSED; ++u) {
             float v = fmaf(le[u], p.correlated ? z[5] : z[5 + u], lm[u]);          // mcz.py:442 / :589
-            if (!finite_f(v)) v = 0.0f;                                            // metallicity.py:96
-            if (v < 0.0f) v = 0.0f;                                                // metallicity.py:99
+            v = fmaxf(v, 0.0f);                       // NaN -> 0 and negative -> 0 (metallicity.py:96, 99)
+            if (!(v <= FLT_MAX)) v = 0.0f;            // +inf -> 0 (metallicity.py:96)
             f[u] = v;
             const bool pos = (u >= U_S2B) ? (v > 1e-9f) : (v > 0.0f);
             if (pos) seen |= 1u << u;
@@ -1126,8 +1126,8 @@ wide_kernel(const __grid_constant__ ProdParams p) {
 #pragma unroll
           for (int u = 0; u < NUSED; ++u) {
             float v = fmaf(le[u], p.correlated ? z[5] : z[5 + u], lm[u]);
-            if (!finite_f(v)) v = 0.0f;
-            if (v < 0.0f) v = 0.0f;
+            v = fmaxf(v, 0.0f);
+            if (!(v <= FLT_MAX)) v = 0.0f;
             f[u] = v;
             const bool pos = (u >= U_S2B) ? (v > 1e-9f) : (v > 0.0f);
             if (pos) seen |= 1u << u;
