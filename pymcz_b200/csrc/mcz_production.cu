@@ -1029,20 +1029,18 @@ int launch_production(const float* meas, const float* err, long long G, long lon
 // set goes through global memory and grid-wide barriers:
 //   A  has* flags: atomicOr;
 //   B  the two KK04 means per trip: fixed-point 64-bit atomics, one grid barrier per two trips;
-//   D  per-slice histograms merged with global atomics, the plan made redundantly by every block
-//      from the merged histogram, candidates appended to a global list, one block finishes.
+//   D  an MSB radix select on the order-preserving bit patterns of the floats, 8 bits per round, for
+//      the six ranks at once: per-slice histograms (shared memory) merged into a global table, the
+//      ranks located redundantly by every block after the barrier; four rounds give exact values.
 // Per-sample results are identical to the per-galaxy kernels (same Philox indexing, same device
-// functions); columns whose target ranges are crowded fall back to warp_percentiles() by one warp
-// over the whole column.
+// functions).  With p.wworld > 1 the samples of the galaxy are also sharded over the GPUs of the
+// node: every atomic goes to every rank's copy of the control block / radix tables (NVLink peer
+// mappings) and each grid barrier is followed by a counter barrier across the ranks.
 struct WideCtl {
   unsigned flags;                 // line flags | SEEN_KD
   unsigned nan[3];                // NaN bits of the KK04 sums, rotating with sums[]
   long long sums[3][4];           // 16.16 fixed point
-  long long divsum;
-  unsigned ccount[NKEYS];         // per slot: candidates appended
-  unsigned ntie[NKEYS];           // per slot: copies of the repeated value
-  unsigned slow[NKEYS];           // per slot: needs the one-warp fallback
-  double colsum[NKEYS];
+  double colsum[NKEYS];           // per slot: sum of the finite values (sum <= 0 test, mcz.py:282-285)
 };
 static_assert(sizeof(WideCtl) <= 4096, "wide control block too large");
 
