@@ -249,20 +249,31 @@ template <typename R> struct Carry {
   uint32_t aux;
 };
 
-// Build the loop constants from the carry; kd = this sample's KD02_N2O2 (NaN when absent).
-template <typename R> MCZ_HD void make_iter(const Carry<R>& c, R kd, IterState<R>& st) {
-  typedef Math<R> M;
-  const R y = c.y, y2 = c.y * c.y, n = c.n2ha, x = c.x;
-  st.num0 = R(32.81) - R(1.153) * y2;                                     // metscales.py:464-465
+// The loop constants in three groups, for callers that recompute them per batch and need only the
+// groups of the loops still running (same expressions as make_iter below, which calls them).
+template <typename R> MCZ_HD void iter_logq(R y, IterState<R>& st) {       // calclogq, metscales.py:464-465
+  const R y2 = y * y;
+  st.num0 = R(32.81) - R(1.153) * y2;
   st.num1 = R(-3.396) - R(0.025) * y + R(0.1444) * y2;
   st.den0 = R(4.603) - R(0.3119) * y - R(0.163) * y2;
   st.den1 = R(-0.48) + R(0.0271) * y + R(0.02037) * y2;
-  st.A = poly3<R>(n, 7.04, 5.28, 6.28, 2.37);                             // metscales.py:1114-1116
-  st.B = poly3<R>(n, -2.44, -2.01, -0.325, 0.128) - M::exp10(n - R(0.2)) * (R(-3.16) + R(4.65) * n);
-  st.U0 = poly4<R>(x, 9.72, -0.777, -0.951, -0.072, -0.811);              // metscales.py:1172-1176
+}
+template <typename R> MCZ_HD void iter_n2ha(R n, IterState<R>& st) {       // metscales.py:1114-1116
+  st.A = poly3<R>(n, 7.04, 5.28, 6.28, 2.37);
+  st.B = poly3<R>(n, -2.44, -2.01, -0.325, 0.128) - Math<R>::exp10(n - R(0.2)) * (R(-3.16) + R(4.65) * n);
+}
+template <typename R> MCZ_HD void iter_r23(R x, IterState<R>& st) {        // metscales.py:1172-1176
+  st.U0 = poly4<R>(x, 9.72, -0.777, -0.951, -0.072, -0.811);
   st.U1 = poly4<R>(x, 0.0737, -0.0713, -0.141, 0.0373, -0.058);
   st.L0 = poly2<R>(x, 9.40, 4.65, -3.17);
   st.L1 = poly2<R>(x, 0.272, 0.547, -0.513);
+}
+
+// Build the loop constants from the carry; kd = this sample's KD02_N2O2 (NaN when absent).
+template <typename R> MCZ_HD void make_iter(const Carry<R>& c, R kd, IterState<R>& st) {
+  iter_logq<R>(c.y, st);
+  iter_n2ha<R>(c.n2ha, st);
+  iter_r23<R>(c.x, st);
   const uint32_t zi = c.aux & AUX_ZI_MASK;
   st.Z1 = kd;        // the kernel overrides with 8.6 when KD02_N2O2 is absent / all-NaN (:1099-1103)
   st.Z2 = zi == 0u ? R(8.2) : (zi == 1u ? R(8.4) : R(8.7));               // metscales.py:1156

@@ -589,8 +589,10 @@ production_kernel(const __grid_constant__ ProdParams p) {
           unsigned nanb = 0u;
 #pragma unroll 2
           for (int s = tid; s < N; s += PT) {
-            IterState<float> k;
-            consts(s, k);
+            IterState<float> k;                       // only the constants of the loops still running
+            iter_logq<float>(st0[s], k);
+            if (act1) iter_n2ha<float>(st1[s], k);
+            if (act2) { iter_r23<float>(st2[s], k); k.aux = __float_as_uint(st3[s]); }
             const float num0 = k.num0, num1 = k.num1, den0 = k.den0, den1 = k.den1;
             if (act1) {
               const float cA = k.A, cB = k.B;
@@ -1208,8 +1210,10 @@ wide_kernel(const __grid_constant__ ProdParams p) {
         float sm4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
         unsigned nanb = 0u;
         for (int s = s_lo + tid; s < s_hi && s < N; s += PT) {
-          IterState<float> k;
-          consts(s, k);
+          IterState<float> k;                         // only the constants of the loops still running
+          iter_logq<float>(st0[s], k);
+          if (act1) iter_n2ha<float>(st1[s], k);
+          if (act2) { iter_r23<float>(st2[s], k); k.aux = __float_as_uint(st3[s]); }
           const float num0 = k.num0, num1 = k.num1, den0 = k.den0, den1 = k.den1;
           if (act1) {
             const float Z1 = F[0ll * Npad + s], lq1 = F[2ll * Npad + s];
