@@ -2,19 +2,27 @@
 """Benchmark of the pyMCZ Monte-Carlo metallicity hot path on B200.
 
     python bench.py --gpus N --steps K --warmup W            # our CUDA arm
-    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU code
 
 Metric (BASELINE.json): galaxy-samples/s, all scales (--md all), dust-corrected.
-Workload: BASELINE config 4 -- the synthetic 10^6 HII-region table x nsample=2000 (N'=2200) of
-SURVEY.md section 8(d), sharded over galaxies.  Scaling is WEAK: every GPU gets 125 000 galaxies
-(at 8 GPUs that is the full 10^6 table), so N=1 runs the first 1/8 of the table.
 
-A "step" is one pass of the hot path over the rank's shard: one fused kernel launch from
-device-resident meas/err tables to device-resident percentile tables; for N>1 the gather of the
-per-rank tables is part of the step and is fused into the kernel (every rank's kernel writes its
+Workloads (BASELINE.json `configs`), chosen with --config:
+  4 (default)  synthetic 10^6 HII-region table x nsample=2000 (N'=2200), --md all
+  3            synthetic 10^4 galaxies x nsample=10^4 (N'=11000), --md all
+  5            KD02comb-only stress: 10^5 galaxies x nsample=10^4 (N'=11000), --md KD02
+Scaling is STRONG by default: the configuration's whole table at every N, sharded over galaxies
+(N=1 runs the full 10^6 x 2200 table on one GPU).  --scaling weak gives every GPU 1/8 of the table.
+
+A "step" is one pass of the hot path over the whole table: on every rank one fused kernel launch
+from device-resident meas/err shards to device-resident percentile tables, plus, for N>1, the
+gather of the per-rank tables, which is fused into the kernel (every rank's kernel writes its
 result rows into all ranks' full tables over NVLink; --gather nccl uses NCCL all-gathers instead).
-`e2e` is the same step through the C-ABI host-buffer entry point (mcz_ctx_run_host): pinned host
-tables in, H2D, kernel, D2H, host tables out.
+`e2e` is the same step through pymcz_b200.dist.production_table -- the call mcz.run makes -- with
+HOST tables in and out: pinned upload, kernel(s), gather, pinned download of the full tables on
+every rank (on one GPU this is the C ABI's mcz_ctx_run_host).
+At N>1 the run also VERIFIES the exchange: the gathered tables must equal an NCCL all-gather of
+the ranks' local tables bit for bit, and a single-object run with its samples sharded over the
+ranks must reproduce the one-GPU result bit for bit.
 """
 import argparse
 import json
@@ -28,10 +36,18 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-GALAXIES_PER_GPU = 125_000
-NSAMPLE = 2000
 METRIC = "galaxy-samples/sec (all scales, dust-corrected)"
 UNIT = "galaxy-samples/s"
+
+CONFIGS = {
+    3: dict(G=10_000, nsample=10_000, md="all",
+            name="BASELINE config 3: synthetic 10^4 galaxies x nsample=10^4 (N'=11000), all 11 lines, --md all, dust on"),
+    4: dict(G=1_000_000, nsample=2_000, md="all",
+            name="BASELINE config 4: synthetic 10^6 HII-region table (SURVEY 8d generator, seed 1004) x nsample=2000 "
+                 "(N'=2200), --md all, dust on"),
+    5: dict(G=100_000, nsample=10_000, md="KD02",
+            name="BASELINE config 5: KD02comb-only stress, synthetic 10^5 galaxies x nsample=10^4 (N'=11000), --md KD02, dust on"),
+}
 
 
 def n_draw(nsample):
@@ -39,25 +55,36 @@ def n_draw(nsample):
 
 
 # ---------------------------------------------------------------------------------------------
-# reference arm / cpu_baseline: the oracle port of the reference algorithm on host cores
+# reference arm / cpu_baseline: the reference's own modules (oracle/_ref) on host cores
 # ---------------------------------------------------------------------------------------------
+def _ref_kind():
+    from oracle import ref_harness
+    return "reference" if ref_harness.available() else "port"
+
+
 def _cpu_worker(args):
-    """One galaxy, as the reference's Pool worker calc() does (mcz.py:432-454): correlated
-    perturbation, metallicity.calculation with the per-sample np.roots loop, percentiles."""
-    meas_row, err_row, nsample, seed = args
-    from oracle import mcz_oracle as orc
+    """One measurement, as the reference's Pool worker calc() does (mcz.py:432-454): correlated
+    perturbation, metallicity.calculation with the per-sample np.roots loops, savehist statistics.
+    Runs the UNMODIFIED reference modules staged in oracle/_ref when present, else the oracle port."""
+    meas_row, err_row, nsample, md, seed, kind = args
     rs = np.random.RandomState(seed)
-    out = orc.run_table(meas_row[None], err_row[None], nsample, mds="all", dust_corr=True,
+    if kind == "reference":
+        from oracle import ref_harness
+        _, ret, table = ref_harness.run_measurement(meas_row, err_row, nsample, mds=md, dust_corr=True, rs=rs)
+        return len(table)
+    from oracle import mcz_oracle as orc
+    out = orc.run_table(meas_row[None], err_row[None], nsample, mds=md, dust_corr=True,
                         mode="correlated", roots_mode="loop", rs=rs, normal=rs.normal)
     return float(np.nansum(out["pct"]))
 
 
-def cpu_reference_run(G, nsample, nps, pool=None, seed0=0):
-    """Time G galaxies over a Pool(nps) like the reference's --multiproc path (mcz.py:545-554)."""
+def cpu_reference_run(G, cfg, config, nps, pool=None, seed0=0, kind=None):
+    """Time G measurements over a Pool(nps) like the reference's --multiproc path (mcz.py:545-554)."""
     import multiprocessing as mp
     from pymcz_b200.synth import synthetic_table
-    meas, err = synthetic_table(max(G, 1), config=4)
-    jobs = [(meas[i], err[i], nsample, seed0 + i) for i in range(G)]
+    kind = kind or _ref_kind()
+    meas, err = synthetic_table(max(G, 1), config=config)
+    jobs = [(meas[i], err[i], cfg["nsample"], cfg["md"], seed0 + i, kind) for i in range(G)]
     own = pool is None
     if own and nps > 1:
         pool = mp.get_context("fork").Pool(nps)
@@ -71,11 +98,16 @@ def cpu_reference_run(G, nsample, nps, pool=None, seed0=0):
     if own and nps > 1:
         pool.close()
         pool.join()
-    return G * n_draw(nsample) / dt, dt
+    return G * n_draw(cfg["nsample"]) / dt, dt
 
 
 def reference_pool_size():
     return min((os.cpu_count() or 2) - 1 or 1, 10)       # mcz.py:48, 545
+
+
+def _ref_describe(kind):
+    return ("unmodified reference modules (oracle/_ref/pyMCZ: metallicity.calculation, metscales.diagnostics, "
+            "savehist statistics)" if kind == "reference" else "oracle port (oracle/mcz_oracle.py, per-sample np.roots loop)")
 
 
 def run_reference_arm(args):
@@ -83,29 +115,35 @@ def run_reference_arm(args):
     if rank != 0:
         return
     import multiprocessing as mp
+    cfg = CONFIGS[args.config]
+    kind = _ref_kind()
     nps = reference_pool_size()
-    G_step = 8 * nps
+    N = n_draw(cfg["nsample"])
+    # a bounded sample of the table per step: ~8 measurements per worker at N'=2200, fewer at 11000
+    per_worker = 8 if N <= 4096 else 2
+    G_step = per_worker * nps
     pool = mp.get_context("fork").Pool(nps) if nps > 1 else None
     for w in range(args.warmup):
-        cpu_reference_run(G_step, NSAMPLE, nps, pool, seed0=1000 * w)
+        cpu_reference_run(nps, cfg, args.config, nps, pool, seed0=1000 * w, kind=kind)
     t_tot = 0.0
     for k in range(args.steps):
-        _, dt = cpu_reference_run(G_step, NSAMPLE, nps, pool, seed0=7000 + 1000 * k)
+        _, dt = cpu_reference_run(G_step, cfg, args.config, nps, pool, seed0=7000 + 1000 * k, kind=kind)
         t_tot += dt
     if pool is not None:
         pool.close()
         pool.join()
-    value = args.steps * G_step * n_draw(NSAMPLE) / t_tot
-    sample = "%d galaxies x N'=%d per step, Pool(%d), per-sample np.roots loop" % (G_step, n_draw(NSAMPLE), nps)
+    value = args.steps * G_step * N / t_tot
+    sample = "%d measurements x N'=%d per step, Pool(%d) one measurement per task (mcz.py:545-554), %s" % (
+        G_step, N, nps, _ref_describe(kind))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / max(args.steps, 1),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "gpu_launches": 0,
-        "config": {"workload": "BASELINE config 4 shape (synthetic HII-region table, nsample=2000, N'=2200, "
-                               "--md all, dust on); bounded sample of %d galaxies per step" % G_step,
-                   "md": "all", "nsample": NSAMPLE, "n_draw": n_draw(NSAMPLE), "sampling": "correlated (mcz.py:442)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": nps, "kind": "port", "sample": sample},
+        "config": {"workload": cfg["name"] + "; bounded sample of %d measurements per step" % G_step,
+                   "config": args.config, "md": cfg["md"], "nsample": cfg["nsample"], "n_draw": N,
+                   "sampling": "correlated (the reference's --multiproc worker, mcz.py:442)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": nps, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -161,6 +199,33 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
+def _bits_equal(a, b):
+    """Bitwise equality of two tensors of the same dtype/shape (NaN payloads included)."""
+    import torch
+    if a.shape != b.shape or a.dtype != b.dtype:
+        return False
+    if a.dtype == torch.float32:
+        a, b = a.view(torch.int32), b.view(torch.int32)
+    return bool(torch.equal(a, b))
+
+
+def _profile_traffic(kernel_name, G, N, md):
+    """dram__bytes_read+write per launch from the committed ncu --set full capture of THIS kernel
+    on THIS launch shape (profiles/r2_*.json written by tools/ncu_summary.py); None if there is no
+    capture that matches -- the number is never rescaled from another shape."""
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r2_*.json"))):
+        try:
+            prof = json.load(open(path))
+        except Exception:
+            continue
+        if (prof.get("kernel_base") == kernel_name and prof.get("galaxies") == G and prof.get("n_draw") == N
+                and prof.get("md") == md and "dram_bytes_read" in prof):
+            return prof["dram_bytes_read"] + prof["dram_bytes_write"], {
+                "file": os.path.relpath(path, ROOT), "commit": prof.get("commit"), "galaxies": G, "n_draw": N}
+    return None, None
+
+
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
@@ -168,6 +233,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from pymcz_b200 import _lib, _scales as sc, ops
+    from pymcz_b200 import dist as mdist
     from pymcz_b200.synth import synthetic_table, shard_bounds
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -181,12 +247,16 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
 
-    G_total = args.galaxies_per_gpu * world
+    cfg = CONFIGS[args.config]
+    G_total = cfg["G"] if args.galaxies is None else args.galaxies
+    if args.scaling == "weak":
+        G_total = max(G_total // 8, 1) * world
     lo, hi = shard_bounds(G_total, world, rank)
-    meas_h, err_h = synthetic_table(G_total, config=4, start=lo, stop=hi)
+    full_m, full_e = synthetic_table(G_total, config=args.config)
+    meas_h, err_h = np.ascontiguousarray(full_m[lo:hi]), np.ascontiguousarray(full_e[lo:hi])
     G = hi - lo
-    N = n_draw(args.nsample)
-    tok = sc.T_ALL
+    N = n_draw(cfg["nsample"])
+    tok, _, _ = sc.parse_md(cfg["md"])
     meas = torch.from_numpy(meas_h).to(dev)
     err = torch.from_numpy(err_h).to(dev)
     ws = ops.ProductionWorkspace(G, N, tok, dev)
@@ -198,16 +268,17 @@ def run_ours(args):
     if world > 1:
         if args.gather == "fused":
             try:
-                from pymcz_b200.dist import GatheredTables
-                fused = GatheredTables(G_total, dev)
+                fused = mdist.GatheredTables(G_total, dev)
             except Exception as exc:        # no peer mappings on this box: measure the NCCL form and say so
                 sys.stderr.write("bench.py: fused gather unavailable (%s); using NCCL all-gathers\n" % (exc,))
-                args.gather = "nccl"
             ok = torch.tensor([1 if fused is not None else 0], device=dev)
             dist.all_reduce(ok, op=dist.ReduceOp.MIN)
             if not int(ok.item()):
                 fused, args.gather = None, "nccl"
         if fused is None:
+            counts = [shard_bounds(G_total, world, r)[1] - shard_bounds(G_total, world, r)[0] for r in range(world)]
+            if len(set(counts)) != 1:
+                raise SystemExit("bench.py --gather nccl needs a table that divides evenly over the ranks")
             gath = dict(pct=torch.empty((G_total, sc.NKEYS, 3), dtype=torch.float32, device=dev),
                         nvalid=torch.empty((G_total, sc.NKEYS), dtype=torch.int32, device=dev),
                         status=torch.empty((G_total, sc.NKEYS), dtype=torch.int8, device=dev))
@@ -260,46 +331,77 @@ def run_ours(args):
     k_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
     mean_trips = float(ws.trips.float().sum(dim=1).mean().item())
     # trips the kernel actually executed (a provably divergent N2Ha loop is cut short and reported
-    # with the reference's outcome of 100 trips): the roofline is credited with EXECUTED work only
+    # with the reference's outcome of 100 trips): the roofline is credited with EXECUTED work only.
+    # The statistics of the last launch live in the header of its scratch buffer.
     import ctypes
     tc = (ctypes.c_ulonglong * 4)()
-    L.mcz_debug_trip_counters.argtypes = [ctypes.c_void_p, ctypes.c_int]
-    L.mcz_debug_trip_counters(tc, 1)
-    ops.forward_production(meas, err, N, tok, sc.DUST_ON, seed=0xB200, galaxy_offset=lo, workspace=ws)
-    torch.cuda.synchronize()
-    L.mcz_debug_trip_counters(tc, 1)
+    _lib.check(L.mcz_production_last_stats(ws.scratch.data_ptr(), tc, torch.cuda.current_stream(dev).cuda_stream),
+               "mcz_production_last_stats")
     exec_trips = (tc[1] + tc[2]) / max(tc[0], 1)
     early_exits = int(tc[3])
 
-    # ---- e2e through the C-ABI host-buffer call (pinned host tables)
-    ctx = L.mcz_ctx_create(local_rank)
-    if not ctx:
-        raise SystemExit("mcz_ctx_create failed: " + L.mcz_last_error().decode())
-    hm = torch.from_numpy(meas_h).pin_memory()
-    he = torch.from_numpy(err_h).pin_memory()
-    hp = torch.empty((G, sc.NKEYS, 3), dtype=torch.float32).pin_memory()
-    hn = torch.empty((G, sc.NKEYS), dtype=torch.int32).pin_memory()
-    hs = torch.empty((G, sc.NKEYS), dtype=torch.int8).pin_memory()
-    ht = torch.empty((G, 2), dtype=torch.int32).pin_memory()
-    hr = torch.empty((G,), dtype=torch.int32).pin_memory()
+    # ---- verification of the exchange (N > 1): after timing, not timed
+    verified = {}
+    if world > 1:
+        counts = [shard_bounds(G_total, world, r)[1] - shard_bounds(G_total, world, r)[0] for r in range(world)]
+        if fused is not None:
+            # local tables of this rank (plain launch) -> NCCL all-gather -> must equal the tables the
+            # kernels wrote into each other's memory, bit for bit, on every rank
+            ops.forward_production(meas, err, N, tok, sc.DUST_ON, seed=0xB200, galaxy_offset=lo, workspace=ws)
+            ref = {k: mdist.all_gather_rows(getattr(ws, k), counts) for k in ("pct", "nvalid", "status")}
+            ops.forward_production(meas, err, N, tok, sc.DUST_ON, seed=0xB200, galaxy_offset=lo, workspace=ws, gather=fused)
+            fused.wait()
+            torch.cuda.synchronize()
+            okg = all(_bits_equal(getattr(fused, k)[:G_total], ref[k]) for k in ("pct", "nvalid", "status"))
+            flag = torch.tensor([1 if okg else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            verified["gather_verified"] = bool(int(flag.item()))
+            del ref
+        # single-object run, samples sharded over the ranks: every rank must end with
+        # the tables a one-GPU run of the same kernel produces (integer reductions: bit-identical)
+        try:
+            so_m, so_e = synthetic_table(3, config=4)
+            so_n = 400_000
+            sh = mdist.production_table_sample_sharded(so_m, so_e, so_n, sc.T_ALL, sc.DUST_ON, 0xB200, device=dev)
+            one = ops.forward_production(torch.from_numpy(so_m).to(dev), torch.from_numpy(so_e).to(dev), so_n,
+                                         sc.T_ALL, sc.DUST_ON, seed=0xB200)
+            torch.cuda.synchronize()
+            oks = (np.array_equal(sh["pct"].view(np.int32), one[0].cpu().numpy().view(np.int32)) and
+                   np.array_equal(sh["nvalid"], one[1].cpu().numpy()) and
+                   np.array_equal(sh["status"], one[2].cpu().numpy()) and
+                   np.array_equal(sh["trips"], one[3].cpu().numpy()))
+            flag = torch.tensor([1 if oks else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            verified["sample_sharded_verified"] = bool(int(flag.item()))
+            verified["sample_sharded_ms"] = sh["kernel_ms"]
+        except Exception as exc:
+            verified["sample_sharded_verified"] = False
+            verified["sample_sharded_error"] = repr(exc)[:200]
+
+    # ---- e2e: the call mcz.run makes (pymcz_b200.dist.production_table), pinned host tables in and out
+    hm = torch.from_numpy(full_m).pin_memory()
+    he = torch.from_numpy(full_e).pin_memory()
+    hm_np, he_np = hm.numpy(), he.numpy()
 
     def e2e_step():
-        rc = L.mcz_ctx_run_host(ctx, hm.data_ptr(), he.data_ptr(), G, N, tok, sc.DUST_ON, 0xB200, lo, 0, 0,
-                                hp.data_ptr(), hn.data_ptr(), hs.data_ptr(), ht.data_ptr(), hr.data_ptr())
-        if rc:
-            raise SystemExit("mcz_ctx_run_host: " + L.mcz_last_error().decode())
+        return mdist.production_table(hm_np, he_np, N, tok, sc.DUST_ON, 0xB200, copy=False)
 
     for _ in range(max(min(args.warmup, 3), 1)):
-        e2e_step()
+        out = e2e_step()
     barrier()
     e2e_n = max(min(args.steps, 10), 1)
     t0 = time.perf_counter()
     for _ in range(e2e_n):
-        e2e_step()
+        out = e2e_step()
+    barrier()
     e2e_s = time.perf_counter() - t0
-    L.mcz_ctx_destroy(ctx)
-    h2d = int(hm.numel() * 4 + he.numel() * 4)
-    d2h = int(hp.numel() * 4 + hn.numel() * 4 + hs.numel() + ht.numel() * 4 + hr.numel() * 4)
+    e2e_matches = True
+    if world == 1:      # the host-path tables are the device-path tables
+        e2e_matches = bool(np.array_equal(out["pct"].view(np.int32), ws.pct.cpu().numpy().view(np.int32)) and
+                           np.array_equal(out["nvalid"], ws.nvalid.cpu().numpy()))
+    h2d = int(meas_h.nbytes + err_h.nbytes)
+    d2h = int(sum(out[k].nbytes for k in ("pct", "nvalid", "status", "trips", "ret")))
+    mdist.release_host_paths()
 
     # max over ranks
     tt = torch.tensor([t_ms, e2e_s, k_ms], dtype=torch.float64, device=dev)
@@ -318,17 +420,13 @@ def run_ours(args):
             pass
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
         f_mhz = clocks.get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0
-        # definitional work per galaxy-sample, md=all: W_alu = 1120 + 35 T, W_sfu = 62 + T
-        w_alu, w_sfu = 1120.0 + 35.0 * exec_trips, 62.0 + exec_trips
-        w_alu_ref = 1120.0 + 35.0 * mean_trips
-        prof = {}
-        try:
-            prof = json.load(open(os.path.join(ROOT, "profiles", "r1_production_kernel.json")))
-        except Exception:
-            pass
-        traffic = None
-        if prof.get("galaxies"):
-            traffic = (prof["dram_bytes_read"] + prof["dram_bytes_write"]) / prof["galaxies"] * G
+        # definitional work per galaxy-sample:
+        #   md=all:  W_alu = 1120 + 35 T, W_sfu = 62 + T;   md=KD02:  W_alu = 520 + 35 T, W_sfu = 39 + T
+        base_alu, base_sfu = (1120.0, 62.0) if cfg["md"] == "all" else (520.0, 39.0)
+        w_alu, w_sfu = base_alu + 35.0 * exec_trips, base_sfu + exec_trips
+        w_alu_ref = base_alu + 35.0 * mean_trips
+        kernel_base = L.mcz_production_kernel_name(G, N, tok).decode()
+        traffic, traffic_src = _profile_traffic(kernel_base, G, N, cfg["md"])
         per_gpu_gs = (G * N) / (k_ms * 1e-3)
         peak_alu = sms * 128 * f_mhz * 1e6
         peak_sfu = sms * 16 * f_mhz * 1e6
@@ -338,10 +436,10 @@ def run_ours(args):
             "bound": "alu_issue",
             "achieved": per_gpu_gs * w_alu / 1e12, "peak": peak_alu / 1e12, "unit": "Tlane-op/s",
             "frac": per_gpu_gs * w_alu / peak_alu,
-            "traffic": traffic,
-            "traffic_note": "ncu dram__bytes_read+write of one launch over %s galaxies (profiles/), scaled per galaxy to "
-                            "this launch; the ~640 B/galaxy result tables stay in the 126 MB L2" % prof.get("galaxies"),
-            "kernel": "production_kernel<4>", "kernel_ms": k_ms,
+            "traffic": traffic, "traffic_source": traffic_src,
+            "traffic_note": ("ncu dram__bytes_read+write of one launch of this kernel on this launch shape"
+                             if traffic is not None else "no ncu --set full capture of this launch shape is committed"),
+            "kernel": kernel_base, "kernel_ms": k_ms,
             "mean_trips_reference": mean_trips, "mean_trips_executed": exec_trips, "early_exits_per_launch": early_exits,
             "frac_if_credited_with_reference_trips": per_gpu_gs * w_alu_ref / peak_alu,
             "w_alu_per_gs": w_alu, "w_sfu_per_gs": w_sfu, "sfu_frac": per_gpu_gs * w_sfu / peak_sfu,
@@ -356,22 +454,22 @@ def run_ours(args):
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             nps = reference_pool_size()
-            # size the sample for ~15 s from a one-galaxy probe
-            _, dt1 = cpu_reference_run(1, NSAMPLE, 1)
+            kind = _ref_kind()
+            # size the sample for ~15 s from a one-measurement probe
+            _, dt1 = cpu_reference_run(1, cfg, args.config, 1, kind=kind)
             Gc = int(max(nps, min(64 * nps, round(15.0 / max(dt1, 1e-3) * nps))))
-            v, dt = cpu_reference_run(Gc, NSAMPLE, nps)
-            cpu = {"value": v, "unit": UNIT, "cores": nps, "kind": "port",
-                   "sample": "%d galaxies x N'=%d of the same table, Pool(%d) one galaxy per task, correlated "
-                             "sampling, per-sample np.roots loop as the reference (%.1f s)" % (Gc, n_draw(NSAMPLE), nps, dt)}
+            v, dt = cpu_reference_run(Gc, cfg, args.config, nps, kind=kind)
+            cpu = {"value": v, "unit": UNIT, "cores": nps, "kind": kind,
+                   "sample": "%d measurements x N'=%d of the same table, Pool(%d) one measurement per task, correlated "
+                             "sampling, %s (%.1f s)" % (Gc, N, nps, _ref_describe(kind), dt)}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": t_ms / max(args.steps, 1), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "BASELINE config 4: synthetic 10^6 HII-region table (SURVEY 8d generator, seed 1004) "
-                                   "x nsample=2000 (N'=2200), --md all, dust on; weak scaling, %d galaxies per GPU "
-                                   "(N=8 is the full 10^6 table)" % args.galaxies_per_gpu,
-                       "galaxies_total": G_total, "galaxies_per_gpu": args.galaxies_per_gpu,
-                       "nsample": args.nsample, "n_draw": N, "md": "all", "dust": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg["name"] + ("; the whole table at every N (strong scaling)" if args.scaling == "strong"
+                                                   else "; weak scaling, 1/8 of the table per GPU"),
+                       "config": args.config, "galaxies_total": G_total, "galaxies_per_gpu": G,
+                       "nsample": cfg["nsample"], "n_draw": N, "md": cfg["md"], "dust": True,
                        "sampling": "independent per line (Philox4x32-10, seed 0xB200)",
                        "parallelism": ("galaxy-sharded x%d; result tables gathered by %s" % (
                            world, "the kernel itself (rows written into every rank's table over NVLink peer "
@@ -380,9 +478,12 @@ def run_ours(args):
                        "l2": "256 MiB buffer written between timed steps (not timed); per-step CUDA events"},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_n, "api": "mcz_ctx_run_host (C ABI, pinned host tables)"},
+                    "steps": e2e_n, "tables_match_device_path": e2e_matches,
+                    "api": "pymcz_b200.dist.production_table (the call mcz.run makes): pinned host tables in, full host "
+                           "tables out on every rank" + ("; mcz_ctx_run_host underneath" if world == 1 else "; gather included")},
             "roofline": roofline,
         }
+        line.update(verified)
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
@@ -396,8 +497,11 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--galaxies-per-gpu", type=int, default=GALAXIES_PER_GPU)
-    ap.add_argument("--nsample", type=int, default=NSAMPLE)
+    ap.add_argument("--config", type=int, default=4, choices=sorted(CONFIGS),
+                    help="BASELINE.json configuration: 4 (default, the metric's), 3 or 5")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong (default): the whole table at every N; weak: 1/8 of it per GPU")
+    ap.add_argument("--galaxies", type=int, default=None, help="override the configuration's table size (debugging)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
                     help="N > 1: result tables gathered by the kernel's own peer writes (default) or by NCCL")

@@ -113,6 +113,19 @@ int mcz_segmented_percentiles(const double* Z_d, const unsigned char* present_d,
  *   scratch_d: mcz_production_scratch_bytes(...) bytes
  */
 size_t mcz_production_scratch_bytes(long long G, long long n_draw, unsigned tokens);
+/* Statistics of the last mcz_forward_production* launch that used scratch_d (they live in the
+ * header of the caller's scratch buffer: the library keeps no per-process state).  Copies them
+ * to the host on `stream` and synchronises it.  out4: [0] galaxies processed, [1] KK04_N2Ha loop
+ * trips executed (metscales.py:1111), [2] KK04_R23 loop trips executed (:1166), [3] galaxies whose
+ * N2Ha loop was ended early because it provably runs to the reference's 100-trip cap (they are
+ * REPORTED with 100 trips, as the reference would; [1] counts what was executed).  All zero after
+ * a single-object (sample-tiled) launch. */
+int mcz_production_last_stats(const void* scratch_d, unsigned long long* out4, void* stream);
+/* Which kernel of the family a launch of this shape runs on the current device (the roofline
+ * accounting and the profiles name it): "production_kernel<4,0>" (columns in shared memory,
+ * N' <= 2304), "production_kernel<0,0>" / "<0,1>" (longer columns) or "wide_kernel" (single-object
+ * runs: few galaxies, N' >= 32768, samples tiled over all thread blocks). */
+const char* mcz_production_kernel_name(long long G, long long n_draw, unsigned tokens);
 int mcz_forward_production(const float* meas_d, const float* err_d, long long G, long long n_draw,
                            unsigned tokens, int dust, unsigned long long seed,
                            unsigned long long galaxy_offset, int sample_mode, int deterministic,

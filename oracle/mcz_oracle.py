@@ -127,6 +127,8 @@ class Diag:
             setattr(self, name, None)
         self.trips_n2ha = 0
         self.trips_r23 = 0
+        self.conv_n2ha = []          # the loops' convergence measure per trip (diagnostics for the tests)
+        self.conv_r23 = []
 
     # ---- dust (metscales.py:273-282)
     def dc(self, l1, l2, flux=False):
@@ -539,6 +541,7 @@ class Diag:
                     self.logq = self.calclogq(Z)
                     Z = self._kk04_n2ha_step(self.logq)
                     convergence = np.abs(self.logq - logq_save).mean()
+                    self.conv_n2ha.append(float(convergence))
                     logq_save = self.logq.copy()
                 if ii >= 100:
                     Z = np.zeros(self.n) + float('NaN')
@@ -572,6 +575,7 @@ class Diag:
             Z[indx] = nppoly.polyval(x[indx], [9.40, 4.65, -3.17]) - \
                 logq[indx] * nppoly.polyval(x[indx], [0.272, 0.547, -0.513])
             convergence = np.abs((logqold - logq).mean())
+            self.conv_r23.append(float(convergence))
             logqold = logq.copy()
         if ii >= 100:
             Z = np.zeros(self.n) + float('NaN')

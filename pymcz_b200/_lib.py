@@ -9,7 +9,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmcz_b200.so")
+# MCZ_B200_LIB: an instrumented / experimental build of the same library (tools/build_variant.sh)
+LIB_PATH = os.environ.get("MCZ_B200_LIB") or os.path.join(_HERE, "libmcz_b200.so")
 
 _lib = None
 
@@ -37,6 +38,8 @@ SIGNATURES = {
         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_void_p,
         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "mcz_production_scratch_bytes": (ctypes.c_size_t, [ctypes.c_longlong, ctypes.c_longlong, ctypes.c_uint]),
+    "mcz_production_kernel_name": (ctypes.c_char_p, [ctypes.c_longlong, ctypes.c_longlong, ctypes.c_uint]),
+    "mcz_production_last_stats": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "mcz_forward_production": (ctypes.c_int, [
         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_uint,
         ctypes.c_int, ctypes.c_ulonglong, ctypes.c_ulonglong, ctypes.c_int, ctypes.c_int,
@@ -63,6 +66,20 @@ SIGNATURES = {
         ctypes.c_void_p]),
 }
 
+#: every symbol include/mcz_b200_debug.h declares (test / profiling entry points)
+DEBUG_SIGNATURES = {
+    "mcz_debug_select_columns": (ctypes.c_int, [
+        ctypes.c_void_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p,
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "mcz_debug_production_samples": (ctypes.c_int, [
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_uint,
+        ctypes.c_ulonglong, ctypes.c_ulonglong, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+        ctypes.c_void_p, ctypes.c_void_p]),
+    "mcz_debug_counters": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "mcz_debug_phase_cycles": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "mcz_debug_col_cycles": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+}
+
 
 class MczLibraryError(RuntimeError):
     pass
@@ -78,7 +95,7 @@ def lib():
             "%s not found: the CUDA library is not built and pymcz_b200 has no CPU fallback. "
             "Build it with `make -C pymcz_b200/csrc` (needs nvcc, sm_100a)." % LIB_PATH)
     l = ctypes.CDLL(LIB_PATH)
-    for name, (res, args) in SIGNATURES.items():
+    for name, (res, args) in list(SIGNATURES.items()) + list(DEBUG_SIGNATURES.items()):
         fn = getattr(l, name)          # AttributeError if the header and the library disagree
         fn.restype = res
         fn.argtypes = args

@@ -6,6 +6,7 @@
 #include <mutex>
 #include <string>
 #include "../../include/mcz_b200.h"
+#include "../../include/mcz_b200_debug.h"
 #include "mcz_common.cuh"
 #include "mcz_internal.h"
 
@@ -91,6 +92,10 @@ size_t mcz_production_scratch_bytes(long long G, long long n_draw, unsigned toke
   return production_scratch_bytes(G, n_draw, tokens);
 }
 
+const char* mcz_production_kernel_name(long long G, long long n_draw, unsigned tokens) {
+  return production_kernel_name(G, n_draw, tokens);
+}
+
 int mcz_forward_production(const float* meas_d, const float* err_d, long long G, long long n_draw,
                            unsigned tokens, int dust, unsigned long long seed,
                            unsigned long long galaxy_offset, int sample_mode, int deterministic,
@@ -153,7 +158,6 @@ int mcz_forward_production_samples(const float* meas_d, const float* err_d, long
 // or > 4 target bins, [4] fallback: > 64 candidates (ties), [5] empty / non-positive columns
 int mcz_debug_counters(unsigned long long* out8, int reset) { return read_sel_counters(out8, reset); }
 
-// [0] galaxies, [1] N2Ha loop trips executed, [2] R23 loop trips executed, [3] proven-divergence early exits
 // test entry point (not part of the public header): the production kernel's warp selection on
 // caller-supplied float32 columns cols_d[ncols][N]; padded_d (ncols * roundup(N,128) floats) is
 // needed for N > 2304 only
@@ -163,7 +167,18 @@ int mcz_debug_select_columns(const float* cols_d, long long ncols, long long N, 
   return launch_select_columns(cols_d, ncols, N, pct_d, nvalid_d, status_d, padded_d, (cudaStream_t)stream);
 }
 
-int mcz_debug_trip_counters(unsigned long long* out4, int reset) { return read_trip_counters(out4, reset); }
+int mcz_debug_production_samples(const float* meas_d, const float* err_d, long long G, long long n_draw,
+                                 unsigned tokens, unsigned long long seed, unsigned long long galaxy_offset,
+                                 int sample_mode, int deterministic, float* flux_d, float* noise_d, void* stream) {
+  if (!meas_d || !err_d || !flux_d || !noise_d) return set_error("mcz_debug_production_samples: null pointer");
+  return launch_sample_export(meas_d, err_d, G, n_draw, tokens, seed, galaxy_offset, sample_mode, deterministic,
+                              flux_d, noise_d, (cudaStream_t)stream);
+}
+
+int mcz_production_last_stats(const void* scratch_d, unsigned long long* out4, void* stream) {
+  if (!scratch_d || !out4) return set_error("mcz_production_last_stats: null pointer");
+  return read_launch_stats(scratch_d, out4, (cudaStream_t)stream);
+}
 int mcz_debug_col_cycles(unsigned long long* out74, int reset) { return read_col_cycles(out74, reset); }
 int mcz_debug_phase_cycles(unsigned long long* out8, int reset) { return read_phase_cycles(out8, reset); }
 

@@ -18,13 +18,17 @@ int launch_replay(const double* flux, const double* noise, long long G, long lon
 int launch_percentiles_f64(const double* Z, const unsigned char* present, long long rows, long long N,
                            double* pct, int* nvalid, signed char* status, cudaStream_t stream);
 
-int read_trip_counters(unsigned long long* out4, int reset);
+int read_launch_stats(const void* scratch_d, unsigned long long* out4, cudaStream_t stream);
+int launch_sample_export(const float* meas, const float* err, long long G, long long n_draw, uint32_t tok,
+                         unsigned long long seed, unsigned long long galaxy_offset, int sample_mode,
+                         int deterministic, float* flux_d, float* noise_d, cudaStream_t stream);
 int read_col_cycles(unsigned long long* out, int reset);
 int read_phase_cycles(unsigned long long* out8, int reset);
 int read_sel_counters(unsigned long long* out8, int reset);
 int launch_select_columns(const float* cols_d, long long ncols, long long N, float* pct_d, int* nvalid_d,
                           signed char* status_d, float* padded_d, cudaStream_t stream);
 size_t production_scratch_bytes(long long G, long long n_draw, uint32_t tok);
+const char* production_kernel_name(long long G, long long n_draw, uint32_t tok);
 // Destination tables of a launch when they are not the caller's own: the gathered tables of up
 // to 8 ranks (peer-mapped device pointers), rows [row0, row0 + G) of each.
 struct ProdDst {

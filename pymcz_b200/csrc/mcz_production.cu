@@ -16,7 +16,9 @@
 // path is fused into the kernel.
 #include <float.h>
 #include <stdlib.h>
+#include <string.h>
 #include <cooperative_groups.h>
+#include <atomic>
 #include "mcz_physics.cuh"
 #include "mcz_philox.cuh"
 #include "mcz_device_utils.cuh"
@@ -30,6 +32,8 @@ static constexpr int CAND_FLOATS = 128;   // per-warp candidate area (counter + 
 static constexpr int CTRL_BYTES = 1024;
 static constexpr int MAX_DST = 8;                 // ranks of one node
 static constexpr uint32_t SEEN_KD = 1u << 8;     // ctrl->flags bit above the eight line flags
+static constexpr int SCRATCH_HEADER = 256;       // scratch_d starts with: galaxy queue counter (u64) at 0, launch statistics at 64
+static constexpr int SCRATCH_STATS_OFF = 64;
 static constexpr int DIVERGENCE_CHECK_TRIP = 8;   // when to test a still-running N2Ha loop for provable divergence
 
 struct ProdParams {
@@ -63,6 +67,7 @@ struct ProdParams {
   int wrank, wworld;
   void* wshared[MAX_DST];
   unsigned long long* counter;
+  unsigned long long* stats;               // scratch header: [0] galaxies, [1] N2Ha trips executed, [2] R23 trips executed, [3] early exits
   float* gscratch;                         // global variant: per-block columns + stash + loop state
   long long gscratch_per_block;            // floats
 };
@@ -73,7 +78,7 @@ struct Ctrl {
   int any_valid_kd;
   float line[2 * NLINES];
   float2 redf[2 * PW];
-  int acc[3][4];           // fixed-point block sums: two KK04 convergence measures x two trips per barrier
+  long long acc[3][4];     // fixed-point block sums: two KK04 convergence measures x two trips per barrier
 };
 static_assert(sizeof(Ctrl) <= CTRL_BYTES, "control block too large");
 
@@ -109,18 +114,30 @@ __device__ __forceinline__ void block_sum2f(float& a, float& c, float2* buf, int
   phase ^= 1;
 }
 
-// Block-wide sums of the two convergence measures in 16.16 fixed point: one REDUX per warp, one
-// shared atomic per warp, and a single barrier that also ORs the NaN flags (BAR.RED.OR).
-// Per-sample terms are clamped to +-8 by the caller, which cannot change the outcome of
-// "mean > tol" (tol * N < 8) and keeps the total within int32 for N <= 2304 * ... (N * 8 * 2^16 < 2^31).
+// Block-wide sums of the convergence measures in fixed point with FX_BITS fractional bits: the
+// thread's partial sum (<= 4 samples, each clamped to +-8 by the caller, which cannot change the
+// outcome of "mean > tol" since tol * N < 8) is rounded to 2^-FX_BITS, one REDUX per warp
+// (|warp total| <= 32 * 32 * 2^20 = 2^30), one 64-bit shared atomic per warp, and a single barrier
+// that also ORs the NaN flags (BAR.RED.OR).  The rounding error of the block total is ~7 quanta
+// (7e-6 at 20 bits, against thresholds tol * N of 0.22 and 2.2): below the float32 rounding of the
+// per-sample terms themselves, so the integer total is an order-independent, deterministic
+// stand-in for the reference's float64 mean (metscales.py:1117, 1177).
+#ifndef MCZ_FX_BITS
+#define MCZ_FX_BITS 20
+#endif
+static constexpr float FX_SCALE = (float)(1 << MCZ_FX_BITS);
+typedef long long fx_t;
+__device__ __forceinline__ void fx_add(fx_t* a, int q) {
+  atomicAdd(reinterpret_cast<unsigned long long*>(a), (unsigned long long)(long long)q);
+}
 __device__ __forceinline__ void block_sum2_fx(float s1, float s2, bool nan, Ctrl* ctrl, int& ph,
-                                              int& t1, int& t2, bool& anynan) {
+                                              fx_t& t1, fx_t& t2, bool& anynan) {
   const int lane = threadIdx.x & 31;
-  int q1 = __reduce_add_sync(0xffffffffu, __float2int_rn(s1 * 65536.0f));
-  int q2 = __reduce_add_sync(0xffffffffu, __float2int_rn(s2 * 65536.0f));
+  int q1 = __reduce_add_sync(0xffffffffu, __float2int_rn(s1 * FX_SCALE));
+  int q2 = __reduce_add_sync(0xffffffffu, __float2int_rn(s2 * FX_SCALE));
   if (lane == 0) {
-    atomicAdd(&ctrl->acc[ph][0], q1);
-    atomicAdd(&ctrl->acc[ph][1], q2);
+    fx_add(&ctrl->acc[ph][0], q1);
+    fx_add(&ctrl->acc[ph][1], q2);
   }
   const int nx = ph == 2 ? 0 : ph + 1;
   if (threadIdx.x < 4) ctrl->acc[nx][threadIdx.x] = 0;
@@ -132,14 +149,14 @@ __device__ __forceinline__ void block_sum2_fx(float s1, float s2, bool nan, Ctrl
 
 // Same for four sums (two loops x two trips per barrier); `nanbits` is OR-ed over the block.
 __device__ __forceinline__ void block_sum4_fx(const float s[4], unsigned nanbits, Ctrl* ctrl, int& ph,
-                                              int t[4], bool& anynan) {
+                                              fx_t t[4], bool& anynan) {
   const int lane = threadIdx.x & 31;
   int q[4];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) q[k] = __reduce_add_sync(0xffffffffu, __float2int_rn(s[k] * 65536.0f));
+  for (int k = 0; k < 4; ++k) q[k] = __reduce_add_sync(0xffffffffu, __float2int_rn(s[k] * FX_SCALE));
   if (lane == 0) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) atomicAdd(&ctrl->acc[ph][k], q[k]);
+    for (int k = 0; k < 4; ++k) fx_add(&ctrl->acc[ph][k], q[k]);
   }
   const int nx = ph == 2 ? 0 : ph + 1;
   if (threadIdx.x < 4) ctrl->acc[nx][threadIdx.x] = 0;
@@ -183,7 +200,6 @@ namespace mcz {
 // optional phase timing (build with -DMCZ_PHASE_TIMING): cycles summed over blocks, read back with
 // mcz_debug_phase_cycles: [0] galaxies, [1] phase A, [2] phases B+C, [3] phase D own work (mean
 // over the 18 warps), [4] phase D wall (start of D to the block barrier), [5] other
-__device__ unsigned long long g_trip_counters[4];   // [0] galaxies, [1] N2Ha trips executed, [2] R23 trips executed, [3] early exits
 __device__ unsigned long long g_phase_cycles[8];
 __device__ unsigned long long g_col_cycles[2 * NKEYS];   // per key: cycles, max-cycles accumulators
 #ifdef MCZ_PHASE_TIMING
@@ -407,7 +423,8 @@ production_kernel(const __grid_constant__ ProdParams p) {
 #pragma unroll
           for (int i = 0; i < SLOTS; ++i) Z1[i] = cA[i] - 7.37177f * cB[i];
         }
-        const int itol1 = (int)(tol1 * 65536.0f), itol2 = (int)(tol2 * 65536.0f);
+        // thresholds tol * N in the same fixed point (exact: N * 2^FX_BITS / 1000 in float64)
+        const fx_t itol1 = (fx_t)(1.0e-3 * (double)N * (double)FX_SCALE), itol2 = (fx_t)(1.0e-4 * (double)N * (double)FX_SCALE);
         int ph = 0;
         // Two trips per barrier: trips a and b are computed back to back, their four sums are
         // reduced together, then the reference's loop conditions are replayed trip by trip.  If a
@@ -459,7 +476,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
               lq2[i] = lqb;
             }
           }
-          int t4[4];
+          fx_t t4[4];
           bool anynan;
           block_sum4_fx(sm4, nanb, ctrl, ph, t4, anynan);
           unsigned nb = 0u;
@@ -519,7 +536,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
               }
               sm += (m == m) ? fminf(m, 8.0f) : 0.0f;
             }
-            int tm, tdummy;
+            fx_t tm, tdummy;
             bool nandummy;
             block_sum2_fx(sm, 0.0f, false, ctrl, ph, tm, tdummy, nandummy);
             if (tm > 4 * itol1) { executed1 = ii1; ii1 = 100; act1 = false; }
@@ -734,10 +751,10 @@ production_kernel(const __grid_constant__ ProdParams p) {
       }
     }
     if (tid == 0) {
-      atomicAdd(&g_trip_counters[0], 1ull);
-      atomicAdd(&g_trip_counters[1], (unsigned long long)(executed1 < 0 ? ii1 : executed1));
-      atomicAdd(&g_trip_counters[2], (unsigned long long)ii2);
-      if (executed1 >= 0 && executed1 != ii1) atomicAdd(&g_trip_counters[3], 1ull);
+      atomicAdd(&p.stats[0], 1ull);
+      atomicAdd(&p.stats[1], (unsigned long long)(executed1 < 0 ? ii1 : executed1));
+      atomicAdd(&p.stats[2], (unsigned long long)ii2);
+      if (executed1 >= 0 && executed1 != ii1) atomicAdd(&p.stats[3], 1ull);
       p.trips[2 * g] = ii1;
       p.trips[2 * g + 1] = ii2;
       if (p.ret) p.ret[g] = ok ? 0 : -1;
@@ -854,15 +871,42 @@ struct ProdPlan {
   long long per_block_floats;
 };
 
+// Per-device state (one process may drive several GPUs through mcz_ctx_create(device)): the SM
+// count, the "227 KB of dynamic shared memory" opt-in of every kernel (a function attribute is
+// per device) and the cooperative grid limit of the wide kernel are cached per device ordinal.
+static constexpr int MAX_DEVICES = 64;
+enum KernelId { KID_PROD_SHARED = 0, KID_PROD_GLOBAL, KID_PROD_GLOBAL_WIDE, KID_WIDE, KID_SELECT, KID_COUNT };
+struct DeviceState {
+  std::atomic<int> sms{0};
+  std::atomic<int> attr_done[KID_COUNT];
+  std::atomic<int> wide_max_blocks{0};
+  DeviceState() { for (auto& a : attr_done) a.store(0); }
+};
+static DeviceState g_dev[MAX_DEVICES];
+static DeviceState& device_state() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return g_dev[(dev >= 0 && dev < MAX_DEVICES) ? dev : 0];
+}
 static int num_sms() {
-  static int n = 0;
+  DeviceState& d = device_state();
+  int n = d.sms.load();
   if (!n) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
+    d.sms.store(n);
   }
   return n;
+}
+template <class K> static int ensure_smem_attr(K kernel, KernelId id, int bytes) {
+  DeviceState& d = device_state();
+  if (d.attr_done[id].load() >= bytes) return 0;
+  const int rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes), "smem attribute");
+  if (rc) return rc;
+  d.attr_done[id].store(bytes);
+  return 0;
 }
 
 static ProdPlan make_plan(long long G, long long N, int nstore) {
@@ -896,14 +940,13 @@ static ProdPlan make_plan(long long G, long long N, int nstore) {
   return pl;
 }
 
-int read_trip_counters(unsigned long long* out4, int reset) {
-  int rc = check_cuda(cudaMemcpyFromSymbol(out4, g_trip_counters, 4 * sizeof(unsigned long long)), "read trip counters");
+// The launch statistics live in the header of the caller's scratch buffer (no process-wide state):
+// bytes [64, 96) = galaxies, N2Ha trips executed, R23 trips executed, proven-divergence exits.
+int read_launch_stats(const void* scratch_d, unsigned long long* out4, cudaStream_t stream) {
+  int rc = check_cuda(cudaMemcpyAsync(out4, reinterpret_cast<const unsigned char*>(scratch_d) + SCRATCH_STATS_OFF,
+                                      4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream), "read launch stats");
   if (rc) return rc;
-  if (reset) {
-    unsigned long long z[4] = {0};
-    rc = check_cuda(cudaMemcpyToSymbol(g_trip_counters, z, sizeof(z)), "reset trip counters");
-  }
-  return rc;
+  return check_cuda(cudaStreamSynchronize(stream), "read launch stats");
 }
 
 int read_col_cycles(unsigned long long* out, int reset) {
@@ -944,12 +987,22 @@ size_t production_scratch_bytes(long long G, long long n_draw, uint32_t tok) {
   ProdParams p;
   build_slots(tok, p);
   const ProdPlan pl = make_plan(G, n_draw, p.nstore);
-  size_t need = 256 + (size_t)pl.grid * (size_t)pl.per_block_floats * sizeof(float);
+  size_t need = SCRATCH_HEADER + (size_t)pl.grid * (size_t)pl.per_block_floats * sizeof(float);
   if (use_wide(G, n_draw, nullptr)) {
     const size_t w = wide_scratch_bytes(n_draw, p.nstore);
     if (w > need) need = w;
   }
   return need;
+}
+
+// name of the kernel launch_production() picks for this launch shape on the current device
+const char* production_kernel_name(long long G, long long n_draw, uint32_t tok) {
+  ProdParams p;
+  build_slots(tok, p);
+  if (use_wide(G, n_draw, nullptr)) return "wide_kernel";
+  const ProdPlan pl = make_plan(G, n_draw, p.nstore);
+  if (!pl.global) return "production_kernel<4,0>";
+  return pl.wide ? "production_kernel<0,1>" : "production_kernel<0,0>";
 }
 
 int launch_production(const float* meas, const float* err, long long G, long long n_draw, uint32_t tok,
@@ -983,41 +1036,21 @@ int launch_production(const float* meas, const float* err, long long G, long lon
     p.pct[0] = pct; p.nvalid[0] = nvalid; p.status[0] = status;
   }
   p.trips = trips; p.ret = ret; p.Z = Z;
-  if ((ws && ws->world > 1) || use_wide(G, n_draw, Z)) return launch_wide(p, scratch, stream, ws);
-  p.counter = reinterpret_cast<unsigned long long*>(scratch);
-  p.gscratch = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(scratch) + 256);
-  p.gscratch_per_block = pl.per_block_floats;
-  int rc = check_cuda(cudaMemsetAsync(scratch, 0, 256, stream), "counter memset");
+  int rc = check_cuda(cudaMemsetAsync(scratch, 0, SCRATCH_HEADER, stream), "scratch header memset");
   if (rc) return rc;
+  p.counter = reinterpret_cast<unsigned long long*>(scratch);
+  p.stats = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(scratch) + SCRATCH_STATS_OFF);
+  if ((ws && ws->world > 1) || use_wide(G, n_draw, Z)) return launch_wide(p, scratch, stream, ws);
+  p.gscratch = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(scratch) + SCRATCH_HEADER);
+  p.gscratch_per_block = pl.per_block_floats;
   if (!pl.global) {
-    static bool attr_done = false;
-    if (!attr_done) {
-      rc = check_cuda(cudaFuncSetAttribute(production_kernel<4, false>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
-                      "smem attribute");
-      if (rc) return rc;
-      attr_done = true;
-    }
+    if ((rc = ensure_smem_attr(production_kernel<4, false>, KID_PROD_SHARED, 227 * 1024))) return rc;
     production_kernel<4, false><<<pl.grid, PT, pl.smem, stream>>>(p);
   } else if (!pl.wide) {
-    static bool attr_done = false;
-    if (!attr_done) {
-      rc = check_cuda(cudaFuncSetAttribute(production_kernel<0, false>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
-                      "smem attribute");
-      if (rc) return rc;
-      attr_done = true;
-    }
+    if ((rc = ensure_smem_attr(production_kernel<0, false>, KID_PROD_GLOBAL, 227 * 1024))) return rc;
     production_kernel<0, false><<<pl.grid, PT, pl.smem, stream>>>(p);
   } else {
-    static bool attr_done = false;
-    if (!attr_done) {
-      rc = check_cuda(cudaFuncSetAttribute(production_kernel<0, true>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
-                      "smem attribute");
-      if (rc) return rc;
-      attr_done = true;
-    }
+    if ((rc = ensure_smem_attr(production_kernel<0, true>, KID_PROD_GLOBAL_WIDE, 227 * 1024))) return rc;
     production_kernel<0, true><<<pl.grid, PT, pl.smem, stream>>>(p);
   }
   count_launch();
@@ -1524,7 +1557,7 @@ static size_t wide_shared_bytes_n(int nstore) {
 }
 static size_t wide_scratch_bytes(long long N, int nstore) {
   const long long Npad = (N + 127) / 128 * 128;
-  return wide_shared_bytes_n(nstore) + (size_t)((long long)nstore + 4 + 6) * Npad * sizeof(float);
+  return SCRATCH_HEADER + wide_shared_bytes_n(nstore) + (size_t)((long long)nstore + 4 + 6) * Npad * sizeof(float);
 }
 size_t wide_private_bytes(long long N, uint32_t tok) {
   ProdParams p;
@@ -1562,26 +1595,29 @@ static int launch_wide(ProdParams& p, void* scratch, cudaStream_t stream, const 
       if (!ws->shared[q]) return set_error("wide kernel: null shared region");
       p.wshared[q] = ws->shared[q];
     }
-    p.gscratch = reinterpret_cast<float*>(scratch);
+    p.gscratch = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(scratch) + SCRATCH_HEADER);
     // the cross-rank barrier counter starts at 0 (the caller makes sure every rank has done this
     // before any rank launches: one host-side barrier)
   } else {
     p.wworld = 1; p.wrank = 0;
-    p.wshared[0] = scratch;
-    p.gscratch = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(scratch) + shb);
-    const int rc = check_cuda(cudaMemsetAsync(reinterpret_cast<unsigned char*>(scratch) + shb - 256, 0, 256, stream), "barrier memset");
+    unsigned char* body = reinterpret_cast<unsigned char*>(scratch) + SCRATCH_HEADER;
+    p.wshared[0] = body;
+    p.gscratch = reinterpret_cast<float*>(body + shb);
+    const int rc = check_cuda(cudaMemsetAsync(body + shb - 256, 0, 256, stream), "barrier memset");
     if (rc) return rc;
   }
   const size_t smem = (size_t)PW * FineHist<false>::BYTES;
-  static int max_blocks = 0;
+  DeviceState& dstate = device_state();
+  int max_blocks = dstate.wide_max_blocks.load();
   if (!max_blocks) {
-    int rc = check_cuda(cudaFuncSetAttribute(wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attribute");
+    int rc = ensure_smem_attr(wide_kernel, KID_WIDE, (int)smem);
     if (rc) return rc;
     int per_sm = 0;
     rc = check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wide_kernel, PT, smem), "occupancy");
     if (rc) return rc;
     if (per_sm < 1) return set_error("wide_kernel does not fit on an SM");
     max_blocks = per_sm * num_sms();
+    dstate.wide_max_blocks.store(max_blocks);
   }
   int grid = max_blocks < num_sms() ? max_blocks : num_sms();
   const int ngroups = p.Npad / 128;
@@ -1632,12 +1668,8 @@ int launch_select_columns(const float* cols_d, long long ncols, long long N, flo
   const int grid = (int)((ncols + 3) / 4);
   if (N <= 18 * 128) {
     const size_t sm = 4 * (size_t)(18 * 128 * 4 + FineHist<true>::BYTES + 512);
-    static bool done = false;
-    if (!done) {
-      const int rc = check_cuda(cudaFuncSetAttribute(select_columns_kernel<18, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm), "smem attribute");
-      if (rc) return rc;
-      done = true;
-    }
+    const int rc = ensure_smem_attr(select_columns_kernel<18, false>, KID_SELECT, (int)sm);
+    if (rc) return rc;
     select_columns_kernel<18, false><<<grid, 128, sm, stream>>>(cols_d, (int)ncols, (int)N, 18 * 128, nullptr, pct_d, nvalid_d, status_d);
   } else {
     if (!padded_d) return set_error("mcz_debug_select_columns: columns longer than 2304 need the padded scratch");
@@ -1652,6 +1684,52 @@ int launch_select_columns(const float* cols_d, long long ncols, long long N, flo
   }
   count_launch();
   return check_cuda(cudaGetLastError(), "select_columns_kernel launch");
+}
+
+// ---- the sampler on its own (test entry point) --------------------------------------------------
+// Writes the perturbed, sanitised fluxes and the scaled coefficient noise exactly as phase A of the
+// production kernels derives them (same draw_normals / fmaf / clamps, hence the same MUFU results
+// bit for bit): flux[G][NUSED][N] in `Used` order, noise[G][5][N].  The parity tests feed these to
+// the oracle, so the comparison is about the arithmetic of the path and not about a host model of
+// the device's Box-Muller.
+__global__ void __launch_bounds__(256)
+sample_export_kernel(const __grid_constant__ ProdParams p, float* __restrict__ flux, float* __restrict__ noise) {
+  const int used2line[NUSED] = {L_HA, L_HB, L_O2, L_O3, L_N2, L_S2A, L_S2B, L_S39069};
+  const long long g = blockIdx.y;
+  const unsigned long long gg = p.goff + (unsigned long long)g;
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < p.N; s += gridDim.x * blockDim.x) {
+    float z[16];
+    draw_normals((uint32_t)s, gg, p, z);
+#pragma unroll
+    for (int u = 0; u < NUSED; ++u) {
+      const float lm = p.meas[g * NLINES + used2line[u]];
+      const float le = p.deterministic ? 0.0f : p.err[g * NLINES + used2line[u]];
+      float v = fmaf(le, p.correlated ? z[5] : z[5 + u], lm);
+      v = fmaxf(v, 0.0f);
+      if (!(v <= FLT_MAX)) v = 0.0f;
+      flux[(g * NUSED + u) * p.N + s] = v;
+    }
+    const float sg[5] = {0.05f, 0.1f, 0.027f, 0.024f, 0.012f};
+#pragma unroll
+    for (int j = 0; j < 5; ++j) noise[(g * 5 + j) * p.N + s] = sg[j] * z[j];
+  }
+}
+
+int launch_sample_export(const float* meas, const float* err, long long G, long long n_draw, uint32_t tok,
+                         unsigned long long seed, unsigned long long galaxy_offset, int sample_mode,
+                         int deterministic, float* flux_d, float* noise_d, cudaStream_t stream) {
+  if (G <= 0 || n_draw <= 0) return 0;
+  if (G > 65535) return set_error("mcz_debug_production_samples: at most 65535 galaxies per call");
+  ProdParams p;
+  memset(&p, 0, sizeof(p));
+  p.meas = meas; p.err = err; p.G = G; p.N = (int)n_draw; p.tok = tok;
+  p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32); p.goff = galaxy_offset;
+  p.correlated = sample_mode == 1; p.deterministic = deterministic != 0;
+  p.calls = philox_calls(tok, p.correlated, p.deterministic);
+  const int bx = (int)((n_draw + 255) / 256 < 64 ? (n_draw + 255) / 256 : 64);
+  sample_export_kernel<<<dim3(bx, (unsigned)G), 256, 0, stream>>>(p, flux_d, noise_d);
+  count_launch();
+  return check_cuda(cudaGetLastError(), "sample_export_kernel launch");
 }
 
 }  // namespace mcz

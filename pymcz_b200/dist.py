@@ -141,17 +141,83 @@ def production_table_sample_sharded(meas, err, n_draw, tokens, dust, seed, corre
                 trips=trips.cpu().numpy(), ret=ret.cpu().numpy(), Z=None, kernel_ms=ev0.elapsed_time(ev1))
 
 
-def production_table(meas, err, n_draw, tokens, dust, seed, correlated=False, deterministic=False,
-                     return_samples=False, device=None):
-    """Run the fused production kernel over a whole host table, sharded over the ranks of the
-    default process group (or on one GPU when torch.distributed is not initialised).
+class _HostPath:
+    """Per-device state of production_table: the C-ABI host-buffer context (mcz_ctx_create) and
+    pinned result tables, both reused from call to call (allocating 640 MB of pinned memory costs
+    more than the whole 10^6-galaxy run)."""
 
-    meas, err: float32 [G, 11] host arrays (every rank passes the same table).
+    def __init__(self, device):
+        from . import _lib
+        self.device = torch.device(device)
+        self.L = _lib.lib()
+        self.ctx = self.L.mcz_ctx_create(self.device.index if self.device.index is not None else torch.cuda.current_device())
+        if not self.ctx:
+            raise RuntimeError("mcz_ctx_create failed: " + self.L.mcz_last_error().decode())
+        self.cap = 0
+        self.out = None
+        self.gathered = {}              # G_total -> GatheredTables (symmetric-memory rendezvous is slow: keep)
+
+    def tables(self, G):
+        from ._scales import NKEYS
+        if G > self.cap:
+            self.out = dict(pct=torch.empty((G, NKEYS, 3), dtype=torch.float32).pin_memory(),
+                            nvalid=torch.empty((G, NKEYS), dtype=torch.int32).pin_memory(),
+                            status=torch.empty((G, NKEYS), dtype=torch.int8).pin_memory(),
+                            trips=torch.empty((G, 2), dtype=torch.int32).pin_memory(),
+                            ret=torch.empty((G,), dtype=torch.int32).pin_memory())
+            self.cap = G
+        return {k: v[:G] for k, v in self.out.items()}
+
+    def close(self):
+        if self.ctx:
+            self.L.mcz_ctx_destroy(self.ctx)
+            self.ctx = None
+
+
+_host_paths = {}
+
+
+def _host_path(device):
+    key = str(device)
+    if key not in _host_paths:
+        _host_paths[key] = _HostPath(device)
+    return _host_paths[key]
+
+
+def release_host_paths():
+    """Free the cached contexts / pinned tables of production_table."""
+    for hp in _host_paths.values():
+        hp.close()
+    _host_paths.clear()
+
+
+def _agree(ok: bool, device) -> bool:
+    """True iff `ok` holds on every rank (the ranks must take the same path through a collective)."""
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+    td.all_reduce(flag, op=td.ReduceOp.MIN)
+    return bool(int(flag.item()))
+
+
+def production_table(meas, err, n_draw, tokens, dust, seed, correlated=False, deterministic=False,
+                     return_samples=False, device=None, copy=True):
+    """Run the fused production kernel over a whole host table, sharded over the ranks of the
+    default process group (or on one GPU when torch.distributed is not initialised).  This is the
+    call mcz.run makes (the reference's loop over measurements, mcz.py:545-607).
+
+    meas, err: float32 [G, 11] host arrays (every rank passes the same table); pinned memory makes
+    the uploads asynchronous.
     Returns a dict of host numpy arrays with the FULL tables on every rank:
     pct [G,37,3] f32, nvalid [G,37] i32, status [G,37] i8, trips [G,2] i32, ret [G] i32,
-    Z [G,37,n_draw] f32 or None.
+    Z [G,37,n_draw] f32 or None.  With copy=False the tables are views of pinned buffers that the
+    next call on this device overwrites.
+
+    One GPU: the C ABI's host-buffer entry point (mcz_ctx_run_host: upload, up to 8 chunked
+    launches, result tables copied back while the next chunk computes).  Several GPUs (NCCL): every
+    rank uploads its shard, the kernel writes its result rows into every rank's full tables over
+    NVLink (GatheredTables), one barrier, and every rank copies the full tables to its host.
     """
     from . import ops
+    from ._scales import NKEYS
     if not torch.cuda.is_available():
         raise RuntimeError("pymcz_b200 needs a CUDA device: there is no CPU fallback")
     meas = np.ascontiguousarray(meas, dtype=np.float32)
@@ -160,27 +226,65 @@ def production_table(meas, err, n_draw, tokens, dust, seed, correlated=False, de
     world, r = world_size(), rank()
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device())
-    if (world > 1 and G < world and n_draw >= 262144 and not return_samples and not deterministic
-            and td.get_backend() == "nccl"):
+    device = torch.device(device)
+    done = (lambda t: {k: (np.array(v) if (copy and v is not None) else v) for k, v in t.items()})
+
+    if world == 1 and not return_samples:
+        hp = _host_path(device)
+        t = hp.tables(max(G, 1))
+        rc = hp.L.mcz_ctx_run_host(hp.ctx, meas.ctypes.data, err.ctypes.data, G, int(n_draw), int(tokens), int(dust),
+                                   int(seed), 0, 1 if correlated else 0, 1 if deterministic else 0,
+                                   t["pct"].data_ptr(), t["nvalid"].data_ptr(), t["status"].data_ptr(),
+                                   t["trips"].data_ptr(), t["ret"].data_ptr())
+        from . import _lib
+        _lib.check(rc, "mcz_ctx_run_host")
+        out = {k: v[:G].numpy() for k, v in t.items()}
+        out["Z"] = None
+        return done(out)
+
+    nccl = world > 1 and td.get_backend() == "nccl"
+    if nccl and G < world and n_draw >= 262144 and not return_samples and not deterministic:
         # single-object run: fewer galaxies than GPUs, very many samples each -> shard the samples
         try:
+            import torch.distributed._symmetric_memory  # noqa: F401
+            have = True
+        except ImportError:
+            have = False
+        if _agree(have, device):
             out = production_table_sample_sharded(meas, err, n_draw, tokens, dust, seed, correlated=correlated,
                                                   device=device)
             out.pop("kernel_ms", None)
             return out
-        except (ImportError, AttributeError):
-            pass                        # no symmetric memory in this torch: galaxy shards below
     lo, hi = shard_bounds(G, world, r)
-    m = torch.from_numpy(meas[lo:hi]).to(device)
-    e = torch.from_numpy(err[lo:hi]).to(device)
+    m = torch.from_numpy(meas[lo:hi]).to(device, non_blocking=True)
+    e = torch.from_numpy(err[lo:hi]).to(device, non_blocking=True)
     gt = None
-    if world > 1 and not return_samples and td.get_backend() == "nccl":
-        # the gather is fused into the kernel: result rows go straight into every rank's tables
-        try:
-            gt = GatheredTables(G, device)
-        except Exception:           # no peer mappings on this system: kernel, then all-gathers (below)
-            gt = None
+    if nccl and not return_samples:
+        # the gather is fused into the kernel: result rows go straight into every rank's tables.
+        # Whether the peer mappings exist is decided COLLECTIVELY: all ranks take the same path.
+        hp = _host_path(device)
+        gt = hp.gathered.get(G)
+        if gt is None:
+            try:
+                import torch.distributed._symmetric_memory  # noqa: F401
+                have = True
+            except ImportError:
+                have = False
+            if _agree(have, device):
+                try:
+                    gt = GatheredTables(G, device)
+                except RuntimeError as exc:            # peer mapping refused on this rank
+                    gt = None
+                    import warnings
+                    warnings.warn("fused gather unavailable on rank %d (%s): NCCL all-gathers instead" % (r, exc))
+                if not _agree(gt is not None, device):
+                    gt = None
+                else:
+                    hp.gathered[G] = gt
     if gt is not None:
+        # (cached tables: no rank's kernel may write into a peer's table while that peer still
+        # copies the previous call's rows out -- the same 4-byte all-reduce, ahead of the kernel)
+        gt.wait()
         if hi > lo:
             _, _, _, trips, ret, _ = ops.forward_production(
                 m, e, n_draw, tokens, dust, seed, galaxy_offset=lo, correlated=correlated,
@@ -190,15 +294,19 @@ def production_table(meas, err, n_draw, tokens, dust, seed, correlated=False, de
             ret = torch.empty((0,), dtype=torch.int32, device=device)
         gt.wait()
         small = gather_tables(dict(trips=trips, ret=ret), G)
+        t = _host_path(device).tables(max(G, 1))
+        for k, src in (("pct", gt.pct), ("nvalid", gt.nvalid), ("status", gt.status),
+                       ("trips", small["trips"]), ("ret", small["ret"])):
+            t[k][:G].copy_(src[:G], non_blocking=True)
         torch.cuda.synchronize(device)
-        out = dict(pct=gt.pct, nvalid=gt.nvalid, status=gt.status, trips=small["trips"], ret=small["ret"], Z=None)
-        return {k: (v.cpu().numpy() if v is not None else None) for k, v in out.items()}
+        out = {k: v[:G].numpy() for k, v in t.items()}
+        out["Z"] = None
+        return done(out)
     if hi > lo:
         pct, nvalid, status, trips, ret, Z = ops.forward_production(
             m, e, n_draw, tokens, dust, seed, galaxy_offset=lo, correlated=correlated,
             deterministic=deterministic, return_samples=return_samples)
     else:
-        from ._scales import NKEYS
         pct = torch.empty((0, NKEYS, 3), dtype=torch.float32, device=device)
         nvalid = torch.empty((0, NKEYS), dtype=torch.int32, device=device)
         status = torch.empty((0, NKEYS), dtype=torch.int8, device=device)

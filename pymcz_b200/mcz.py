@@ -212,6 +212,11 @@ def run(fi, nsample, mds, multiproc, logf, unpickle=False, dust_corr=True, verbo
     if RUNSIM:
         if seed is None:
             seed = int.from_bytes(os.urandom(8), 'little')                 # the reference is unseeded
+        if dist.world_size() > 1:                                          # one realisation: rank 0's seed everywhere
+            import torch.distributed as td
+            box = [seed]
+            td.broadcast_object_list(box, src=0)
+            seed = int(box[0])
         out = dist.production_table(meas_t, err_t, newnsample, tokens,
                                     sc.DUST_ON if dust_corr else sc.DUST_NONE, seed,
                                     correlated=bool(multiproc), deterministic=(nsample == 1),
@@ -223,8 +228,9 @@ def run(fi, nsample, mds, multiproc, logf, unpickle=False, dust_corr=True, verbo
         if out["Z"] is not None:
             # res[key] -> (N', nm) float64, NaN where the scale is None (mcz.py:600-611)
             res = {key: np.ascontiguousarray(out["Z"][:, j, :].T.astype(np.float64)) for j, key in enumerate(Zs)}
-            with open(picklefile, 'wb') as fpk:                            # mcz.py:618
-                pickle.dump(res, fpk)
+            if dist.rank() == 0:
+                with open(picklefile, 'wb') as fpk:                        # mcz.py:618
+                    pickle.dump(res, fpk)
         last_result = dict(res=res, pct=pct, nvalid=nvalid, status=status, trips=trips, ret=ret, seed=seed)
     else:
         # statistics of a pickled realisation: the float64 percentile op on the stored samples

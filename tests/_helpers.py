@@ -117,3 +117,82 @@ def production_flux_model(meas_row, err_row, seed, galaxy, n, correlated=False):
         flux[line] = (np.float32(meas_row[line]) + np.float32(err_row[line]) * zz.astype(np.float32)).astype(np.float64)
     noise = np.array([NOISE_SIGMA[j] * z[j] for j in range(5)])
     return flux, noise
+
+
+# ---- the production kernels' own samples, read back from the device --------------------------
+def kernel_samples(meas, err, n, seed, goff, tokens, correlated=False, deterministic=False):
+    """flux [G, 11, n] float64 and noise [G, 5, n] float64 exactly as the production kernels sample
+    them (mcz_debug_production_samples: same device code as phase A, bit for bit).  Lines the
+    arithmetic never reads keep their measured value ([OIII]4959, [OI]6300, [SIII]9532)."""
+    import torch
+    from pymcz_b200 import _lib
+    L = _lib.lib()
+    meas = np.ascontiguousarray(meas, dtype=np.float32)
+    err = np.ascontiguousarray(err, dtype=np.float32)
+    G = meas.shape[0]
+    flux = np.repeat(meas.astype(np.float64)[:, :, None], n, axis=2)
+    noise = np.zeros((G, 5, n))
+    for lo in range(0, G, 4096):
+        hi = min(G, lo + 4096)
+        m, e = torch.from_numpy(meas[lo:hi]).cuda(), torch.from_numpy(err[lo:hi]).cuda()
+        f = torch.empty((hi - lo, 8, n), dtype=torch.float32, device="cuda")
+        z = torch.empty((hi - lo, 5, n), dtype=torch.float32, device="cuda")
+        rc = L.mcz_debug_production_samples(m.data_ptr(), e.data_ptr(), hi - lo, n, int(tokens), int(seed),
+                                            int(goff) + lo, 1 if correlated else 0, 1 if deterministic else 0,
+                                            f.data_ptr(), z.data_ptr(), None)
+        _lib.check(rc, "mcz_debug_production_samples")
+        torch.cuda.synchronize()
+        f = f.cpu().numpy().astype(np.float64)
+        for u, line in enumerate(USED_LINES):
+            flux[lo:hi, line] = f[:, u]
+        noise[lo:hi] = z.cpu().numpy().astype(np.float64)
+    return flux, noise
+
+
+class FixedNoise:
+    """Feeds pre-computed coefficient noise to the oracle in its np.random.normal call order."""
+
+    def __init__(self, noise):
+        self.noise = noise
+        self.toggle = 0
+
+    def __call__(self, loc, scale, size):
+        row = {0.05: 0, 0.1: 1, 0.027: 2, 0.024: 3}.get(scale)
+        if row is None:
+            self.toggle ^= 1
+            return self.noise[4] if self.toggle == 1 else np.zeros(size)
+        return self.noise[row]
+
+
+def _oracle_one(args):
+    flux, noise, mds, dust = args
+    d, ret, _ = orc.calculation(flux, mds, dust, False, "batched", FixedNoise(noise))
+    n = flux.shape[1]
+    present = np.zeros(len(orc.KEYS), dtype=bool)
+    Z = np.full((len(orc.KEYS), n), np.nan)
+    for j, k in enumerate(orc.KEYS):
+        if d.mds[k] is not None:
+            present[j] = True
+            Z[j] = d.mds[k]
+    return present, Z, (d.trips_n2ha, d.trips_r23), (d.conv_n2ha, d.conv_r23)
+
+
+def oracle_on_samples(flux, noise, mds, dust, procs=None):
+    """The oracle on [G, 11, n] flux samples (float64) + [G, 5, n] coefficient noise, galaxies spread
+    over a process pool.  Returns Z [G,37,n], present [G,37], trips [G,2] and the per-trip
+    convergence measures of the two KK04 loops (list of (conv_n2ha, conv_r23) per galaxy)."""
+    import multiprocessing as mp
+    import os
+    G, _, n = flux.shape
+    jobs = [(flux[g], noise[g], mds, dust) for g in range(G)]
+    procs = procs or min(os.cpu_count() or 1, 16)
+    if procs > 1 and G >= 8:
+        with mp.get_context("fork").Pool(procs) as pool:
+            res = pool.map(_oracle_one, jobs, chunksize=max(1, G // (8 * procs)))
+    else:
+        res = [_oracle_one(j) for j in jobs]
+    Zo = np.stack([r[1] for r in res])
+    po = np.stack([r[0] for r in res])
+    trips = np.array([r[2] for r in res], dtype=np.int32)
+    conv = [r[3] for r in res]
+    return Zo, po, trips, conv
