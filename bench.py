@@ -334,11 +334,11 @@ def run_ours(args):
     # with the reference's outcome of 100 trips): the roofline is credited with EXECUTED work only.
     # The statistics of the last launch live in the header of its scratch buffer.
     import ctypes
-    tc = (ctypes.c_ulonglong * 4)()
+    tc = (ctypes.c_ulonglong * 8)()
     _lib.check(L.mcz_production_last_stats(ws.scratch.data_ptr(), tc, torch.cuda.current_stream(dev).cuda_stream),
                "mcz_production_last_stats")
     exec_trips = (tc[1] + tc[2]) / max(tc[0], 1)
-    early_exits = int(tc[3])
+    early_exits = int(tc[3]) + int(tc[4])
 
     # ---- verification of the exchange (N > 1): after timing, not timed
     verified = {}

@@ -98,6 +98,31 @@ int mcz_segmented_percentiles(const double* Z_d, const unsigned char* present_d,
                               long long N, double* pct_d, int* nvalid_d, signed char* status_d,
                               void* stream);
 
+/* ---- after the path: binning and sample-size assists --------------------------
+ * mcz_histogram_assist replaces the data-parallel inside of the reference's histogram binning:
+ * savehist's np.std (mcz.py:289) and getknuth's np.histogram(data, np.linspace(min(data),
+ * max(data), m + 1)) (mcz.py:90-99), which Knuth's rule (knuthn, mcz.py:102-116) evaluates for every
+ * bin number m the optimiser visits.  The optimiser and the gammaln posterior stay on the host.
+ *   Z_d      [rows][N] float64 distributions (res[key][:, i] of mcz.py:600-611); non-finite = dropped
+ *   bin_numbers_h  HOST array of n_bin_numbers bin numbers m, each in [1, 8192]
+ *   stats_d  [rows][6] float64: n, min, max, mean, std (population, like np.std), sum of the finite values
+ *   counts_d [rows][sum of all m] int32: for each row, the m counts of each requested m, one after
+ *            the other in request order; bit-identical to np.histogram on the np.linspace edges
+ *   scratch_d n_bin_numbers int32 of device memory (the bin list is uploaded there)
+ */
+int mcz_histogram_assist(const double* Z_d, long long rows, long long N, const int* bin_numbers_h,
+                         int n_bin_numbers, double* stats_d, int* counts_d, int* scratch_d, void* stream);
+
+/* mcz_ks_2samp replaces the statistic of scipy.stats.ks_2samp(x, xold) in the reference's sample-size
+ * diagnostic (testcompleteness.py:111): both empirical CDFs at every data point, exactly as scipy
+ * forms them (searchsorted(.., 'right') / n), then the extremes of their difference.  Neither sample
+ * needs to be sorted; both must be finite and non-empty.  The p-value stays on the host.
+ *   a_d [n1], b_d [n2] float64;  out_d [3] float64: D (two-sided), D+ = max(F_a - F_b), D- = max(F_b - F_a)
+ *   scratch_d 16 bytes of device memory
+ */
+int mcz_ks_2samp(const double* a_d, long long n1, const double* b_d, long long n2, double* out_d,
+                 void* scratch_d, void* stream);
+
 /* ---- production: the fused Monte-Carlo path ---------------------------------------------------
  * Replaces, for G galaxies in one launch: the sampling and perturbation of run()/calc()
  * (mcz.py:509-519, 436-442, 580-589), metallicity.calculation (metallicity.py:86-257) and the
@@ -115,12 +140,13 @@ int mcz_segmented_percentiles(const double* Z_d, const unsigned char* present_d,
 size_t mcz_production_scratch_bytes(long long G, long long n_draw, unsigned tokens);
 /* Statistics of the last mcz_forward_production* launch that used scratch_d (they live in the
  * header of the caller's scratch buffer: the library keeps no per-process state).  Copies them
- * to the host on `stream` and synchronises it.  out4: [0] galaxies processed, [1] KK04_N2Ha loop
+ * to the host on `stream` and synchronises it.  out8: [0] galaxies processed, [1] KK04_N2Ha loop
  * trips executed (metscales.py:1111), [2] KK04_R23 loop trips executed (:1166), [3] galaxies whose
- * N2Ha loop was ended early because it provably runs to the reference's 100-trip cap (they are
- * REPORTED with 100 trips, as the reference would; [1] counts what was executed).  All zero after
- * a single-object (sample-tiled) launch. */
-int mcz_production_last_stats(const void* scratch_d, unsigned long long* out4, void* stream);
+ * N2Ha loop was ended early because it provably runs to the reference's 100-trip cap, [4] the same
+ * for the R23 loop (such galaxies are REPORTED with 100 trips and blanked, as the reference does,
+ * metscales.py:1119-1121, 1179-1181; [1], [2] count what was executed), [5..7] reserved.  All zero
+ * after a single-object (sample-tiled) launch. */
+int mcz_production_last_stats(const void* scratch_d, unsigned long long* out8, void* stream);
 /* Which kernel of the family a launch of this shape runs on the current device (the roofline
  * accounting and the profiles name it): "production_kernel<4,0>" (columns in shared memory,
  * N' <= 2304), "production_kernel<0,0>" / "<0,1>" (longer columns) or "wide_kernel" (single-object

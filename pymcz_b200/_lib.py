@@ -37,6 +37,12 @@ SIGNATURES = {
     "mcz_segmented_percentiles": (ctypes.c_int, [
         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_void_p,
         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "mcz_histogram_assist": (ctypes.c_int, [
+        ctypes.c_void_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "mcz_ks_2samp": (ctypes.c_int, [
+        ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p,
+        ctypes.c_void_p]),
     "mcz_production_scratch_bytes": (ctypes.c_size_t, [ctypes.c_longlong, ctypes.c_longlong, ctypes.c_uint]),
     "mcz_production_kernel_name": (ctypes.c_char_p, [ctypes.c_longlong, ctypes.c_longlong, ctypes.c_uint]),
     "mcz_production_last_stats": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),

@@ -88,6 +88,18 @@ int mcz_segmented_percentiles(const double* Z_d, const unsigned char* present_d,
   return launch_percentiles_f64(Z_d, present_d, rows, N, pct_d, nvalid_d, status_d, (cudaStream_t)stream);
 }
 
+int mcz_histogram_assist(const double* Z_d, long long rows, long long N, const int* bin_numbers_h,
+                         int n_bin_numbers, double* stats_d, int* counts_d, int* scratch_d, void* stream) {
+  if (!Z_d || !stats_d || (n_bin_numbers > 0 && !bin_numbers_h)) return set_error("mcz_histogram_assist: null pointer");
+  return launch_histogram_assist(Z_d, rows, N, bin_numbers_h, n_bin_numbers, stats_d, counts_d, scratch_d,
+                                 (cudaStream_t)stream);
+}
+
+int mcz_ks_2samp(const double* a_d, long long n1, const double* b_d, long long n2, double* out_d,
+                 void* scratch_d, void* stream) {
+  return launch_ks_2samp(a_d, n1, b_d, n2, out_d, static_cast<unsigned long long*>(scratch_d), (cudaStream_t)stream);
+}
+
 size_t mcz_production_scratch_bytes(long long G, long long n_draw, unsigned tokens) {
   return production_scratch_bytes(G, n_draw, tokens);
 }
@@ -175,9 +187,9 @@ int mcz_debug_production_samples(const float* meas_d, const float* err_d, long l
                               flux_d, noise_d, (cudaStream_t)stream);
 }
 
-int mcz_production_last_stats(const void* scratch_d, unsigned long long* out4, void* stream) {
-  if (!scratch_d || !out4) return set_error("mcz_production_last_stats: null pointer");
-  return read_launch_stats(scratch_d, out4, (cudaStream_t)stream);
+int mcz_production_last_stats(const void* scratch_d, unsigned long long* out8, void* stream) {
+  if (!scratch_d || !out8) return set_error("mcz_production_last_stats: null pointer");
+  return read_launch_stats(scratch_d, out8, (cudaStream_t)stream);
 }
 int mcz_debug_col_cycles(unsigned long long* out74, int reset) { return read_col_cycles(out74, reset); }
 int mcz_debug_phase_cycles(unsigned long long* out8, int reset) { return read_phase_cycles(out8, reset); }

@@ -18,7 +18,11 @@ int launch_replay(const double* flux, const double* noise, long long G, long lon
 int launch_percentiles_f64(const double* Z, const unsigned char* present, long long rows, long long N,
                            double* pct, int* nvalid, signed char* status, cudaStream_t stream);
 
-int read_launch_stats(const void* scratch_d, unsigned long long* out4, cudaStream_t stream);
+int launch_histogram_assist(const double* Z_d, long long rows, long long N, const int* mlist_h, int nm,
+                            double* stats_d, int* counts_d, int* mlist_scratch_d, cudaStream_t stream);
+int launch_ks_2samp(const double* a_d, long long n1, const double* b_d, long long n2, double* out_d,
+                    unsigned long long* scratch_d, cudaStream_t stream);
+int read_launch_stats(const void* scratch_d, unsigned long long* out8, cudaStream_t stream);
 int launch_sample_export(const float* meas, const float* err, long long G, long long n_draw, uint32_t tok,
                          unsigned long long seed, unsigned long long galaxy_offset, int sample_mode,
                          int deterministic, float* flux_d, float* noise_d, cudaStream_t stream);

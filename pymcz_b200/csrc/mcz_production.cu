@@ -67,7 +67,7 @@ struct ProdParams {
   int wrank, wworld;
   void* wshared[MAX_DST];
   unsigned long long* counter;
-  unsigned long long* stats;               // scratch header: [0] galaxies, [1] N2Ha trips executed, [2] R23 trips executed, [3] early exits
+  unsigned long long* stats;               // scratch header: [0] galaxies, [1] N2Ha trips executed, [2] R23 trips executed, [3] N2Ha early exits, [4] R23 early exits
   float* gscratch;                         // global variant: per-block columns + stash + loop state
   long long gscratch_per_block;            // floats
 };
@@ -79,6 +79,7 @@ struct Ctrl {
   float line[2 * NLINES];
   float2 redf[2 * PW];
   long long acc[3][4];     // fixed-point block sums: two KK04 convergence measures x two trips per barrier
+  unsigned chg[3];         // some sample's R23 loop state changed over the batch (rotates with acc)
 };
 static_assert(sizeof(Ctrl) <= CTRL_BYTES, "control block too large");
 
@@ -141,6 +142,7 @@ __device__ __forceinline__ void block_sum2_fx(float s1, float s2, bool nan, Ctrl
   }
   const int nx = ph == 2 ? 0 : ph + 1;
   if (threadIdx.x < 4) ctrl->acc[nx][threadIdx.x] = 0;
+  if (threadIdx.x == 4) ctrl->chg[nx] = 0u;
   anynan = __syncthreads_or(nan);
   t1 = ctrl->acc[ph][0];
   t2 = ctrl->acc[ph][1];
@@ -148,21 +150,27 @@ __device__ __forceinline__ void block_sum2_fx(float s1, float s2, bool nan, Ctrl
 }
 
 // Same for four sums (two loops x two trips per barrier); `nanbits` is OR-ed over the block.
-__device__ __forceinline__ void block_sum4_fx(const float s[4], unsigned nanbits, Ctrl* ctrl, int& ph,
-                                              fx_t t[4], bool& anynan) {
+// `changed`: this thread's R23 loop state differs from the state before the batch; `anychanged`
+// is its OR over the block.
+__device__ __forceinline__ void block_sum4_fx(const float s[4], unsigned nanbits, bool changed, Ctrl* ctrl, int& ph,
+                                              fx_t t[4], bool& anynan, bool& anychanged) {
   const int lane = threadIdx.x & 31;
   int q[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) q[k] = __reduce_add_sync(0xffffffffu, __float2int_rn(s[k] * FX_SCALE));
+  const bool wchg = __any_sync(0xffffffffu, changed);
   if (lane == 0) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) fx_add(&ctrl->acc[ph][k], q[k]);
+    if (wchg) ctrl->chg[ph] = 1u;
   }
   const int nx = ph == 2 ? 0 : ph + 1;
   if (threadIdx.x < 4) ctrl->acc[nx][threadIdx.x] = 0;
+  if (threadIdx.x == 4) ctrl->chg[nx] = 0u;
   anynan = __syncthreads_or(nanbits != 0u);
 #pragma unroll
   for (int k = 0; k < 4; ++k) t[k] = ctrl->acc[ph][k];
+  anychanged = ctrl->chg[ph] != 0u;
   ph = nx;
 }
 
@@ -278,6 +286,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
     if (lane == 0) {
       ctrl->g = gn;
       ctrl->flags = 0u; ctrl->acc[0][0] = 0; ctrl->acc[0][1] = 0; ctrl->acc[0][2] = 0; ctrl->acc[0][3] = 0;
+      ctrl->chg[0] = 0u;
     }
   };
   if (warp == PW - 1) fetch_next();
@@ -367,6 +376,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
     // ---- phases B and C ----------------------------------------------------------------------
     int ii1 = 0, ii2 = 0;
     int executed1 = -1;       // N2Ha trips actually executed (differs from ii1 after a proven early exit)
+    int executed2 = -1;       // same for the R23 loop (periodic-state exit)
     if ((p.tok & T_KD02) && ok) {
       const bool has_kd = (pm >> K_KD02_N2O2) & 1ull;
       const bool has_kn = (pm >> K_KK04_N2HA) & 1ull, has_kr = (pm >> K_KK04_R23) & 1ull;
@@ -436,6 +446,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
         while (act1 || act2) {
           float sm4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
           unsigned nanb = 0u;
+          bool changed = false;       // R23 loop: some sample's logq after this batch differs from before it
           float lq1a[SLOTS], lq2a[SLOTS];
           if (act1) {
 #pragma unroll
@@ -473,12 +484,13 @@ production_kernel(const __grid_constant__ ProdParams p) {
               d = lq - lqb;
               nanb |= (d != d) ? 8u : 0u;
               sm4[3] += fminf(fmaxf(d, -8.0f), 8.0f);
+              changed = changed || (lqb != lq2[i]);
               lq2[i] = lqb;
             }
           }
           fx_t t4[4];
-          bool anynan;
-          block_sum4_fx(sm4, nanb, ctrl, ph, t4, anynan);
+          bool anynan, anychanged;
+          block_sum4_fx(sm4, nanb, changed, ctrl, ph, t4, anynan, anychanged);
           unsigned nb = 0u;
           if (anynan) {      // rare: which loop / trip saw the NaN (a NaN mean stops that loop)
 #pragma unroll
@@ -510,6 +522,15 @@ production_kernel(const __grid_constant__ ProdParams p) {
             } else {
               ++ii2;
               act2 = !(nb & 8u) && ((t4[3] < 0 ? -t4[3] : t4[3]) > itol2) && ii2 < 100;
+              // Periodic-state exit.  logq of EVERY sample is bit-identical to what it was two trips
+              // ago, and Z is a function of logq: every later batch repeats this one, sums included.
+              // Both of its trips passed the loop test with a factor 2 to spare, so the loop runs to
+              // the 100-trip cap and the galaxy is blanked (metscales.py:1179-1181) -- report that now.
+              // (What the reference's capped R23 loops do: samples caught in a 2-cycle between the
+              // lower and the upper branch keep |mean(dlogq)| at a constant far above the tolerance.)
+              if (act2 && !anychanged && (t4[2] < 0 ? -t4[2] : t4[2]) > 2 * itol2 && (t4[3] < 0 ? -t4[3] : t4[3]) > 2 * itol2) {
+                executed2 = ii2; ii2 = 100; act2 = false;
+              }
             }
           }
           if (act1 && ii1 == DIVERGENCE_CHECK_TRIP) {
@@ -753,8 +774,9 @@ production_kernel(const __grid_constant__ ProdParams p) {
     if (tid == 0) {
       atomicAdd(&p.stats[0], 1ull);
       atomicAdd(&p.stats[1], (unsigned long long)(executed1 < 0 ? ii1 : executed1));
-      atomicAdd(&p.stats[2], (unsigned long long)ii2);
+      atomicAdd(&p.stats[2], (unsigned long long)(executed2 < 0 ? ii2 : executed2));
       if (executed1 >= 0 && executed1 != ii1) atomicAdd(&p.stats[3], 1ull);
+      if (executed2 >= 0 && executed2 != ii2) atomicAdd(&p.stats[4], 1ull);
       p.trips[2 * g] = ii1;
       p.trips[2 * g + 1] = ii2;
       if (p.ret) p.ret[g] = ok ? 0 : -1;
@@ -941,10 +963,11 @@ static ProdPlan make_plan(long long G, long long N, int nstore) {
 }
 
 // The launch statistics live in the header of the caller's scratch buffer (no process-wide state):
-// bytes [64, 96) = galaxies, N2Ha trips executed, R23 trips executed, proven-divergence exits.
-int read_launch_stats(const void* scratch_d, unsigned long long* out4, cudaStream_t stream) {
-  int rc = check_cuda(cudaMemcpyAsync(out4, reinterpret_cast<const unsigned char*>(scratch_d) + SCRATCH_STATS_OFF,
-                                      4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream), "read launch stats");
+// bytes [64, 128) = galaxies, N2Ha trips executed, R23 trips executed, N2Ha proven-divergence exits,
+// R23 periodic-state exits, 3 spare.
+int read_launch_stats(const void* scratch_d, unsigned long long* out8, cudaStream_t stream) {
+  int rc = check_cuda(cudaMemcpyAsync(out8, reinterpret_cast<const unsigned char*>(scratch_d) + SCRATCH_STATS_OFF,
+                                      8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream), "read launch stats");
   if (rc) return rc;
   return check_cuda(cudaStreamSynchronize(stream), "read launch stats");
 }
@@ -1074,10 +1097,20 @@ int launch_production(const float* meas, const float* err, long long G, long lon
 struct WideCtl {
   unsigned flags;                 // line flags | SEEN_KD
   unsigned nan[3];                // NaN bits of the KK04 sums, rotating with sums[]
-  long long sums[3][4];           // 16.16 fixed point
+  long long sums[3][4];           // fixed point, 18 fractional bits, per-sample rounding (wfx)
   double colsum[NKEYS];           // per slot: sum of the finite values (sum <= 0 test, mcz.py:282-285)
 };
 static_assert(sizeof(WideCtl) <= 4096, "wide control block too large");
+
+// Wide kernel: the per-sample terms of the KK04 convergence sums are rounded to 2^-18 ONE BY ONE and
+// added as integers (the 1.5 * 2^23 bias makes the FMA itself round to an integer held in the low
+// mantissa bits; exact for |d| <= 8).  Integer sums do not depend on how the samples are grouped
+// into threads, blocks or GPUs, so a run gives the same trip counts -- hence bit-identical tables --
+// whatever the grid and however many ranks share the object.
+static constexpr float WFX_SCALE = 262144.0f;     // 2^18
+__device__ __forceinline__ int wfx(float d) {     // d already clamped to [-8, 8]; NaN is flagged by the caller
+  return __float_as_int(fmaf(d, WFX_SCALE, 12582912.0f)) - 0x4B400000;
+}
 
 __global__ void __launch_bounds__(PT, 1)
 wide_kernel(const __grid_constant__ ProdParams p) {
@@ -1201,7 +1234,7 @@ wide_kernel(const __grid_constant__ ProdParams p) {
       const bool o3o2 = (flags & F_O2) && (flags & F_O3);
       const int sl_kd = p.slot_of_key[K_KD02_N2O2], sl_m91 = p.slot_of_key[K_M91];
       bool act1 = has_kn && o3o2, act2 = has_kr;
-      const long long itol1 = (long long)(1.0e-3 * (double)N * 65536.0), itol2 = (long long)(1.0e-4 * (double)N * 65536.0);
+      const long long itol1 = (long long)(1.0e-3 * (double)N * (double)WFX_SCALE), itol2 = (long long)(1.0e-4 * (double)N * (double)WFX_SCALE);
       auto consts = [&](int s, IterState<float>& st) {
         Carry<float> c;
         c.y = st0[s]; c.n2ha = st1[s]; c.x = st2[s];
@@ -1219,13 +1252,16 @@ wide_kernel(const __grid_constant__ ProdParams p) {
       }
       int ph = 0;
       // fixed-point block -> grid sums of (up to) four terms; returns the four totals and NaN bits
-      auto grid_sums = [&](const float sm4[4], unsigned nanb, long long t4[4], unsigned& nb) {
+      auto grid_sums = [&](const long long sm4[4], unsigned nanb, long long t4[4], unsigned& nb) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const int q = __reduce_add_sync(0xffffffffu, __float2int_rn(sm4[k] * 65536.0f));
+          // (a thread holds at most a few hundred samples of <= 2^21 each; the warp total may pass 2^31)
+          long long q = sm4[k];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
           if (lane == 0 && q)
             for (int r = 0; r < W; ++r)
-              atomicAdd_system(reinterpret_cast<unsigned long long*>(peer(&ctl->sums[ph][k], r)), (unsigned long long)(long long)q);
+              atomicAdd_system(reinterpret_cast<unsigned long long*>(peer(&ctl->sums[ph][k], r)), (unsigned long long)q);
         }
         nanb = __reduce_or_sync(0xffffffffu, nanb);
         if (lane == 0 && nanb)
@@ -1240,7 +1276,7 @@ wide_kernel(const __grid_constant__ ProdParams p) {
         ph = nx;
       };
       while (act1 || act2) {
-        float sm4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        long long sm4[4] = {0, 0, 0, 0};
         unsigned nanb = 0u;
         for (int s = s_lo + tid; s < s_hi && s < N; s += PT) {
           IterState<float> k;                         // only the constants of the loops still running
@@ -1254,11 +1290,11 @@ wide_kernel(const __grid_constant__ ProdParams p) {
             const float z = k.A - lq * k.B;
             float d = fabsf(lq - lq1);
             nanb |= (d != d) ? 1u : 0u;
-            sm4[0] += fminf(d, 8.0f);
+            sm4[0] += wfx(fminf(d, 8.0f));
             const float lqb = (num0 + z * num1) * fast_rcp(den0 + z * den1);
             d = fabsf(lqb - lq);
             nanb |= (d != d) ? 2u : 0u;
-            sm4[1] += fminf(d, 8.0f);
+            sm4[1] += wfx(fminf(d, 8.0f));
             F[0ll * Npad + s] = k.A - lqb * k.B;
             F[2ll * Npad + s] = lqb;
             F[4ll * Npad + s] = lq;
@@ -1271,12 +1307,12 @@ wide_kernel(const __grid_constant__ ProdParams p) {
             const float z = (lower ? k.L0 : k.U0) - lq * (lower ? k.L1 : k.U1);
             float d = lq2 - lq;
             nanb |= (d != d) ? 4u : 0u;
-            sm4[2] += fminf(fmaxf(d, -8.0f), 8.0f);
+            sm4[2] += wfx(fminf(fmaxf(d, -8.0f), 8.0f));
             const float lqb = (num0 + z * num1) * fast_rcp(den0 + z * den1);
             lower = lowz && (lqb >= 6.7f) && (lqb < 8.3f);
             d = lq - lqb;
             nanb |= (d != d) ? 8u : 0u;
-            sm4[3] += fminf(fmaxf(d, -8.0f), 8.0f);
+            sm4[3] += wfx(fminf(fmaxf(d, -8.0f), 8.0f));
             F[1ll * Npad + s] = (lower ? k.L0 : k.U0) - lqb * (lower ? k.L1 : k.U1);
             F[3ll * Npad + s] = lqb;
             F[5ll * Npad + s] = lq;
@@ -1319,7 +1355,7 @@ wide_kernel(const __grid_constant__ ProdParams p) {
           }
         }
         if (act1 && ii1 == DIVERGENCE_CHECK_TRIP) {      // proven-divergence exit (see production_kernel)
-          float sm[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+          long long sm[4] = {0, 0, 0, 0};
           for (int s = s_lo + tid; s < s_hi && s < N; s += PT) {
             IterState<float> k;
             consts(s, k);
@@ -1332,7 +1368,7 @@ wide_kernel(const __grid_constant__ ProdParams p) {
               const float q1 = (de * u1 - bg) * u1 + al, q2 = (de * u2 - bg) * u2 + al;
               m = fminf(fabsf(q1), fabsf(q2)) * fast_rcp(r);
             }
-            sm[0] += (m == m) ? fminf(m, 8.0f) : 0.0f;
+            sm[0] += wfx((m == m) ? fminf(m, 8.0f) : 0.0f);
           }
           long long t4b[4];
           unsigned nbb;

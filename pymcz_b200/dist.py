@@ -191,6 +191,15 @@ def release_host_paths():
     _host_paths.clear()
 
 
+def _have_symm() -> bool:
+    import importlib
+    try:
+        importlib.import_module("torch.distributed._symmetric_memory")
+        return True
+    except ImportError:
+        return False
+
+
 def _agree(ok: bool, device) -> bool:
     """True iff `ok` holds on every rank (the ranks must take the same path through a collective)."""
     flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
@@ -245,12 +254,7 @@ def production_table(meas, err, n_draw, tokens, dust, seed, correlated=False, de
     nccl = world > 1 and td.get_backend() == "nccl"
     if nccl and G < world and n_draw >= 262144 and not return_samples and not deterministic:
         # single-object run: fewer galaxies than GPUs, very many samples each -> shard the samples
-        try:
-            import torch.distributed._symmetric_memory  # noqa: F401
-            have = True
-        except ImportError:
-            have = False
-        if _agree(have, device):
+        if _agree(_have_symm(), device):
             out = production_table_sample_sharded(meas, err, n_draw, tokens, dust, seed, correlated=correlated,
                                                   device=device)
             out.pop("kernel_ms", None)
@@ -265,12 +269,7 @@ def production_table(meas, err, n_draw, tokens, dust, seed, correlated=False, de
         hp = _host_path(device)
         gt = hp.gathered.get(G)
         if gt is None:
-            try:
-                import torch.distributed._symmetric_memory  # noqa: F401
-                have = True
-            except ImportError:
-                have = False
-            if _agree(have, device):
+            if _agree(_have_symm(), device):
                 try:
                     gt = GatheredTables(G, device)
                 except RuntimeError as exc:            # peer mapping refused on this rank

@@ -161,3 +161,58 @@ def present_to_bool(present):
     """[G] int64 bit masks -> [G,37] bool tensor."""
     bits = torch.arange(NKEYS, device=present.device, dtype=torch.int64)
     return ((present.unsqueeze(-1) >> bits) & 1).bool()
+
+
+def histogram_assist(Z, bin_numbers):
+    """Z [..., N] f64 (cuda) distributions; bin_numbers: iterable of ints m in [1, 8192] ->
+    (stats [..., 6] f64 = n, min, max, mean, std, sum of the finite values;
+     counts: list with one int32 tensor [..., m] per requested m, equal to
+     np.histogram(data, np.linspace(min(data), max(data), m + 1))[0] of each row's finite values).
+    Replaces the data-parallel inside of savehist's binning (/root/reference/pyMCZ/mcz.py:90-99, 289)."""
+    import ctypes
+    L = _lib.lib()
+    _need_cuda(Z, "Z")
+    if Z.dtype != torch.float64:
+        raise ValueError("Z must be float64")
+    lead = tuple(Z.shape[:-1])
+    N = int(Z.shape[-1])
+    rows = 1
+    for d in lead:
+        rows *= int(d)
+    ms = [int(m) for m in bin_numbers]
+    total = sum(ms)
+    dev = Z.device
+    with torch.cuda.device(dev):
+        stats = torch.empty((rows, 6), dtype=torch.float64, device=dev)
+        counts = torch.empty((rows, max(total, 1)), dtype=torch.int32, device=dev)
+        scratch = torch.empty((max(len(ms), 1),), dtype=torch.int32, device=dev)
+        arr = (ctypes.c_int * max(len(ms), 1))(*ms)
+        rc = L.mcz_histogram_assist(Z.data_ptr(), rows, N, arr, len(ms), stats.data_ptr(), counts.data_ptr(),
+                                    scratch.data_ptr(), _stream_ptr(dev))
+        _lib.check(rc, "mcz_histogram_assist")
+        scratch.record_stream(torch.cuda.current_stream(dev))
+    out, o = [], 0
+    for m in ms:
+        out.append(counts[:, o:o + m].reshape(lead + (m,)))
+        o += m
+    return stats.reshape(lead + (6,)), out
+
+
+def ks_2samp(a, b):
+    """Two-sample Kolmogorov-Smirnov statistic of two 1-D float64 CUDA tensors (finite values, any
+    order): tensor [3] = D (two-sided), D+, D- exactly as scipy.stats.ks_2samp forms them
+    (/root/reference/pyMCZ/testcompleteness.py:111).  The p-value is host work."""
+    L = _lib.lib()
+    _need_cuda(a, "a")
+    _need_cuda(b, "b")
+    if a.dtype != torch.float64 or b.dtype != torch.float64 or a.dim() != 1 or b.dim() != 1:
+        raise ValueError("a, b must be 1-D float64")
+    dev = a.device
+    with torch.cuda.device(dev):
+        out = torch.empty((3,), dtype=torch.float64, device=dev)
+        scratch = torch.empty((2,), dtype=torch.int64, device=dev)
+        rc = L.mcz_ks_2samp(a.data_ptr(), a.numel(), b.data_ptr(), b.numel(), out.data_ptr(), scratch.data_ptr(),
+                            _stream_ptr(dev))
+        _lib.check(rc, "mcz_ks_2samp")
+        scratch.record_stream(torch.cuda.current_stream(dev))
+    return out

@@ -15,7 +15,7 @@ from oracle import mcz_oracle as orc
 from pymcz_b200 import _scales as sc
 from pymcz_b200 import ops
 from pymcz_b200.synth import synthetic_table
-from tests._helpers import oracle_galaxy, production_flux_model, RecordingNormal
+from tests._helpers import oracle_galaxy, kernel_samples, oracle_on_samples, compare_with_oracle
 
 pytestmark = pytest.mark.gpu
 
@@ -35,59 +35,43 @@ def run_prod(meas, err, n_draw, mds="all", dust=True, seed=0xB200, goff=0, corre
     return [o.cpu().numpy() if o is not None else None for o in out]
 
 
-class FixedNoise:
-    """Feeds pre-computed coefficient noise to the oracle in its np.random.normal call order."""
-
-    def __init__(self, noise):
-        self.noise = noise
-        self.toggle = 0
-
-    def __call__(self, loc, scale, size):
-        row = {0.05: 0, 0.1: 1, 0.027: 2, 0.024: 3}.get(scale)
-        if row is None:
-            self.toggle ^= 1
-            return self.noise[4] if self.toggle == 1 else np.zeros(size)
-        return self.noise[row]
-
-
 def oracle_on_kernel_samples(meas, err, n, seed, goff, mds, dust, correlated):
-    G = meas.shape[0]
-    Zo = np.full((G, sc.NKEYS, n), np.nan)
-    po = np.zeros((G, sc.NKEYS), dtype=bool)
-    trips = np.zeros((G, 2), dtype=np.int32)
-    for g in range(G):
-        flux, noise = production_flux_model(meas[g], err[g], seed, goff + g, n, correlated)
-        d, ret, _ = orc.calculation(flux, mds, dust, False, "batched", FixedNoise(noise))
-        trips[g] = (d.trips_n2ha, d.trips_r23)
-        for j, k in enumerate(orc.KEYS):
-            if d.mds[k] is not None:
-                po[g, j] = True
-                Zo[g, j] = d.mds[k]
+    """The oracle (float64) on the kernel's OWN samples: the perturbed fluxes and coefficient noise
+    are read back from the device (mcz_debug_production_samples runs the sampler of phase A, bit
+    for bit), so the comparison is about the arithmetic of the path, not about a host model of the
+    device's Box-Muller."""
+    tok, _, _ = sc.parse_md(mds)
+    flux, noise = kernel_samples(meas, err, n, seed, goff, tok, correlated)
+    Zo, po, trips, _conv = oracle_on_samples(flux, noise, mds, dust)
     return Zo, po, trips
 
 
-@pytest.mark.parametrize("mds,dust,correlated,n", [("all", True, False, 2200), ("all", False, True, 700),
-                                                   ("KD02", True, False, 2304),
-                                                   ("P05,C01,P01,DP00,D16,M08all,all", True, False, 1000)])
-def test_per_sample_values_vs_oracle(mds, dust, correlated, n):
-    sm, se = synthetic_table(40, config=4)
+@pytest.mark.parametrize("mds,dust,correlated,n,ngal",
+                         [("all", True, False, 2200, 2400), ("all", False, True, 700, 600),
+                          ("KD02", True, False, 2304, 1000),
+                          ("P05,C01,P01,DP00,D16,M08all,all", True, False, 1000, 400)])
+def test_per_sample_values_vs_oracle(mds, dust, correlated, n, ngal):
+    sm, se = synthetic_table(ngal, config=4)
     meas, err = np.concatenate([EX_M, sm]), np.concatenate([EX_E, se])
     seed, goff = 0x1234ABCD5678, 1000
     pct, nvalid, status, trips, ret, Z = run_prod(meas, err, n, mds, dust, seed, goff, correlated)
     Zo, po, trips_o = oracle_on_kernel_samples(meas, err, n, seed, goff, mds, dust, correlated)
-    pres = status != sc.ST_ABSENT
-    assert np.array_equal(pres, po)
-    same = np.all(trips == trips_o, axis=1)
-    assert same.mean() >= 0.95, (trips[~same], trips_o[~same])
-    Zs, Zos = Z[same].astype(np.float64), Zo[same]
-    nan_mism = np.sum(np.isnan(Zs) != np.isnan(Zos))
-    assert nan_mism <= 5e-5 * Zs.size + 2, nan_mism
-    both = np.isfinite(Zs) & np.isfinite(Zos)
-    d = np.abs(Zs[both] - Zos[both])
-    # the device normals differ from the float64 model by MUFU rounding (~1e-6 sigma): values agree
-    # far inside the 1e-3 dex bar except where a branch choice flips on such a rounding
-    assert np.mean(d > 1e-3) < 1e-4, (np.mean(d > 1e-3), d.max())
-    assert np.median(d) < 2e-5
+    compare_with_oracle(Z, status, trips, Zo, po, trips_o, what="%s dust=%s corr=%s n=%d" % (mds, dust, correlated, n))
+
+
+def test_kernel_sample_export_is_the_kernels_stream():
+    """The sampler entry point used by the parity tests really is phase A's sampler: E(B-V) recomputed
+    in float64 from the exported Ha/Hb samples equals the production kernel's E(B-V) column."""
+    meas, err = synthetic_table(50, config=4)
+    pct, nvalid, status, trips, ret, Z = run_prod(meas, err, 900, "all", True, 99, 5)
+    flux, noise = kernel_samples(meas, err, 900, 99, 5, sc.T_ALL)
+    with np.errstate(all="ignore"):
+        E = np.log10(2.86 * flux[:, 1] / flux[:, 5]) / (0.4 * (orc.k_Ha - orc.k_Hb))      # metscales.py:389
+    E[E <= 0] = 1e-5
+    assert np.allclose(Z[:, sc.KEY_INDEX["E(B-V)"]], E, rtol=0, atol=2e-6)
+    # and it is a float32 stream: exporting twice gives the same bits
+    flux2, _ = kernel_samples(meas, err, 900, 99, 5, sc.T_ALL)
+    assert np.array_equal(flux, flux2)
 
 
 @pytest.mark.parametrize("ngal", [30, 700])
@@ -215,22 +199,18 @@ def test_flag_fallback_and_missing_lines():
     assert np.array_equal(status != sc.ST_ABSENT, po)
     assert np.array_equal(trips, trips_o)
     nan_mism = np.sum(np.isnan(Z) != np.isnan(Zo))
-    assert nan_mism <= 3
+    assert nan_mism <= 1
     both = np.isfinite(Z) & np.isfinite(Zo)
-    assert np.mean(np.abs(Z[both] - Zo[both]) > 1e-3) < 1e-3
+    assert np.max(np.abs(Z[both] - Zo[both])) < 1e-3
 
 
 def test_large_nsample_global_variant():
     """N' = 11000 (configs 3/5 shape) runs the global-scratch instantiation."""
-    meas, err = synthetic_table(6, config=3)
+    meas, err = synthetic_table(100, config=3)
     n = 11000
     pct, nvalid, status, trips, ret, Z = run_prod(meas, err, n, seed=5, goff=0)
     Zo, po, trips_o = oracle_on_kernel_samples(meas, err, n, 5, 0, "all", True, False)
-    assert np.array_equal(status != sc.ST_ABSENT, po)
-    same = np.all(trips == trips_o, axis=1)
-    assert same.all()
-    both = np.isfinite(Z) & np.isfinite(Zo)
-    assert np.mean(np.abs(Z[both] - Zo[both]) > 1e-3) < 1e-4
+    compare_with_oracle(Z, status, trips, Zo, po, trips_o, what="N'=11000")
     for g in range(meas.shape[0]):
         for j in range(sc.NKEYS):
             if status[g, j] == sc.ST_OK:
@@ -274,21 +254,43 @@ def test_host_buffer_entry_point(ngal, n):
     assert np.array_equal(nvalid, ref[1]) and np.array_equal(status, ref[2]) and np.array_equal(trips, ref[3])
 
 
-@pytest.mark.parametrize("ngal,n,min_capped", [(360, 440, 10), (150, 2400, 4)])   # shared / global-scratch variant
-def test_divergent_galaxies_match_reference_cap(ngal, n, min_capped):
-    """The kernel ends an N2Ha loop early when it can PROVE non-convergence (elliptic Moebius
-    maps: mean |dlogq| bounded below by more than the tolerance) and reports the reference's
-    outcome: 100 trips, galaxy blanked (metscales.py:1119-1121).  Every such galaxy must be a
-    100-trip galaxy in the oracle, and every 100-trip galaxy of the oracle must be capped here."""
+@pytest.mark.parametrize("ngal,n,min_capped", [(1200, 440, 40), (150, 2400, 4)])   # shared / global-scratch variant
+def test_capped_galaxies_match_reference_cap(ngal, n, min_capped):
+    """The kernel ends a KK04 loop early when the outcome is decided: an N2Ha loop whose elliptic
+    Moebius maps keep mean |dlogq| above the tolerance by a proven bound, and an R23 loop whose state
+    has become exactly periodic with both trips of the period above the tolerance.  It then reports
+    the reference's outcome: 100 trips, galaxy blanked (metscales.py:1119-1121, 1179-1181).  The set of
+    100-trip galaxies must be the oracle's, for both loops (one marginal galaxy may differ, see
+    compare_with_oracle), and the launch statistics must show that trips were indeed saved."""
+    import ctypes
+    from pymcz_b200 import _lib
     meas, err = synthetic_table(ngal, config=4)
     seed = 0xD1CE
-    pct, nvalid, status, trips, ret, Z = run_prod(meas, err, n, "KD02", True, seed, 0, False)
+    tok, _, _ = sc.parse_md("KD02")
+    ws = ops.ProductionWorkspace(ngal, n, tok, torch.device("cuda"), True)
+    out = ops.forward_production(torch.from_numpy(meas).cuda(), torch.from_numpy(err).cuda(), n, tok, sc.DUST_ON,
+                                 seed, 0, False, False, True, workspace=ws)
+    torch.cuda.synchronize()
+    st8 = (ctypes.c_ulonglong * 8)()
+    _lib.check(_lib.lib().mcz_production_last_stats(ws.scratch.data_ptr(), st8, None), "stats")
+    pct, nvalid, status, trips, ret, Z = [o.cpu().numpy() for o in out]
     Zo, po, trips_o = oracle_on_kernel_samples(meas, err, n, seed, 0, "KD02", True, False)
-    capped, capped_o = trips[:, 0] >= 100, trips_o[:, 0] >= 100
-    assert capped_o.sum() >= min_capped              # the table does contain divergent galaxies
-    assert np.array_equal(capped, capped_o), (np.nonzero(capped != capped_o), trips[capped != capped_o], trips_o[capped != capped_o])
-    j = sc.KEY_INDEX["KK04_N2Ha"]
-    assert np.all(np.isnan(Z[capped, j])) and np.all(status[capped, j] == sc.ST_EMPTY)
-    # galaxies that are not capped keep the oracle's trip counts (float32 vs float64 decisions)
-    same = trips[~capped] == trips_o[~capped]
-    assert same.mean() > 0.97
+    for k, key in ((0, "KK04_N2Ha"), (1, "KK04_R23")):
+        capped, capped_o = trips[:, k] >= 100, trips_o[:, k] >= 100
+        if k == 0:
+            assert capped_o.sum() >= min_capped              # the table does contain divergent galaxies
+        diff = np.nonzero(capped != capped_o)[0]
+        assert len(diff) <= 1, (key, diff, trips[diff], trips_o[diff])
+        for g in diff:
+            assert min(trips[g, k], trips_o[g, k]) >= 9
+        j = sc.KEY_INDEX[key]
+        assert np.all(np.isnan(Z[capped, j])) and np.all(status[capped, j] == sc.ST_EMPTY)
+    same = np.all(trips == trips_o, axis=1)
+    assert same.mean() >= 0.995, (trips[~same], trips_o[~same])
+    assert st8[0] == ngal
+    # executed trips never exceed reported trips; with capped galaxies in the table some were saved
+    assert st8[1] <= trips[:, 0].sum() and st8[2] <= trips[:, 1].sum()
+    if n <= 2304:
+        assert st8[3] > 0 and st8[1] < trips[:, 0].sum()
+        if (trips_o[:, 1] >= 100).sum() >= 5:
+            assert st8[4] > 0 and st8[2] < trips[:, 1].sum()

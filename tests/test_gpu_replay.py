@@ -76,19 +76,26 @@ def test_replay_f64_matches_oracle(case):
 
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
 def test_replay_f32_production_arithmetic(case):
-    """The float32 (production) instantiation on the reference's samples: values within 1e-3 dex;
-    a sample whose ratio sits within float rounding of a validity threshold may flip its mask."""
+    """The float32 (production) instantiation against the oracle on the SAME float32-representable
+    samples (the reference's numpy draws rounded to float32, as the production sampler's are): trip
+    counts identical, every galaxy included in the 1e-3 dex bar; a sample whose ratio sits within
+    float rounding of a validity threshold may flip its mask (counted, bounded)."""
+    from tests._helpers import oracle_on_samples
     _, meas, err, nsample, seed, mode, mds, dust = case
-    flux, noise, Zo, po, trips_o, rets_o = oracle_table(meas, err, nsample, seed, mode, mds, dust)
+    flux, noise, _, _, _, rets_o = oracle_table(meas, err, nsample, seed, mode, mds, dust)
+    flux = flux.astype(np.float32).astype(np.float64)
+    noise = noise.astype(np.float32).astype(np.float64)
+    Zo, po, trips_o, _ = oracle_on_samples(np.ascontiguousarray(flux.transpose(1, 0, 2)),
+                                           np.ascontiguousarray(noise.transpose(1, 0, 2)), mds, dust, procs=1)
     Z, pm, trips, ret = gpu_replay(flux, noise, mds, dust, "f32")
     assert np.array_equal(ret, rets_o)
     assert np.array_equal(pm, po)
-    same_trips = np.all(trips == trips_o, axis=1)
-    assert same_trips.mean() > 0.97
-    nan_mism = np.sum(np.isnan(Z[same_trips]) != np.isnan(Zo[same_trips]))
-    assert nan_mism <= 2e-5 * Z[same_trips].size + 2, nan_mism
-    both = np.isfinite(Z) & np.isfinite(Zo) & same_trips[:, None, None]
+    assert np.array_equal(trips, trips_o)
+    nan_mism = int(np.sum(np.isnan(Z) != np.isnan(Zo)))
+    assert nan_mism <= 1e-5 * Z.size + 1, nan_mism
+    both = np.isfinite(Z) & np.isfinite(Zo)
     assert np.max(np.abs(Z[both] - Zo[both])) < 1e-3
+    print(case[0], "mask flips:", nan_mism, "of", Z.size, "max |dZ|:", float(np.max(np.abs(Z[both] - Zo[both]))))
 
 
 def test_replay_golden_fixtures_from_reference(golden_dir):

@@ -72,6 +72,30 @@ def test_wide_kernel_equals_per_galaxy_kernel(n, mds):
     assert np.allclose(a[:, it], b[:, it], rtol=0, atol=4e-6, equal_nan=True), np.nanmax(np.abs(a[:, it] - b[:, it]))
 
 
+@pytest.mark.parametrize("n,ngal,mds", [(40000, 24, "all"), (150000, 6, "all"), (33000, 40, "KD02")])
+def test_wide_kernel_vs_oracle(n, ngal, mds):
+    """The wide kernel against the ORACLE on the kernel's own samples (read back from the device):
+    present table, trip counts, NaN masks and per-sample values to the same bar as the per-galaxy
+    kernel (tests/_helpers.py::compare_with_oracle), and its percentile table against numpy on its
+    own float32 columns."""
+    from tests._helpers import kernel_samples, oracle_on_samples, compare_with_oracle
+    meas, err = tables()
+    sm, se = synthetic_table(max(ngal, 1), config=4)
+    meas, err = np.concatenate([meas[:10], sm])[:ngal], np.concatenate([err[:10], se])[:ngal]
+    tok = sc.parse_md(mds)[0]
+    wid = run(meas, err, n, tok, wide=True, samples=True)
+    pct, nvalid, status, trips, ret, Z = wid
+    flux, noise = kernel_samples(meas, err, n, 0xB200, 3, tok)
+    Zo, po, trips_o, _ = oracle_on_samples(flux, noise, mds, True)
+    compare_with_oracle(Z, status, trips, Zo, po, trips_o, what="wide n=%d %s" % (n, mds))
+    for g in range(meas.shape[0]):
+        for j in range(sc.NKEYS):
+            if status[g, j] == sc.ST_OK:
+                fin = Z[g, j][np.isfinite(Z[g, j])]
+                want = np.percentile(fin.astype(np.float64), [50, 16, 84]).astype(np.float32)
+                assert np.array_equal(pct[g, j], want), (g, sc.KEYS[j])
+
+
 def test_wide_kernel_per_sample_output():
     """Z[G,37,N'] (pickle / --asciidistrib product) from the wide kernel equals the per-galaxy kernel's,
     bit for bit outside the KK04 iteration."""

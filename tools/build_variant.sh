@@ -8,5 +8,5 @@ tag=$1; shift
 mkdir -p dbgbuild
 nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC --expt-relaxed-constexpr "$@" \
   -shared -o dbgbuild/libmcz_$tag.so pymcz_b200/csrc/mcz_abi.cu pymcz_b200/csrc/mcz_replay.cu \
-  pymcz_b200/csrc/mcz_percentiles.cu pymcz_b200/csrc/mcz_production.cu -lcudart
+  pymcz_b200/csrc/mcz_percentiles.cu pymcz_b200/csrc/mcz_production.cu pymcz_b200/csrc/mcz_histassist.cu -lcudart
 echo built dbgbuild/libmcz_$tag.so
