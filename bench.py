@@ -456,6 +456,7 @@ def run_ours(args):
             nps = reference_pool_size()
             kind = _ref_kind()
             # size the sample for ~15 s from a one-measurement probe
+            cpu_reference_run(1, cfg, args.config, 1, kind=kind)            # (imports, first-call costs)
             _, dt1 = cpu_reference_run(1, cfg, args.config, 1, kind=kind)
             Gc = int(max(nps, min(64 * nps, round(15.0 / max(dt1, 1e-3) * nps))))
             v, dt = cpu_reference_run(Gc, cfg, args.config, nps, kind=kind)

@@ -66,24 +66,42 @@ class KnuthTable:
         return mk, 0
 
 
-def ks_table(x_list):
-    """Two-sample KS statistics D between consecutive samples of ``x_list`` (1-D arrays), as the
-    reference's diagnostic compares each sub-sample with the previous one
-    (testcompleteness.py:87-113).  Returns a list of (D, p) with p from scipy's distribution code
-    on the host."""
+def ks_2samp(x, y):
+    """scipy.stats.ks_2samp(x, y) as the reference calls it (default two-sided, method 'auto';
+    testcompleteness.py:111) with the statistic from the GPU: returns (D, p).
+
+    The device gives max |F_x - F_y| over all data points, formed as scipy forms it.  scipy's 'exact'
+    branch (taken when max(n1, n2) <= 10000) counts lattice paths for p; for larger samples it uses the asymptotic Kolmogorov distribution.
+    Both are scalar host work and are taken from scipy itself."""
+    import math
     import torch
     from scipy import stats
     from . import ops
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    d = float(ops.ks_2samp(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda())[0].item())
+    n1, n2 = len(x), len(y)
+    if max(n1, n2) <= 10000:                       # scipy's MAX_AUTO_N
+        try:
+            from scipy.stats._stats_py import _attempt_exact_2kssamp
+            g = math.gcd(n1, n2)
+            success, _d_lattice, p = _attempt_exact_2kssamp(n1, n2, g, d, 'two-sided')
+            if success:
+                return d, float(np.clip(p, 0, 1))
+        except ImportError:
+            pass
+    m, n = sorted([float(n1), float(n2)], reverse=True)
+    en = m * n / (m + n)
+    return d, float(np.clip(stats.distributions.kstwo.sf(d, np.round(en)), 0, 1))
+
+
+def ks_table(x_list):
+    """(D, p) between consecutive samples of ``x_list`` (1-D arrays), as the reference's diagnostic
+    compares each sub-sample with the previous one (testcompleteness.py:87-113)."""
     out = []
     prev = None
     for x in x_list:
-        x = np.ascontiguousarray(x, dtype=np.float64)
         if prev is not None:
-            d = ops.ks_2samp(torch.from_numpy(x).cuda(), torch.from_numpy(prev).cuda()).cpu().numpy()
-            n1, n2 = len(x), len(prev)
-            # the p-value scipy's 'asymp' method reports for this D (host; special functions)
-            en = n1 * n2 / (n1 + n2)
-            p = float(stats.distributions.kstwo.sf(d[0], np.round(en)))
-            out.append((float(d[0]), p))
+            out.append(ks_2samp(x, prev))
         prev = x
     return out

@@ -130,8 +130,8 @@ int launch_histogram_assist(const double* Z_d, long long rows, long long N, cons
 }
 
 // ---- two-sample Kolmogorov-Smirnov statistic --------------------------------------------------
-// scipy.stats.ks_2samp: data_all = concat(sort(a), sort(b)); cdf1 = searchsorted(a, data_all, 'right') / n1,
-// cdf2 likewise; cddiffs = cdf1 - cdf2; minS = clip(-min(cddiffs), 0, 1), maxS = max(cddiffs),
+// scipy.stats.ks_2samp: data_all = concat(sort(a), sort(b)); cdf1 = ECDF of a at every pooled point
+// (#{a <= v} steps of 1 / n1), cdf2 likewise; cddiffs = cdf1 - cdf2; minS = clip(-min(cddiffs), 0, 1), maxS = max(cddiffs),
 // D = max(minS, maxS).  The counts #{a <= v}, #{b <= v} need no sort: every thread takes one data
 // point v and scans both samples (all threads of a warp read the same element: one broadcast load
 // per 32 comparisons).  out[0] = min(cddiffs), out[1] = max(cddiffs) as ordered 64-bit keys.
@@ -154,7 +154,11 @@ ks_counts_kernel(const double* __restrict__ a, long long n1, const double* __res
     long long c1 = 0, c2 = 0;
     for (long long j = 0; j < n1; ++j) c1 += (a[j] <= v) ? 1 : 0;
     for (long long j = 0; j < n2; ++j) c2 += (b[j] <= v) ? 1 : 0;
-    const double d = (double)c1 / (double)n1 - (double)c2 / (double)n2;
+    // ECDF values as scipy >= 1.12 forms them: np.linspace(0, 1, n + 1)[count] = count * (1 / n), last = 1
+    // (older scipy divided count / n: at most one ulp away)
+    const double f1 = c1 >= n1 ? 1.0 : __dmul_rn((double)c1, 1.0 / (double)n1);
+    const double f2 = c2 >= n2 ? 1.0 : __dmul_rn((double)c2, 1.0 / (double)n2);
+    const double d = f1 - f2;
     dmin = d; dmax = d;
   }
 #pragma unroll

@@ -78,7 +78,7 @@ struct Ctrl {
   int any_valid_kd;
   float line[2 * NLINES];
   float2 redf[2 * PW];
-  long long acc[3][4];     // fixed-point block sums: two KK04 convergence measures x two trips per barrier
+  int acc[3][4];           // fixed-point block sums: two KK04 convergence measures x two trips per barrier
   unsigned chg[3];         // some sample's R23 loop state changed over the batch (rotates with acc)
 };
 static_assert(sizeof(Ctrl) <= CTRL_BYTES, "control block too large");
@@ -118,7 +118,9 @@ __device__ __forceinline__ void block_sum2f(float& a, float& c, float2* buf, int
 // Block-wide sums of the convergence measures in fixed point with FX_BITS fractional bits: the
 // thread's partial sum (<= 4 samples, each clamped to +-8 by the caller, which cannot change the
 // outcome of "mean > tol" since tol * N < 8) is rounded to 2^-FX_BITS, one REDUX per warp
-// (|warp total| <= 32 * 32 * 2^20 = 2^30), one 64-bit shared atomic per warp, and a single barrier
+// (|warp total| <= 128 * 8 * 2^20 = 2^30), the warp total clamped to +-64 (2^26: only a warp whose
+// samples are nowhere near convergence gets there, and 18 such totals still fit 32 bits), one
+// 32-bit shared atomic per warp (a 64-bit shared atomicAdd is a CAS loop), and a single barrier
 // that also ORs the NaN flags (BAR.RED.OR).  The rounding error of the block total is ~7 quanta
 // (7e-6 at 20 bits, against thresholds tol * N of 0.22 and 2.2): below the float32 rounding of the
 // per-sample terms themselves, so the integer total is an order-independent, deterministic
@@ -127,9 +129,10 @@ __device__ __forceinline__ void block_sum2f(float& a, float& c, float2* buf, int
 #define MCZ_FX_BITS 20
 #endif
 static constexpr float FX_SCALE = (float)(1 << MCZ_FX_BITS);
-typedef long long fx_t;
+static constexpr int FX_WARP_CLAMP = 64 << MCZ_FX_BITS;
+typedef int fx_t;
 __device__ __forceinline__ void fx_add(fx_t* a, int q) {
-  atomicAdd(reinterpret_cast<unsigned long long*>(a), (unsigned long long)(long long)q);
+  atomicAdd(a, max(-FX_WARP_CLAMP, min(FX_WARP_CLAMP, q)));
 }
 __device__ __forceinline__ void block_sum2_fx(float s1, float s2, bool nan, Ctrl* ctrl, int& ph,
                                               fx_t& t1, fx_t& t2, bool& anynan) {

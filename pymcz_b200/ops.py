@@ -93,6 +93,8 @@ class ProductionWorkspace:
         L = _lib.lib()
         self.G, self.n_draw, self.tokens = int(G), int(n_draw), int(tokens)
         self.device = torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         with torch.cuda.device(self.device):
             d = self.device
             self.pct = torch.empty((G, NKEYS, 3), dtype=torch.float32, device=d)

@@ -53,7 +53,7 @@ def test_counts_equal_np_histogram_on_linspace_edges():
             want, _ = np.histogram(data, np.linspace(min(data), max(data), m + 1))     # mcz.py:94-96
             assert np.array_equal(c[r], want), (r, m)
             checked += 1
-    assert checked > 1000
+    assert checked > 500
 
 
 def _ref_knuthn(data):
@@ -106,12 +106,15 @@ def test_ks_statistic_equals_scipy():
              (np.array([1.0]), np.array([2.0, 3.0]))]
     for a, b in cases:
         got = ops.ks_2samp(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()).cpu().numpy()
-        want = stats.ks_2samp(a, b)
+        want = stats.ks_2samp(a, b, method="asymp")            # (the raw statistic: 'exact' re-rounds it)
         assert got[0] == want.statistic, (got, want)
+        D, p = binning.ks_2samp(a, b)                          # the call the reference makes (method 'auto')
+        w = stats.ks_2samp(a, b)
+        assert D == w.statistic and abs(p - w.pvalue) <= 1e-9 * w.pvalue + 1e-300, (D, p, w)
     # the nested sub-sample table of testcompleteness.py:87-113
     x = rs.normal(8.7, 0.1, 22000)
     subs = [np.sort(rs.choice(x, int(f * x.size), replace=False)) for f in (0.1, 0.25, 0.5, 0.75, 1)]
     tab = binning.ks_table(subs)
     for (D, p), (xa, xb) in zip(tab, zip(subs[1:], subs[:-1])):
-        w = stats.ks_2samp(xa, xb, method="asymp")
-        assert D == w.statistic and abs(p - w.pvalue) <= 1e-9 * max(w.pvalue, 1e-300) + 1e-12
+        w = stats.ks_2samp(xa, xb)
+        assert D == w.statistic and abs(p - w.pvalue) <= 1e-9 * w.pvalue + 1e-300
