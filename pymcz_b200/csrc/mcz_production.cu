@@ -19,6 +19,7 @@
 #include <string.h>
 #include <cooperative_groups.h>
 #include <atomic>
+#include <type_traits>
 #include "mcz_physics.cuh"
 #include "mcz_philox.cuh"
 #include "mcz_device_utils.cuh"
@@ -100,6 +101,22 @@ __device__ __forceinline__ void draw_normals(uint32_t s, unsigned long long gg, 
   }
 }
 
+// the same with the set of Philox calls known at compile time
+template <uint32_t CALLS>
+__device__ __forceinline__ void draw_normals_c(uint32_t s, unsigned long long gg, const ProdParams& p, float z[16]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    if (CALLS & (1u << c)) {
+      uint32_t o[4];
+      philox4x32_10(s, (uint32_t)c, (uint32_t)gg, (uint32_t)(gg >> 32), p.seed_lo, p.seed_hi, o);
+      box_muller(o[0], o[1], z[4 * c + 0], z[4 * c + 1]);
+      box_muller(o[2], o[3], z[4 * c + 2], z[4 * c + 3]);
+    } else {
+      z[4 * c + 0] = z[4 * c + 1] = z[4 * c + 2] = z[4 * c + 3] = 0.0f;
+    }
+  }
+}
+
 // Block-wide sums of two floats, every thread gets both totals (NaN propagates); one barrier per
 // call thanks to the alternating buffer.
 __device__ __forceinline__ void block_sum2f(float& a, float& c, float2* buf, int& phase) {
@@ -125,6 +142,10 @@ __device__ __forceinline__ void block_sum2f(float& a, float& c, float2* buf, int
 // (7e-6 at 20 bits, against thresholds tol * N of 0.22 and 2.2): below the float32 rounding of the
 // per-sample terms themselves, so the integer total is an order-independent, deterministic
 // stand-in for the reference's float64 mean (metscales.py:1117, 1177).
+#ifndef MCZ_A_UNROLL
+#define MCZ_A_UNROLL 1
+#endif
+static constexpr int A_UNROLL = MCZ_A_UNROLL;     // samples of a thread evaluated side by side in phase A
 #ifndef MCZ_FX_BITS
 #define MCZ_FX_BITS 20
 #endif
@@ -322,41 +343,59 @@ production_kernel(const __grid_constant__ ProdParams p) {
     for (;;) {
       const int de = effective_dust(p.dust, flags);
       uint32_t seen = 0u;
-#pragma unroll 1
-      for (int i = 0; i < nsl; ++i) {
-        const int s = i * PT + tid;
-        if (s < N) {
-          float z[16];
-          draw_normals((uint32_t)s, gg, p, z);
-          float f[NUSED], e[5];
+      // The line flags, the token mask, the dust mode and the sampling mode are the same for every
+      // sample of the galaxy, but phase_a tests them per sample (about forty uniform branches).  The
+      // two launch shapes that matter for throughput -- every line measured, dust on, independent
+      // sampling, `--md all` or `--md KD02` -- get a copy of the loop with those values as
+      // compile-time constants: straight-line code, identical arithmetic.
+      const uint32_t need = F_ALL & ~F_S39069;      // [SIII]9069 only matters for DP00
+      const bool full = (flags & need) == need && de == 0 && !p.correlated && !p.deterministic;
+      auto pass = [&](auto mode_tag) {
+        constexpr int MODE = decltype(mode_tag)::value;      // 0 generic, 1 --md all, 2 --md KD02
+        const uint32_t fl = MODE ? (uint32_t)F_ALL : flags;
+        const uint32_t tk = MODE == 1 ? (uint32_t)T_ALL : (MODE == 2 ? (uint32_t)T_KD02 : p.tok);
+        const int dm = MODE ? 0 : de;
+#pragma unroll A_UNROLL
+        for (int i = 0; i < nsl; ++i) {
+          const int s = i * PT + tid;
+          if (s < N) {
+            float z[16];
+            if (MODE == 1) draw_normals_c<7u>((uint32_t)s, gg, p, z);
+            else if (MODE == 2) draw_normals_c<6u>((uint32_t)s, gg, p, z);
+            else draw_normals((uint32_t)s, gg, p, z);
+            float f[NUSED], e[5];
 #pragma unroll
-          for (int u = 0; u < NUSED; ++u) {
-            float v = fmaf(le[u], p.correlated ? z[5] : z[5 + u], lm[u]);          // mcz.py:442 / :589
-            v = fmaxf(v, 0.0f);                       // NaN -> 0 and negative -> 0 (metallicity.py:96, 99)
-            if (!(v <= FLT_MAX)) v = 0.0f;            // +inf -> 0 (metallicity.py:96)
-            f[u] = v;
-            const bool pos = (u >= U_S2B) ? (v > 1e-9f) : (v > 0.0f);
-            if (pos) seen |= 1u << u;
+            for (int u = 0; u < NUSED; ++u) {
+              float v = fmaf(le[u], (!MODE && p.correlated) ? z[5] : z[5 + u], lm[u]);   // mcz.py:442 / :589
+              v = fmaxf(v, 0.0f);                       // NaN -> 0 and negative -> 0 (metallicity.py:96, 99)
+              if (!(v <= FLT_MAX)) v = 0.0f;            // +inf -> 0 (metallicity.py:96)
+              f[u] = v;
+              const bool pos = (u >= U_S2B) ? (v > 1e-9f) : (v > 0.0f);
+              if (pos) seen |= 1u << u;
+            }
+            e[0] = 0.05f * z[0];            // metscales.py:679
+            e[1] = 0.1f * z[1];             // metscales.py:680
+            e[2] = 0.027f * z[2];           // metscales.py:948
+            e[3] = 0.024f * z[3];           // metscales.py:949
+            e[4] = 0.012f * z[4];           // metscales.py:952
+            SlotPut<!GLOBAL> put{vals + s, p.col_off, vals_sa + 4u * (unsigned)s};
+            Carry<float> c;
+            c.y = c.n2ha = c.x = 0.0f;
+            c.aux = 0u;
+            phase_a<float>(f, e, fl, tk, dm, put, c);
+            if (c.aux & AUX_KD_VALID) seen |= SEEN_KD;
+            store_f32<!GLOBAL>(st0 + s, st0_sa + 4u * (unsigned)s, c.y);
+            store_f32<!GLOBAL>(st1 + s, st1_sa + 4u * (unsigned)s, c.n2ha);
+            store_f32<!GLOBAL>(st2 + s, st2_sa + 4u * (unsigned)s, c.x);
+            store_f32<!GLOBAL>(st3 + s, st3_sa + 4u * (unsigned)s, __uint_as_float(c.aux));
+          } else if (s < Npad) {
+            for (int sl = 0; sl < p.nstore; ++sl) vals[(long long)sl * Npad + s] = Math<float>::nan();
           }
-          e[0] = 0.05f * z[0];            // metscales.py:679
-          e[1] = 0.1f * z[1];             // metscales.py:680
-          e[2] = 0.027f * z[2];           // metscales.py:948
-          e[3] = 0.024f * z[3];           // metscales.py:949
-          e[4] = 0.012f * z[4];           // metscales.py:952
-          SlotPut<!GLOBAL> put{vals + s, p.col_off, vals_sa + 4u * (unsigned)s};
-          Carry<float> c;
-          c.y = c.n2ha = c.x = 0.0f;
-          c.aux = 0u;
-          phase_a<float>(f, e, flags, p.tok, de, put, c);
-          if (c.aux & AUX_KD_VALID) seen |= SEEN_KD;
-          store_f32<!GLOBAL>(st0 + s, st0_sa + 4u * (unsigned)s, c.y);
-          store_f32<!GLOBAL>(st1 + s, st1_sa + 4u * (unsigned)s, c.n2ha);
-          store_f32<!GLOBAL>(st2 + s, st2_sa + 4u * (unsigned)s, c.x);
-          store_f32<!GLOBAL>(st3 + s, st3_sa + 4u * (unsigned)s, __uint_as_float(c.aux));
-        } else if (s < Npad) {
-          for (int sl = 0; sl < p.nstore; ++sl) vals[(long long)sl * Npad + s] = Math<float>::nan();
         }
-      }
+      };
+      if (full && p.tok == T_ALL && p.calls == 7u) pass(std::integral_constant<int, 1>());
+      else if (full && p.tok == T_KD02 && p.calls == 6u) pass(std::integral_constant<int, 2>());
+      else pass(std::integral_constant<int, 0>());
       seen = __reduce_or_sync(0xffffffffu, seen);
       if (lane == 0 && seen) atomicOr(&ctrl->flags, seen);
       __syncthreads();

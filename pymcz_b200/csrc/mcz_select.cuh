@@ -46,7 +46,9 @@ static constexpr int FB = 1024;     // fine-index bins per round
 // samples); otherwise 1024 32-bit words.
 template <bool PACK16> struct FineHist {
   static constexpr int WORDS = PACK16 ? FB / 2 : FB;
-  static constexpr int BYTES = WORDS * 4;
+  // + 32 spare words, one per lane: the streaming pass sends the increment of a sample that must not
+  // be counted (NaN, inf, padding) there instead of making the atomic conditional
+  static constexpr int BYTES = WORDS * 4 + 128;
   static __device__ __forceinline__ void zero(unsigned* h, int lane) {
 #pragma unroll
     for (int i = 0; i < WORDS / 32; ++i) h[i * 32 + lane] = 0u;
@@ -59,8 +61,33 @@ template <bool PACK16> struct FineHist {
   // branch-free form for the streaming pass: a sample that is not counted adds 0 to a word of
   // its lane's own bank, so the four samples of a 128-bit load keep independent instruction chains
   static __device__ __forceinline__ void add_if(unsigned* h, int f, bool ok, int lane) {
+#ifdef MCZ_PRED_ATOMS
+    // a PREDICATED shared reduction (no branch, no redirected address): the byte address of the word
+    // is 2 * (f & ~1), the increment 1 or 65536 by the parity of the bin
+    (void)lane;
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(h) + (PACK16 ? 2u * ((unsigned)f & ~1u) : 4u * (unsigned)f);
+    const unsigned val = PACK16 ? 1u + ((unsigned)f & 1u) * 65535u : 1u;
+    asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p red.shared.add.u32 [%0], %1; }"
+                 :: "r"(addr), "r"(val), "r"((unsigned)ok) : "memory");
+#else
     if (PACK16) atomicAdd(h + (ok ? (f >> 1) : lane), ok ? (1u << ((f & 1) << 4)) : 0u);
     else atomicAdd(h + (ok ? f : lane), ok ? 1u : 0u);
+#endif
+  }
+  // the same on the raw index bits (fine_tbits) and 32-bit shared addresses: `hs` = address of the
+  // table, `ls` = address of the lane's own word (a sample that is not counted adds 0 there)
+  static __device__ __forceinline__ void add_t(unsigned hs, unsigned ls, int tb, bool ok) {
+    unsigned addr, val;
+    if (PACK16) {
+      addr = hs + 2u * ((unsigned)tb & (unsigned)(FB - 2));        // word (bin >> 1): byte offset 2 * (bin & ~1)
+      // low or high 16-bit counter: 1 + parity * 65535, as a multiply-add (FMA pipe, not compare + select)
+      asm("mad.lo.u32 %0, %1, 65535, 1;" : "=r"(val) : "r"((unsigned)tb & 1u));
+    } else {
+      addr = hs + 4u * ((unsigned)tb & (unsigned)(FB - 1));
+      val = 1u;
+    }
+    addr = ok ? addr : ls;                                         // ls: the lane's spare word
+    asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(addr), "r"(val) : "memory");
   }
   static __device__ __forceinline__ void add_n(unsigned* h, int f, unsigned n) {      // n < 65536 when PACK16
     if (PACK16) atomicAdd(h + (f >> 1), n << ((f & 1) << 4));
@@ -149,12 +176,20 @@ struct SelWarp {
 #endif
 };
 
-// Monotone map of a value to a bin of [0, FB): round(x * scale + nLs), clamped.  The 2^23 bias
-// makes the FMA itself round to an integer that sits in the float's low mantissa bits, so no
-// float-to-int conversion (a quarter-rate instruction) is needed.  NaN maps to bin 0.
+// Monotone map of a value to a bin of [0, FB): u = saturate(x * scale + nLs) in [0, 1] (one FFMA.SAT:
+// it clamps AND sends NaN to 0), then round(u * (FB - 1)) read from the mantissa of a 2^23-biased
+// FMA.  Two instructions on the FMA pipe -- no FMNMX clamps, no float-to-int conversion: the
+// streaming passes of the selection are bound by the ALU pipe (integer, compare, min/max, select
+// instructions issue at half the FMA rate), so work is moved off it wherever it can be.
+// fine_tbits() returns the raw bits 0x4B000000 + bin; the callers mask or compare them as they are.
+static constexpr int FINE_BIAS = 0x4B000000;
+__device__ __forceinline__ int fine_tbits(float x, float scale, float nLs) {
+  float u;
+  asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(u) : "f"(x), "f"(scale), "f"(nLs));
+  return __float_as_int(fmaf(u, (float)(FB - 1), 8388608.0f));
+}
 __device__ __forceinline__ int fine_index(float x, float scale, float nLs) {
-  const float t = fminf(fmaxf(fmaf(x, scale, nLs + 8388608.0f), 8388608.0f), 8388608.0f + (float)(FB - 1));
-  return __float_as_int(t) - 0x4B000000;
+  return fine_tbits(x, scale, nLs) - FINE_BIAS;
 }
 
 // After pass H: every lane gets its exclusive prefix over lanes (32 bins per lane) and its total.
@@ -422,9 +457,9 @@ __device__ __forceinline__ bool subsample_range(const float* __restrict__ v, int
     L = fmaxf(L, pmin - d);
     H = fminf(H, pmax + d);
   }
-  scale = (float)FB / (H - L);
+  scale = 1.0f / (H - L);               // u = saturate((x - L) / (H - L)), see fine_tbits
   nLs = -L * scale;
-  return finite_f(scale) && finite_f(nLs);
+  return finite_f(scale) && finite_f(nLs) && scale > 0.0f;
 }
 
 // ---- the selection of one column, in stages --------------------------------------------------
@@ -652,9 +687,11 @@ __device__ __forceinline__ bool exact_range(const SelWarp& w, float& scale, floa
     qlo -= d;
     qhi += d;
   }
-  scale = (float)FB / (qhi - qlo);
+  scale = 1.0f / (qhi - qlo);
   nLs = -qlo * scale;
-  if (!finite_f(scale) || !finite_f(nLs)) { scale = (float)FB / (FLT_MAX * 0.5f); nLs = 0.5f * (float)FB; }
+  // a span beyond the float range (or a flushed scale): one bin for everything, the rounds on the
+  // ordered bit patterns (select_in_interval) take it from there
+  if (!finite_f(scale) || !finite_f(nLs) || !(scale > 0.0f)) { scale = 0.0f; nLs = 0.5f; }
   return true;
 }
 
@@ -697,6 +734,8 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
   float sum = 0.0f;
   FH::zero(hist, lane);
   const int nH = NG > 0 ? NG * 128 : Npad;      // (compile-time trip count when the length is known)
+  const unsigned hist_sa = (unsigned)__cvta_generic_to_shared(hist);
+  const unsigned lane_sa = hist_sa + 4u * (unsigned)(FH::WORDS + lane);
   if (!has_tie) {
 #pragma unroll 3
     for (int s0 = 4 * lane; s0 < nH; s0 += 128) {
@@ -706,7 +745,7 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
       for (int j = 0; j < 4; ++j) {
         const bool fin = finite_f(xs[j]);
         sum += fin ? xs[j] : 0.0f;
-        FH::add_if(hist, fine_index(xs[j], scale, nLs), fin, lane);                 // mcz.py:273
+        FH::add_t(hist_sa, lane_sa, fine_tbits(xs[j], scale, nLs), fin);            // mcz.py:273
       }
     }
   } else {
@@ -720,7 +759,7 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
         const bool fin = finite_f(xs[j]);
         ntie += is_tie ? 1 : 0;
         sum += fin ? xs[j] : 0.0f;
-        FH::add_if(hist, fine_index(xs[j], scale, nLs), fin && !is_tie, lane);
+        FH::add_t(hist_sa, lane_sa, fine_tbits(xs[j], scale, nLs), fin && !is_tie);
       }
     }
     ntie = __reduce_add_sync(0xffffffffu, ntie);
@@ -738,6 +777,8 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
   int tlo[3];
   unsigned tsp[3];
   sel_tests(P, true, tlo, tsp);
+#pragma unroll
+  for (int r = 0; r < 3; ++r) tlo[r] += FINE_BIAS;        // the tests below compare the raw index bits
   __syncwarp();
   unsigned gcnt = 0;                             // candidates gathered so far (same in every lane)
   const unsigned lt = (1u << lane) - 1u;
@@ -773,7 +814,7 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const float x = xs[j];
-              const int f = fine_index(x, scale, nLs);
+              const int f = fine_tbits(x, scale, nLs);
               const bool hit = ((unsigned)(f - tlo[0]) <= tsp[0]) || ((unsigned)(f - tlo[1]) <= tsp[1]) ||
                                ((unsigned)(f - tlo[2]) <= tsp[2]);
               mask |= (hit && x != skip) ? (1u << (4 * i + j)) : 0u;
@@ -810,7 +851,7 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float x = xs[j];
-            const int f = fine_index(x, scale, nLs);            // non-finite x: an end bin, no member here
+            const int f = fine_tbits(x, scale, nLs);            // non-finite x: an end bin, no member here
             const bool hit = ((unsigned)(f - tlo[0]) <= tsp[0]) || ((unsigned)(f - tlo[1]) <= tsp[1]) ||
                              ((unsigned)(f - tlo[2]) <= tsp[2]);
             mask |= (hit && x != skip) ? (1u << (4 * i + j)) : 0u;
@@ -836,6 +877,8 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
     int clo[3];
     unsigned csp[3];
     sel_tests(P, false, clo, csp);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) clo[r] += FINE_BIAS;
     int bcm[3] = {0, 0, 0};
     int cw = 0;                                  // members compacted by this lane so far
     float* const vm = const_cast<float*>(v);
@@ -846,7 +889,7 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
       for (int j = 0; j < 4; ++j) {
         const float x = xs[j];
         const bool fin = finite_f(x);
-        const int f = fine_index(x, scale, nLs);
+        const int f = fine_tbits(x, scale, nLs);
         const bool take = fin && x != skip &&
                           (((unsigned)(f - tlo[0]) <= tsp[0]) || ((unsigned)(f - tlo[1]) <= tsp[1]) ||
                            ((unsigned)(f - tlo[2]) <= tsp[2]));
