@@ -32,10 +32,11 @@ static constexpr int PW = PT / 32;
 static constexpr int CAND_FLOATS = 128;   // per-warp candidate area (counter + 64-entry list)
 static constexpr int CTRL_BYTES = 1024;
 static constexpr int MAX_DST = 8;                 // ranks of one node
-static constexpr uint32_t SEEN_KD = 1u << 8;     // ctrl->flags bit above the eight line flags
+static constexpr uint32_t SEEN_KD = 1u << 8;     // ctrl->flags bits above the eight line flags: some sample has a KD02_N2O2 value
+static constexpr uint32_t SEEN_ZI_LOW = 1u << 9; // some sample's Z_init_guess is not 8.7
 static constexpr int SCRATCH_HEADER = 256;       // scratch_d starts with: galaxy queue counter (u64) at 0, launch statistics at 64
 static constexpr int SCRATCH_STATS_OFF = 64;
-static constexpr int DIVERGENCE_CHECK_TRIP = 8;   // when to test a still-running N2Ha loop for provable divergence
+static constexpr int DIVERGENCE_CHECK_TRIP = 6;   // when to test a still-running N2Ha loop for provable divergence
 
 struct ProdParams {
   const float* meas;
@@ -339,7 +340,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
     MCZ_T(tA0);
     // ---- phase A (repeated once in the rare case the assumed flags were wrong) ----------------
     uint32_t flags = assumed;
-    bool anykd = false;
+    bool anykd = false, all_zi_high = false;
     for (;;) {
       const int de = effective_dust(p.dust, flags);
       uint32_t seen = 0u;
@@ -349,7 +350,12 @@ production_kernel(const __grid_constant__ ProdParams p) {
       // sampling, `--md all` or `--md KD02` -- get a copy of the loop with those values as
       // compile-time constants: straight-line code, identical arithmetic.
       const uint32_t need = F_ALL & ~F_S39069;      // [SIII]9069 only matters for DP00
-      const bool full = (flags & need) == need && de == 0 && !p.correlated && !p.deterministic;
+      // (|z| <= sqrt(-2 ln 2^-24) = 5.8 for the Box-Muller normals: with |meas| + 6 |err| inside the float
+      // range no perturbed flux can overflow, and the +inf -> 0 clamp of metallicity.py:96 is dead code)
+      bool bounded = true;
+#pragma unroll
+      for (int u = 0; u < NUSED; ++u) bounded = bounded && (fabsf(lm[u]) + 6.0f * fabsf(le[u]) < FLT_MAX);
+      const bool full = (flags & need) == need && de == 0 && !p.correlated && !p.deterministic && bounded;
       auto pass = [&](auto mode_tag) {
         constexpr int MODE = decltype(mode_tag)::value;      // 0 generic, 1 --md all, 2 --md KD02
         const uint32_t fl = MODE ? (uint32_t)F_ALL : flags;
@@ -368,7 +374,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
             for (int u = 0; u < NUSED; ++u) {
               float v = fmaf(le[u], (!MODE && p.correlated) ? z[5] : z[5 + u], lm[u]);   // mcz.py:442 / :589
               v = fmaxf(v, 0.0f);                       // NaN -> 0 and negative -> 0 (metallicity.py:96, 99)
-              if (!(v <= FLT_MAX)) v = 0.0f;            // +inf -> 0 (metallicity.py:96)
+              if (!MODE && !(v <= FLT_MAX)) v = 0.0f;   // +inf -> 0 (metallicity.py:96); cannot happen when `bounded`
               f[u] = v;
               const bool pos = (u >= U_S2B) ? (v > 1e-9f) : (v > 0.0f);
               if (pos) seen |= 1u << u;
@@ -384,6 +390,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
             c.aux = 0u;
             phase_a<float>(f, e, fl, tk, dm, put, c);
             if (c.aux & AUX_KD_VALID) seen |= SEEN_KD;
+            if ((c.aux & AUX_ZI_MASK) != 2u) seen |= SEEN_ZI_LOW;
             store_f32<!GLOBAL>(st0 + s, st0_sa + 4u * (unsigned)s, c.y);
             store_f32<!GLOBAL>(st1 + s, st1_sa + 4u * (unsigned)s, c.n2ha);
             store_f32<!GLOBAL>(st2 + s, st2_sa + 4u * (unsigned)s, c.x);
@@ -402,6 +409,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
       const uint32_t all = ctrl->flags;
       const uint32_t actual = all & F_ALL;
       anykd = (all & SEEN_KD) != 0u;          // some sample has a KD02_N2O2 value (start of the N2Ha loop)
+      all_zi_high = (all & SEEN_ZI_LOW) == 0u;
       if (actual == flags) break;
       flags = actual;               // deterministic samples: the second pass reproduces `actual`
       __syncthreads();              // (rare path) drop the KD bit of the discarded pass
@@ -487,7 +495,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
 #endif
         while (act1 || act2) {
           float sm4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-          unsigned nanb = 0u;
+          bool bad = false;           // some logq of this batch is NaN (it stays NaN: tested once per loop and batch)
           bool changed = false;       // R23 loop: some sample's logq after this batch differs from before it
           float lq1a[SLOTS], lq2a[SLOTS];
           if (act1) {
@@ -496,14 +504,13 @@ production_kernel(const __grid_constant__ ProdParams p) {
               float lq = (num0[i] + Z1[i] * num1[i]) * fast_rcp(den0[i] + Z1[i] * den1[i]);
               float z = cA[i] - lq * cB[i];
               float d = fabsf(lq - lq1[i]);
-              nanb |= (d != d) ? 1u : 0u;
               sm4[0] += fminf(d, 8.0f);
               lq1a[i] = lq;
               const float lqb = (num0[i] + z * num1[i]) * fast_rcp(den0[i] + z * den1[i]);
               Z1[i] = cA[i] - lqb * cB[i];
               d = fabsf(lqb - lq);
-              nanb |= (d != d) ? 2u : 0u;
               sm4[1] += fminf(d, 8.0f);
+              bad = bad || (lqb != lqb);
               lq1[i] = lqb;
             }
           }
@@ -517,24 +524,31 @@ production_kernel(const __grid_constant__ ProdParams p) {
               bool lower = lowz && (lq >= 6.7f) && (lq < 8.3f);
               float z = (lower ? l0 : u0) - lq * (lower ? l1 : u1);
               float d = lq2[i] - lq;
-              nanb |= (d != d) ? 4u : 0u;
               sm4[2] += fminf(fmaxf(d, -8.0f), 8.0f);
               lq2a[i] = lq;
               const float lqb = (num0[i] + z * num1[i]) * fast_rcp(den0[i] + z * den1[i]);
               lower = lowz && (lqb >= 6.7f) && (lqb < 8.3f);
               Z2[i] = (lower ? l0 : u0) - lqb * (lower ? l1 : u1);
               d = lq - lqb;
-              nanb |= (d != d) ? 8u : 0u;
               sm4[3] += fminf(fmaxf(d, -8.0f), 8.0f);
+              bad = bad || (lqb != lqb);
               changed = changed || (lqb != lq2[i]);
               lq2[i] = lqb;
             }
           }
           fx_t t4[4];
           bool anynan, anychanged;
-          block_sum4_fx(sm4, nanb, changed, ctrl, ph, t4, anynan, anychanged);
+          block_sum4_fx(sm4, bad ? 1u : 0u, changed, ctrl, ph, t4, anynan, anychanged);
           unsigned nb = 0u;
-          if (anynan) {      // rare: which loop / trip saw the NaN (a NaN mean stops that loop)
+          if (anynan) {
+            // rare: which loop / trip saw the NaN first (a NaN mean stops that loop, as in numpy).  A NaN
+            // logq makes every later one NaN, so trip a's mean is NaN iff some logq after trip a is.
+            unsigned nanb = 0u;
+#pragma unroll
+            for (int i = 0; i < SLOTS; ++i) {
+              if (act1) nanb |= ((lq1a[i] != lq1a[i]) ? 1u : 0u) | ((lq1[i] != lq1[i]) ? 2u : 0u);
+              if (act2) nanb |= ((lq2a[i] != lq2a[i]) ? 4u : 0u) | ((lq2[i] != lq2[i]) ? 8u : 0u);
+            }
 #pragma unroll
             for (int k = 0; k < 4; ++k) nb |= __syncthreads_or((nanb >> k) & 1u) ? (1u << k) : 0u;
           }
@@ -824,9 +838,14 @@ production_kernel(const __grid_constant__ ProdParams p) {
       if (p.ret) p.ret[g] = ok ? 0 : -1;
     }
     if (warp == PW - 1) fetch_next();    // (the lines / ticket of this galaxy were read into registers in phase A)
+    // Z_init_guess = 8.7 for every sample (two galaxies in three of the benchmark table): KD02comb is
+    // KD02_N2O2 sample by sample (metscales.py:1250-1252), so its row is a copy and needs no selection
+    const bool twin = all_zi_high && ((pm >> K_KD02_N2O2) & 1ull) && ((pm >> K_KD02COMB) & 1ull) &&
+                      p.slot_of_key[K_KD02_N2O2] >= 0 && p.slot_of_key[K_KD02COMB] >= 0;
     for (int sl = warp; sl < p.nstore; sl += PW) {
       const int k = p.key_of_slot[sl];
       if (!((pm >> k) & 1ull)) continue;
+      if (twin && k == K_KD02COMB) continue;
       float pc[3];
       int nv, stt;
 #ifdef MCZ_PHASE_TIMING
@@ -841,17 +860,17 @@ production_kernel(const __grid_constant__ ProdParams p) {
       }
 #endif
       if (lane == 0) {
-        const long long o = (p.row0 + g) * NKEYS + k;
-        for (int q = 0; q < p.ndst; ++q) {
-          p.status[q][o] = (signed char)stt;
-          p.nvalid[q][o] = nv;
-          p.pct[q][3 * o] = pc[0];
-          p.pct[q][3 * o + 1] = pc[1];
-          p.pct[q][3 * o + 2] = pc[2];
+        const int ncopy = (twin && k == K_KD02_N2O2) ? 2 : 1;
+        for (int c = 0; c < ncopy; ++c) {
+          const long long o = (p.row0 + g) * NKEYS + (c ? (int)K_KD02COMB : k);
+          for (int q = 0; q < p.ndst; ++q) {
+            p.status[q][o] = (signed char)stt;
+            p.nvalid[q][o] = nv;
+            p.pct[q][3 * o] = pc[0];
+            p.pct[q][3 * o + 1] = pc[1];
+            p.pct[q][3 * o + 2] = pc[2];
+          }
         }
-#if defined(MCZ_COLTIME_DUMP) && MCZ_COLTIME_DUMP == 1
-        p.pct[0][3 * o + 2] = (float)(clock64() - tc0);
-#endif
       }
     }
 #ifdef MCZ_PHASE_TIMING

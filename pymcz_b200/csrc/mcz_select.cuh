@@ -522,21 +522,45 @@ __device__ __forceinline__ void sel_make_plan(const SelWarp& w, SelPlan& P, bool
       }
     }
   }
-  // Merge the three pair ranges [fa, fb] where they touch or overlap (small n, ties).
-  int nr = 0;
-#pragma unroll
-  for (int q = 0; q < 3; ++q) {
-    const int a = fa[q], b = fb[q];
-    const unsigned endcount = endb[q];                            // samples with f <= b
-    if (nr > 0 && a <= P.rhi[nr - 1]) {
-      if (b > P.rhi[nr - 1]) { P.rhi[nr - 1] = b; P.rM[nr - 1] = endcount - P.rE[nr - 1]; }
+  // Merge the three pair ranges [fa, fb] where they touch or overlap (small n, ties).  Written out
+  // case by case with constant indices: a loop over a run-time range count would put the whole
+  // plan into local memory.
+  {
+    // range 0 starts as pair 0
+    int lo0 = fa[0], hi0 = fb[0];
+    unsigned E0 = exa[0], M0 = endb[0] - exa[0];
+    int lo1 = 0, hi1 = 0, lo2 = 0, hi2 = 0;
+    unsigned E1 = 0u, M1 = 0u, E2 = 0u, M2 = 0u;
+    // pair 1: joins range 0 or opens range 1
+    const bool j1 = fa[1] <= hi0;
+    if (j1) {
+      if (fb[1] > hi0) { hi0 = fb[1]; M0 = endb[1] - E0; }
     } else {
-      P.rlo[nr] = a; P.rhi[nr] = b; P.rE[nr] = exa[q]; P.rM[nr] = endcount - exa[q];
-      ++nr;
+      lo1 = fa[1]; hi1 = fb[1]; E1 = exa[1]; M1 = endb[1] - exa[1];
     }
-    P.rq[q] = nr - 1;
+    // pair 2: joins the last range or opens the next one
+    const int last_hi = j1 ? hi0 : hi1;
+    const bool j2 = fa[2] <= last_hi;
+    int q2;
+    if (j2) {
+      if (fb[2] > last_hi) {
+        if (j1) { hi0 = fb[2]; M0 = endb[2] - E0; } else { hi1 = fb[2]; M1 = endb[2] - E1; }
+      }
+      q2 = j1 ? 0 : 1;
+    } else if (j1) {
+      lo1 = fa[2]; hi1 = fb[2]; E1 = exa[2]; M1 = endb[2] - exa[2];
+      q2 = 1;
+    } else {
+      lo2 = fa[2]; hi2 = fb[2]; E2 = exa[2]; M2 = endb[2] - exa[2];
+      q2 = 2;
+    }
+    P.rlo[0] = lo0; P.rhi[0] = hi0; P.rE[0] = E0; P.rM[0] = M0;
+    P.rlo[1] = lo1; P.rhi[1] = hi1; P.rE[1] = E1; P.rM[1] = M1;
+    P.rlo[2] = lo2; P.rhi[2] = hi2; P.rE[2] = E2; P.rM[2] = M2;
+    P.rq[0] = 0; P.rq[1] = j1 ? 0 : 1; P.rq[2] = q2;
+    P.nr = q2 + 1;
   }
-  P.nr = nr;
+  const int nr = P.nr;
   if (has_tie && ntie > 0u) {
 #pragma unroll
     for (int r = 0; r < 3; ++r)
@@ -656,8 +680,8 @@ __device__ __forceinline__ void sel_finish(const SelWarp& w, const SelPlan& P, c
     // A crowded range is exactly the set of finite values in [bmn, bmx] (the fine index is
     // monotone), so a rank inside it is an order statistic of that interval.
     sel_count(SEL_CROWDED);
-#pragma unroll 1
-    for (int q = 0; q < 3; ++q) {
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {          // (unrolled: constant indices keep the plan in registers)
       const int r = P.rq[q];
       const bool cr = r == 0 ? P.crowded[0] : (r == 1 ? P.crowded[1] : P.crowded[2]);
       if (!cr) continue;
@@ -800,46 +824,54 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
     const int ngroups = Npad / 128;
     if (lane == 0) *w.ccount = 0u;
     __syncwarp();
+    bool done = false;
     if constexpr (NG > 0 && NCH <= 4) {
-      // known column length: straight-line code, all masks kept, members appended once at the end
-      unsigned m[NCH];
+      if (!(skip == skip)) {
+        // known column length and no value to leave out: straight-line code, all masks kept, members
+        // appended once at the end.  The membership bits are shifted in (mask = 2 * mask + hit: one
+        // select and one multiply-add per sample), so sample k of a chunk ends up in bit (nbits - 1 - k).
+        unsigned m[NCH];
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        unsigned mask = 0u;
+        for (int c = 0; c < NCH; ++c) {
+          unsigned mask = 0u;
 #pragma unroll
-        for (int i = 0; i < CH; ++i) {
-          if (c * CH + i < NG) {
-            const float4 x4 = *reinterpret_cast<const float4*>(v + 4 * lane + 128 * (c * CH + i));
-            const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+          for (int i = 0; i < CH; ++i) {
+            if (c * CH + i < NG) {
+              const float4 x4 = *reinterpret_cast<const float4*>(v + 4 * lane + 128 * (c * CH + i));
+              const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float x = xs[j];
-              const int f = fine_tbits(x, scale, nLs);
-              const bool hit = ((unsigned)(f - tlo[0]) <= tsp[0]) || ((unsigned)(f - tlo[1]) <= tsp[1]) ||
-                               ((unsigned)(f - tlo[2]) <= tsp[2]);
-              mask |= (hit && x != skip) ? (1u << (4 * i + j)) : 0u;
+              for (int j = 0; j < 4; ++j) {
+                const int f = fine_tbits(xs[j], scale, nLs);
+                const bool hit = ((unsigned)(f - tlo[0]) <= tsp[0]) || ((unsigned)(f - tlo[1]) <= tsp[1]) ||
+                                 ((unsigned)(f - tlo[2]) <= tsp[2]);
+                mask = 2u * mask + (hit ? 1u : 0u);
+              }
+            }
+          }
+          m[c] = mask;
+        }
+        unsigned mine = 0u;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) mine += (unsigned)__popc(m[c]);
+        if (mine) {
+          unsigned pos = atomicAdd(w.ccount, mine);
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            constexpr int dummy = 0; (void)dummy;
+            const int nbits = 4 * ((NG - c * CH) < CH ? (NG - c * CH) : CH);
+            unsigned mask = m[c];
+            while (mask) {
+              const int k = nbits - __ffs(mask);          // sample k of the chunk (group k >> 2, element k & 3)
+              mask &= mask - 1u;
+              w.glist[pos & 255u] = v[4 * lane + 128 * (c * CH + (k >> 2)) + (k & 3)];
+              ++pos;
             }
           }
         }
-        m[c] = mask;
+        done = true;
       }
-      unsigned mine = 0u;
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) mine += (unsigned)__popc(m[c]);
-      if (mine) {
-        unsigned pos = atomicAdd(w.ccount, mine);
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-          unsigned mask = m[c];
-          while (mask) {
-            const int b = __ffs(mask) - 1;
-            mask &= mask - 1u;
-            w.glist[pos & 255u] = v[4 * lane + 128 * (c * CH + (b >> 2)) + (b & 3)];
-            ++pos;
-          }
-        }
-      }
-    } else
+    }
+    if (!done)
 #pragma unroll 1
     for (int g0 = 0; g0 < ngroups; g0 += CH) {
       unsigned mask = 0u;
