@@ -87,6 +87,20 @@ int mcz_forward_replay(const double* flux_d, const double* noise_d, long long G,
                        unsigned long long* present_d, int* trips_d, int* ret_d, void* scratch_d,
                        size_t scratch_bytes, void* stream);
 
+/* The same, also returning the intermediate per-sample quantities the reference keeps as attributes
+ * of the diagnostics object (calcNIIOII, calcNIISII, calcR23, initialguess, calcKK04_N2Ha;
+ * metscales.py:393-440, 468-489, 1112):
+ *   aux_d [G][MCZ_NAUX][N] float64 (may be NULL): logN2O2, logN2S2, N2S2, R2, R3, R23, Z_init_guess,
+ *         logq (as calcKK04_N2Ha leaves it), and the real root pair of the [NII]/[OII] quartic
+ *         (larger, smaller; the real entries of N2O2_roots inside the KD02_N2O2 window); NaN where the
+ *         reference would not have set the attribute.
+ */
+#define MCZ_NAUX 10
+int mcz_forward_replay_aux(const double* flux_d, const double* noise_d, long long G, long long N,
+                           unsigned tokens, int dust, int precision, double* Z_d,
+                           unsigned long long* present_d, int* trips_d, int* ret_d, double* aux_d,
+                           void* scratch_d, size_t scratch_bytes, void* stream);
+
 /* ---- percentiles of stored distributions ------------------------------------------------------
  * Replaces the statistics part of savehist() (mcz.py:273-301): finite filter, n, sum<=0 test,
  * np.percentile(data, [50, 16, 84]) with linear interpolation, in float64.

@@ -81,6 +81,17 @@ int mcz_forward_replay(const double* flux_d, const double* noise_d, long long G,
                        scratch_d, scratch_bytes, (cudaStream_t)stream);
 }
 
+int mcz_forward_replay_aux(const double* flux_d, const double* noise_d, long long G, long long N,
+                           unsigned tokens, int dust, int precision, double* Z_d,
+                           unsigned long long* present_d, int* trips_d, int* ret_d, double* aux_d,
+                           void* scratch_d, size_t scratch_bytes, void* stream) {
+  if (!flux_d || !Z_d || !present_d || !trips_d || !ret_d) return set_error("mcz_forward_replay_aux: null pointer");
+  if (precision != 0 && precision != 1) return set_error("mcz_forward_replay_aux: precision must be 0 or 1");
+  if ((tokens & (T_D02 | T_M13)) && !noise_d) return set_error("mcz_forward_replay_aux: D02/M13 need noise_d");
+  return launch_replay(flux_d, noise_d, G, N, tokens, dust, precision, Z_d, present_d, trips_d, ret_d,
+                       scratch_d, scratch_bytes, (cudaStream_t)stream, aux_d);
+}
+
 int mcz_segmented_percentiles(const double* Z_d, const unsigned char* present_d, long long rows,
                               long long N, double* pct_d, int* nvalid_d, signed char* status_d,
                               void* stream) {

@@ -30,6 +30,22 @@ enum Key : int {
   NKEYS = 37
 };
 
+// Intermediate per-sample quantities the reference keeps as attributes of the diagnostics object
+// (metscales.py:393-440, 468-489, 1112): handed to put() under indices >= NKEYS.  Only the replay
+// kernel stores them (optional output); the production kernels' put() drops them at compile time.
+enum AuxKey : int {
+  A_LOGN2O2 = NKEYS,   // self.logN2O2 (metscales.py:404)
+  A_LOGN2S2,           // self.logN2S2 (:396)
+  A_N2S2,              // self.N2S2 (:395)
+  A_R2, A_R3, A_R23,   // self.R2, self.R3, self.R23 (:431-433)
+  A_ZINIT,             // self.Z_init_guess (:471-489)
+  A_LOGQ,              // self.logq left by calcKK04_N2Ha (:1112, :1124)
+  A_N2O2_ROOT_HI,      // the two real roots of the [NII]/[OII] quartic (of self.N2O2_roots, :423), NaN if complex
+  A_N2O2_ROOT_LO,
+  A_END,
+  NAUX = A_END - NKEYS
+};
+
 // keys that are present but NaN for every sample (the reference's `highZ is True` tests never hold
 // for a numpy.bool_, metscales.py:1013-1018, 1030-1047): never stored, reported as n = 0
 MCZ_HD bool const_nan_key(int k) { return k == K_M08_R23 || k == K_M08_O3HB || k == K_M08_O2HB; }

@@ -13,7 +13,7 @@ void count_launch(int n = 1);
 size_t replay_scratch_bytes(long long G, long long N, int precision, int* grid_out);
 int launch_replay(const double* flux, const double* noise, long long G, long long N, uint32_t tok,
                   int dust, int precision, double* Z, unsigned long long* present, int* trips,
-                  int* ret, void* scratch, size_t scratch_bytes, cudaStream_t stream);
+                  int* ret, void* scratch, size_t scratch_bytes, cudaStream_t stream, double* aux = nullptr);
 
 int launch_percentiles_f64(const double* Z, const unsigned char* present, long long rows, long long N,
                            double* pct, int* nvalid, signed char* status, cudaStream_t stream);

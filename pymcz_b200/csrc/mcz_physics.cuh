@@ -148,6 +148,18 @@ template <typename R> MCZ_HD R kd02_n2o2(R L) {
   const R t = rt_n2o2_t<R>(L <= R(RT_N2O2_F_LO) ? -s : s);
   return R(RT_N2O2_X0) + t;
 }
+// the real root pair of that quartic (both NaN when it has none): part of self.N2O2_roots
+template <typename R> MCZ_HD void kd02_n2o2_real_roots(R L, R& hi, R& lo) {
+  hi = lo = Math<R>::nan();
+  if (!Math<R>::isfinite(L)) return;
+  const R d = L - R(RT_N2O2_F0);
+  if (!(d >= R(0))) return;
+  const R s = Math<R>::sqrt(d);
+  // (the fitted t(s) covers the window of KD02_N2O2 only: outside it the roots are not reported)
+  if (L > R(RT_N2O2_F_HI)) return;
+  hi = R(RT_N2O2_X0) + rt_n2o2_t<R>(s);
+  lo = R(RT_N2O2_X0) + rt_n2o2_t<R>(-s);
+}
 
 // M08 [NII]/Ha (metscales.py:994-999): first root (np.roots order) with root+8.69 in [7.1, 9.4].
 // One real maximum f0 at x0; for y <= f0 two real roots, listed in descending order, so the
@@ -287,7 +299,7 @@ template <typename R> MCZ_HD void make_iter(const Carry<R>& c, R kd, IterState<R
 // e[5]:     scaled coefficient noise: D02 e1,e2 (metscales.py:679-680), M13_N2 e1,e2 (:948-949),
 //           M13_O3N2 e1 (:952; its e2 is drawn but never used, :953-955)
 // put(key, value) is called for every key that is present for this galaxy except the three KK04
-// iteration outputs, which phase C writes.  `carry` is filled when the KD02 group is requested.
+// iteration outputs, which phase C writes; with Put::WANT_AUX also for the AuxKey intermediates.  `carry` is filled when the KD02 group is requested.
 template <typename R, class Put>
 MCZ_HD void phase_a(const R* f, const R* e, uint32_t flags, uint32_t tok, int dust_eff,
                     Put& put, Carry<R>& carry) {
@@ -328,6 +340,18 @@ MCZ_HD void phase_a(const R* f, const R* e, uint32_t flags, uint32_t tok, int du
     R23 = R2 + R3;
     x = M::log10(R23);
     put(K_LOGR23, x);
+    if (Put::WANT_AUX) { put(A_R2, R2); put(A_R3, R3); put(A_R23, R23); }
+  }
+  if (Put::WANT_AUX && n2 && o2) {                                        // calcNIIOII, metscales.py:402-423
+    put(A_LOGN2O2, logN2O2);
+    R rhi, rlo;
+    kd02_n2o2_real_roots<R>(logN2O2, rhi, rlo);
+    put(A_N2O2_ROOT_HI, rhi); put(A_N2O2_ROOT_LO, rlo);
+  }
+  if (Put::WANT_AUX && s2 && n2) {                                        // calcNIISII, metscales.py:393-396
+    const R lns = lN2 - M::log10(f[U_S2A]) + a * R(MCZ_K_N2 - MCZ_K_S2);
+    put(A_LOGN2S2, lns);
+    put(A_N2S2, M::exp10(lns));
   }
 
   // Z_init_guess (metscales.py:471-489)
@@ -345,6 +369,7 @@ MCZ_HD void phase_a(const R* f, const R* e, uint32_t flags, uint32_t tok, int du
     }
   }
   const bool zi_lt84 = zi == 0u;      // Z_init_guess < 8.4
+  if (Put::WANT_AUX) put(A_ZINIT, zi == 0u ? R(8.2) : (zi == 1u ? R(8.4) : R(8.7)));
 
   if ((tok & T_D02) && n2 && ha)                                          // metscales.py:682
     put(K_D02, R(9.12) + e[0] + (R(0.73) + e[1]) * logN2Ha);

@@ -33,10 +33,12 @@ static constexpr int CAND_FLOATS = 128;   // per-warp candidate area (counter + 
 static constexpr int CTRL_BYTES = 1024;
 static constexpr int MAX_DST = 8;                 // ranks of one node
 static constexpr uint32_t SEEN_KD = 1u << 8;     // ctrl->flags bits above the eight line flags: some sample has a KD02_N2O2 value
-static constexpr uint32_t SEEN_ZI_LOW = 1u << 9; // some sample's Z_init_guess is not 8.7
 static constexpr int SCRATCH_HEADER = 256;       // scratch_d starts with: galaxy queue counter (u64) at 0, launch statistics at 64
 static constexpr int SCRATCH_STATS_OFF = 64;
-static constexpr int DIVERGENCE_CHECK_TRIP = 6;   // when to test a still-running N2Ha loop for provable divergence
+#ifndef MCZ_DIV_TRIP
+#define MCZ_DIV_TRIP 6
+#endif
+static constexpr int DIVERGENCE_CHECK_TRIP = MCZ_DIV_TRIP;   // when to test a still-running N2Ha loop for provable divergence
 
 struct ProdParams {
   const float* meas;
@@ -210,13 +212,14 @@ __device__ __forceinline__ float fast_rcp(float x) {
 // is computed once and the store is issued as st.shared: through a generic pointer the compiler
 // re-derives the shared window base (S2UR / ULEA / IMAD) at every one of the 17 stores.
 template <bool SHARED> struct SlotPut {
+  static constexpr bool WANT_AUX = false;
   float* col;                 // &vals[0][s]
   const int* col_off;         // per key: float offset of its column (kernel parameter space)
   uint32_t saddr;             // shared-space byte address of col (SHARED only)
   __device__ __forceinline__ void operator()(int key, float v) const {
     // every key the physics can emit under the launch's tokens owns a column, except the
     // constant-NaN ones (M08_R23, M08_O3Hb, M08_O2Hb: const_nan_key), which are never stored
-    if (const_nan_key(key)) return;
+    if (const_nan_key(key) || key >= NKEYS) return;       // (aux keys: replay only)
     if (SHARED) asm volatile("st.shared.f32 [%0], %1;" :: "r"(saddr + 4u * (unsigned)col_off[key]), "f"(v) : "memory");
     else col[col_off[key]] = v;
   }
@@ -340,7 +343,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
     MCZ_T(tA0);
     // ---- phase A (repeated once in the rare case the assumed flags were wrong) ----------------
     uint32_t flags = assumed;
-    bool anykd = false, all_zi_high = false;
+    bool anykd = false;
     for (;;) {
       const int de = effective_dust(p.dust, flags);
       uint32_t seen = 0u;
@@ -390,7 +393,6 @@ production_kernel(const __grid_constant__ ProdParams p) {
             c.aux = 0u;
             phase_a<float>(f, e, fl, tk, dm, put, c);
             if (c.aux & AUX_KD_VALID) seen |= SEEN_KD;
-            if ((c.aux & AUX_ZI_MASK) != 2u) seen |= SEEN_ZI_LOW;
             store_f32<!GLOBAL>(st0 + s, st0_sa + 4u * (unsigned)s, c.y);
             store_f32<!GLOBAL>(st1 + s, st1_sa + 4u * (unsigned)s, c.n2ha);
             store_f32<!GLOBAL>(st2 + s, st2_sa + 4u * (unsigned)s, c.x);
@@ -409,7 +411,6 @@ production_kernel(const __grid_constant__ ProdParams p) {
       const uint32_t all = ctrl->flags;
       const uint32_t actual = all & F_ALL;
       anykd = (all & SEEN_KD) != 0u;          // some sample has a KD02_N2O2 value (start of the N2Ha loop)
-      all_zi_high = (all & SEEN_ZI_LOW) == 0u;
       if (actual == flags) break;
       flags = actual;               // deterministic samples: the second pass reproduces `actual`
       __syncthreads();              // (rare path) drop the KD bit of the discarded pass
@@ -838,14 +839,9 @@ production_kernel(const __grid_constant__ ProdParams p) {
       if (p.ret) p.ret[g] = ok ? 0 : -1;
     }
     if (warp == PW - 1) fetch_next();    // (the lines / ticket of this galaxy were read into registers in phase A)
-    // Z_init_guess = 8.7 for every sample (two galaxies in three of the benchmark table): KD02comb is
-    // KD02_N2O2 sample by sample (metscales.py:1250-1252), so its row is a copy and needs no selection
-    const bool twin = all_zi_high && ((pm >> K_KD02_N2O2) & 1ull) && ((pm >> K_KD02COMB) & 1ull) &&
-                      p.slot_of_key[K_KD02_N2O2] >= 0 && p.slot_of_key[K_KD02COMB] >= 0;
     for (int sl = warp; sl < p.nstore; sl += PW) {
       const int k = p.key_of_slot[sl];
       if (!((pm >> k) & 1ull)) continue;
-      if (twin && k == K_KD02COMB) continue;
       float pc[3];
       int nv, stt;
 #ifdef MCZ_PHASE_TIMING
@@ -860,16 +856,13 @@ production_kernel(const __grid_constant__ ProdParams p) {
       }
 #endif
       if (lane == 0) {
-        const int ncopy = (twin && k == K_KD02_N2O2) ? 2 : 1;
-        for (int c = 0; c < ncopy; ++c) {
-          const long long o = (p.row0 + g) * NKEYS + (c ? (int)K_KD02COMB : k);
-          for (int q = 0; q < p.ndst; ++q) {
-            p.status[q][o] = (signed char)stt;
-            p.nvalid[q][o] = nv;
-            p.pct[q][3 * o] = pc[0];
-            p.pct[q][3 * o + 1] = pc[1];
-            p.pct[q][3 * o + 2] = pc[2];
-          }
+        const long long o = (p.row0 + g) * NKEYS + k;
+        for (int q = 0; q < p.ndst; ++q) {
+          p.status[q][o] = (signed char)stt;
+          p.nvalid[q][o] = nv;
+          p.pct[q][3 * o] = pc[0];
+          p.pct[q][3 * o + 1] = pc[1];
+          p.pct[q][3 * o + 2] = pc[2];
         }
       }
     }

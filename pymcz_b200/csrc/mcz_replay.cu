@@ -17,9 +17,14 @@ __device__ __forceinline__ double sanitise(double v) {      // metallicity.py:96
 }
 
 template <typename R> struct GlobalPut {
+  static constexpr bool WANT_AUX = true;
   double* base;       // &Z[g][0][s]
   long long N;
-  __device__ __forceinline__ void operator()(int key, R v) { base[(long long)key * N] = (double)v; }
+  double* aux;        // &aux[g][0][s] or null: the intermediate quantities (AuxKey)
+  __device__ __forceinline__ void operator()(int key, R v) {
+    if (key < NKEYS) base[(long long)key * N] = (double)v;
+    else if (aux) aux[(long long)(key - NKEYS) * N] = (double)v;
+  }
 };
 
 template <typename R>
@@ -27,7 +32,7 @@ __global__ void __launch_bounds__(RB)
 replay_kernel(const double* __restrict__ flux, const double* __restrict__ noise, long long G,
               long long N, uint32_t tok, int dust, double* __restrict__ Z,
               unsigned long long* __restrict__ present_out, int* __restrict__ trips_out,
-              int* __restrict__ ret_out, IterState<R>* __restrict__ scratch) {
+              int* __restrict__ ret_out, IterState<R>* __restrict__ scratch, double* __restrict__ aux) {
   __shared__ uint32_t sh_flags;
   __shared__ double sh_red[4 * (RB / 32)];
   const int tid = threadIdx.x;
@@ -66,7 +71,10 @@ replay_kernel(const double* __restrict__ flux, const double* __restrict__ noise,
         f[u] = (R)sanitise(flux[((long long)used2line[u] * G + g) * N + s]);
 #pragma unroll
       for (int j = 0; j < 5; ++j) e[j] = noise ? (R)noise[((long long)j * G + g) * N + s] : R(0);
-      GlobalPut<R> put{Z + ((long long)g * NKEYS) * N + s, N};
+      double* auxs = aux ? aux + ((long long)g * NAUX) * N + s : nullptr;
+      if (auxs)
+        for (int k = 0; k < NAUX; ++k) auxs[(long long)k * N] = Math<double>::nan();
+      GlobalPut<R> put{Z + ((long long)g * NKEYS) * N + s, N, auxs};
       Carry<R> c;
       phase_a<R>(f, e, flags, tok, de, put, c);
       if ((tok & T_KD02) && ok) {
@@ -127,10 +135,12 @@ replay_kernel(const double* __restrict__ flux, const double* __restrict__ noise,
       // ---- phase C
       for (long long s = tid; s < N; s += RB) {
         double* col = Z + ((long long)g * NKEYS) * N + s;
-        GlobalPut<R> put{col, N};
+        GlobalPut<R> put{col, N, nullptr};
         const R kd = ((pm >> K_KD02_N2O2) & 1ull) ? (R)col[(long long)K_KD02_N2O2 * N] : Math<R>::nan();
         const R m91 = (R)col[(long long)K_M91 * N];
         phase_c<R>(st[s], pm, ii1 >= 100, ii2 >= 100, kd, m91, put);
+        // self.logq as calcKK04_N2Ha leaves it: the last logq of its loop, or 7.37177 without [OIII]/[OII]
+        if (aux && has_kn) aux[((long long)g * NAUX + (A_LOGQ - NKEYS)) * N + s] = o3o2 ? (double)st[s].lq1 : 7.37177;
       }
     }
     if (tid == 0) {
@@ -151,17 +161,17 @@ size_t replay_scratch_bytes(long long G, long long N, int precision, int* grid_o
 
 int launch_replay(const double* flux, const double* noise, long long G, long long N, uint32_t tok,
                   int dust, int precision, double* Z, unsigned long long* present, int* trips,
-                  int* ret, void* scratch, size_t scratch_bytes, cudaStream_t stream) {
+                  int* ret, void* scratch, size_t scratch_bytes, cudaStream_t stream, double* aux) {
   int grid = 0;
   const size_t need = replay_scratch_bytes(G, N, precision, &grid);
   if (scratch_bytes < need) return set_error("mcz_forward_replay: scratch too small");
   if (G <= 0 || N <= 0) return 0;
   if (precision == 0)
     replay_kernel<double><<<grid, RB, 0, stream>>>(flux, noise, G, N, tok, dust, Z, present, trips,
-                                                   ret, (IterState<double>*)scratch);
+                                                   ret, (IterState<double>*)scratch, aux);
   else
     replay_kernel<float><<<grid, RB, 0, stream>>>(flux, noise, G, N, tok, dust, Z, present, trips,
-                                                  ret, (IterState<float>*)scratch);
+                                                  ret, (IterState<float>*)scratch, aux);
   count_launch();
   return check_cuda(cudaGetLastError(), "replay_kernel launch");
 }

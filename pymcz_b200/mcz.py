@@ -210,6 +210,23 @@ def run(fi, nsample, mds, multiproc, logf, unpickle=False, dust_corr=True, verbo
         keep_samples = nm * sc.NKEYS * newnsample * 4 <= (2 << 30)
 
     if RUNSIM:
+        # The per-measurement log of the reference's serial loop (mcz.py:577-590: header, the measured
+        # fluxes, then the "calculating X" line of every scale calculation() dispatches, metscales.py:388-1196).
+        # The Pool path logs nothing per measurement; neither do tables too long for a text log.
+        if not multiproc and dist.rank() == 0 and logf is not None and nm <= 100000:
+            names = metallicity.dispatch_order(mds.split(','))
+            for i in range(NM0, nm):
+                logf.write("\n\n measurements %d\n" % (i + 1))
+                for k in alllines:
+                    if k in flux.dtype.names:
+                        logf.write('{0:15} '.format(k))
+                        logf.write('{0:0.2} +/- {1:0.2}\n'.format(flux[k][i], err[k][i]))
+                logf.write("\n")
+                if dust_corr and np.isfinite(flux['Ha'][i]) and np.isfinite(flux['Hb'][i]):
+                    logf.write("calculating E(B-V)\n")
+                logf.write("calculating R23\n")
+                for nme in names:
+                    logf.write("calculating %s\n" % nme)
         if seed is None:
             seed = int.from_bytes(os.urandom(8), 'little')                 # the reference is unseeded
         if dist.world_size() > 1:                                          # one realisation: rank 0's seed everywhere

@@ -34,6 +34,27 @@ def printsafemulti(string, logf, nps):     # metallicity.py:71-78
         print(string)
 
 
+def dispatch_order(toks):
+    """The scales the reference's dispatch evaluates for an --md token list, in its order
+    (metallicity.py:161-257), by the name each calc* logs ("calculating <name>")."""
+    KD = ["KD02_N2O2", "KK04_N2Ha", "KK04_R23", "KD_combined"]
+    order = []
+    if 'all' in toks:
+        order += ["D02", "Z94", "M91", "PP04", "P10", "M08", "M13"] + KD
+    for t, names in (("DP00", ["DP00"]), ("P01", ["old P05"]), ("D02", ["D02"]), ("PP04", ["PP04"]), ("Z94", ["Z94"]),
+                     ("M91", ["M91"]), ("P10", ["P10"]), ("M13", ["M13"])):
+        if t in toks:
+            order += names
+    if 'M08all' in toks:
+        order += ["M08", "other M08s"]
+    elif 'M08' in toks:
+        order += ["M08"]
+    for t, names in (("P05", ["P05"]), ("C01", ["C01"]), ("KD02", KD), ("KD02comb", KD)):
+        if t in toks:
+            order += names
+    return order
+
+
 def calculation(mscales, measured, num, mds, nps, logf, dust_corr=True, disp=False, verbose=False):
     """metallicity.py:86-257.  ``measured``: dict line name -> float64 array of samples."""
     global IGNOREDUST
@@ -49,6 +70,7 @@ def calculation(mscales, measured, num, mds, nps, logf, dust_corr=True, disp=Fal
 
     if dust_corr and mscales.hasHa and mscales.hasHb:                      # metallicity.py:113-115
         dust = sc.DUST_ON
+        printsafemulti("calculating E(B-V)", logf, nps)                    # metscales.py:388
     elif dust_corr and not IGNOREDUST:                                     # metallicity.py:116-129
         # the reference prompts on stdin when nps == 1; a library must not block: always warn
         print('''WARNING: reddening correction cannot be done
@@ -76,8 +98,6 @@ def calculation(mscales, measured, num, mds, nps, logf, dust_corr=True, disp=Fal
 
     tokens, third, _unknown = sc.parse_md(mds)
     toks = mds.split(',')
-    if verbose:
-        print("calculating metallicity diagnostic scales: ", toks)
     # coefficient-noise draws in the order the reference's dispatch makes them (metallicity.py:161-257)
     draws = []
     if 'all' in toks:
@@ -99,4 +119,19 @@ def calculation(mscales, measured, num, mds, nps, logf, dust_corr=True, disp=Fal
                 e1, _unused = mscales._draw([0.012, 0.012])
                 mscales._set_noise([4], [e1])
     mscales._run(tokens)
+    # the always-run precompute of metallicity.py:148-154: attributes, warnings and log lines as the
+    # reference's calcNIIOII / calcNIISII / calcR23 / initialguess leave them
+    mscales._take_niioii()
+    mscales._take_niisii()
+    mscales._take_r23()
+    mscales._take_initialguess()
+    if verbose:
+        print("calculating metallicity diagnostic scales: ", toks)
+    for name in dispatch_order(toks):
+        printsafemulti("calculating " + name, logf, nps)
+        if name == "KK04_N2Ha" and mscales.hasN2 and mscales.hasHa:
+            mscales.logq = mscales._aux["logq"].copy()                     # metscales.py:1112, 1124
+            mscales._loop_warnings(0)
+        elif name == "KK04_R23":
+            mscales._loop_warnings(1)
     return None

@@ -54,6 +54,11 @@ class diagnostics:
         self._noise = np.zeros((5, 1, 1))
         self.trips = (0, 0)              # trips of the KK04_N2Ha / KK04_R23 loops of the last run
         self.ret = None
+        # intermediate quantities (metscales.py:100-147): filled by the calc* that set them in the reference
+        self.logN2O2 = self.N2O2_roots = self.logN2S2 = self.N2S2 = None
+        self.R2 = self.R3 = self.R23 = self.logR23 = None
+        self.Z_init_guess = self.logq = None
+        self._aux = None
 
     # ---- dust switch (metscales.py:265-271), per instance
     def setdustcorrect(self):
@@ -127,10 +132,11 @@ class diagnostics:
         n = flux.shape[2]
         noise = self._noise if self._noise.shape == (5, 1, n) else np.zeros((5, 1, n))
         dev = torch.device("cuda", torch.cuda.current_device())
-        Z, present, trips, ret = ops.forward_replay(torch.from_numpy(flux).to(dev), torch.from_numpy(noise).to(dev),
-                                                    tokens, self._dust, "f64")
+        Z, present, trips, ret, aux = ops.forward_replay(torch.from_numpy(flux).to(dev), torch.from_numpy(noise).to(dev),
+                                                         tokens, self._dust, "f64", return_aux=True)
         pres = ops.present_to_bool(present)[0].cpu().numpy()
         Zh = Z[0].cpu().numpy()
+        self._aux = dict(zip(ops.AUX_NAMES, aux[0].cpu().numpy()))
         self.trips = tuple(int(t) for t in trips[0].cpu().numpy())
         self.ret = int(ret[0].item())
         for j, key in enumerate(sc.KEYS):
@@ -151,51 +157,112 @@ class diagnostics:
         for r, v in zip(rows, values):
             self._noise[r, 0] = v
 
+    # ---- the reference's intermediate attributes, from the replay op's aux output
+    def _say(self, string):
+        _warn(string, self.logf, self.nps)
+
+    def _take_niioii(self):                                                # metscales.py:402-423
+        if self.hasN2 and self.hasO2:
+            self.logN2O2 = self._aux["logN2O2"].copy()
+            self.hasN2O2 = True
+        if not self.hasN2O2 or np.mean(self.logN2O2) < -1.2:
+            try:
+                self._say('''WARNING: the KD02 and KK04 (+M08) methods should only be used for  log([NII]6564/[OII]3727) > -1.2, 
+                the mean log([NII]6564/[OII]3727)= %f''' % np.mean(self.logN2O2))
+            except TypeError:
+                self._say('''WARNING: the KD02 and KK04 (+M08) methods 
+                should only be used for  log([NII]6564/[OII]3727) >-1.2, 
+                the mean log([NII]6564/[OII]3727)= %s''' % self.logN2O2)
+        if not self.hasN2O2:
+            self.N2O2_roots = np.zeros(self._n()) + float('NaN')
+        else:
+            # the REAL root pair of the quartic (descending, as np.roots lists it), NaN where the pair
+            # is complex or outside the KD02_N2O2 window; the reference also keeps the complex pair(s),
+            # which nothing reads (documented deviation)
+            self.N2O2_roots = np.stack([self._aux["N2O2_root_hi"], self._aux["N2O2_root_lo"]], axis=1)
+
+    def _take_niisii(self):                                                # metscales.py:393-399
+        if self.hasS2 and self.hasN2:
+            self.N2S2 = self._aux["N2S2"].copy()
+            self.logN2S2 = self._aux["logN2S2"].copy()
+            self.hasN2S2 = True
+        else:
+            self._say("WARNING: needs SII6717 and NII6584 to calculate NIISII: did you run setN2() and setS?")
+
+    def _take_r23(self):                                                   # metscales.py:426-440
+        self._say("calculating R23")
+        if self.hasO3 and self.hasO2 and self.hasHb:
+            self.R2, self.R3, self.R23 = (self._aux[k].copy() for k in ("R2", "R3", "R23"))
+            self.logR23 = self.mds['logR23']
+        else:
+            self._say("WARNING: need O3, O2, Hb")
+
+    def _take_initialguess(self):                                          # metscales.py:468-489
+        self.Z_init_guess = self._aux["Z_init_guess"].copy()
+
     # ---- calc* (metscales.py:387-1356), each a request to the kernels
     def calcEB_V(self):
+        self._say("calculating E(B-V)")
         return self._run(0, ["E(B-V)"])
 
     def calcNIIOII(self):
-        return None          # the root solve is folded into KD02_N2O2 on the GPU (metscales.py:402-423)
+        self._run(0, [])
+        self._take_niioii()
 
     def calcNIISII(self):
-        return None          # folded into C01 / D16 (metscales.py:393-399)
+        self._run(0, [])
+        self._take_niisii()
 
     def calcR23(self):
-        return self._run(0, ["logR23"])
+        self._run(0, ["logR23"])
+        self._take_r23()
 
     def calcS23(self):
-        return None          # folded into DP00 (metscales.py:443-453)
+        self._say("calculating S23")
+        return None          # folded into DP00 on the GPU (metscales.py:443-453)
 
     def initialguess(self):
-        return None          # per-sample Z_init_guess lives on the GPU (metscales.py:468-489)
+        self._run(0, [])
+        if self.hasN2 and self.hasO2 and not self.hasN2O2:
+            self._say("WARNING: must calculate logN2O2 first")
+            self._take_niioii()
+        self._take_initialguess()
 
     def calcD02(self):
+        self._say("calculating D02")
         self._set_noise([0, 1], self._draw([0.05, 0.1]))                   # metscales.py:679-680
         return self._run(sc.T_D02, _GROUP_KEYS[sc.T_D02])
 
     def calcPP04(self):
+        self._say("calculating PP04")
         return self._run(sc.T_PP04, _GROUP_KEYS[sc.T_PP04])
 
     def calcZ94(self):
+        self._say("calculating Z94")
         return self._run(sc.T_Z94, _GROUP_KEYS[sc.T_Z94] + ["logR23"])
 
     def calcP05(self):
+        self._say("calculating P05")
         return self._run(sc.T_P05, _GROUP_KEYS[sc.T_P05] + ["logR23"])
 
     def calcP10(self):
+        self._say("calculating P10")
         return self._run(sc.T_P10, _GROUP_KEYS[sc.T_P10])
 
     def calcP01(self):
+        self._say("calculating old P05")
         return self._run(sc.T_P01, _GROUP_KEYS[sc.T_P01] + ["logR23"])
 
     def calcC01_ZR23(self):
+        self._say("calculating C01")
         return self._run(sc.T_C01, _GROUP_KEYS[sc.T_C01])
 
     def calcM91(self):
+        self._say("calculating M91")
         return self._run(sc.T_M91, _GROUP_KEYS[sc.T_M91] + ["logR23"])
 
     def calcM13(self):
+        self._say("calculating M13")
         if not self.hasHa or not self.hasN2:                               # metscales.py:943-946
             _warn("WARNING: need O3, N2, Ha and Hb, or at least N2 and Ha", self.logf, self.nps)
             return -1
@@ -206,25 +273,41 @@ class diagnostics:
         return self._run(sc.T_M13, _GROUP_KEYS[sc.T_M13])
 
     def calcM08(self, allM08=False):
+        self._say("calculating M08")
         if allM08:                                                         # metscales.py:1019-1059
             return self._run(sc.T_M08ALL, _GROUP_KEYS[sc.T_M08] + ["M08_O3Hb", "M08_O2Hb", "M08_O3N2", "logR23"])
         return self._run(sc.T_M08, _GROUP_KEYS[sc.T_M08] + ["logR23"])
 
     def calcKD02_N2O2(self):
+        self._say("calculating KD02_N2O2")
         self._run(sc.T_KD02, ["KD02_N2O2"])
         return 1
 
+    def _loop_warnings(self, which):
+        if self.trips[which] >= 100:                                       # metscales.py:1119-1120, 1179-1180
+            self._say("WARNING: loop did not converge")
+
     def calcKK04_N2Ha(self):
-        return self._run(sc.T_KD02, ["KD02_N2O2", "KK04_N2Ha"])
+        self._say("calculating KK04_N2Ha")
+        r = self._run(sc.T_KD02, ["KD02_N2O2", "KK04_N2Ha"])
+        if self.hasN2 and self.hasHa:
+            self.logq = self._aux["logq"].copy()                           # metscales.py:1112, 1124
+            self._loop_warnings(0)
+        return r
 
     def calcKK04_R23(self):
-        return self._run(sc.T_KD02, ["KK04_R23", "logR23"])
+        self._say("calculating KK04_R23")
+        r = self._run(sc.T_KD02, ["KK04_R23", "logR23"])
+        self._loop_warnings(1)
+        return r
 
     def calcKDcombined(self):
+        self._say("calculating KD_combined")
         # fills whatever of KD02_N2O2 / KK04_N2Ha / M91 / KK04_R23 is still None (metscales.py:1202-1216)
         return self._run(sc.T_KD02, ["KD02_N2O2", "KK04_N2Ha", "KK04_R23", "M91", "KD02comb", "logR23"])
 
     def calcDP00(self):
+        self._say("calculating DP00")
         return self._run(sc.T_DP00, _GROUP_KEYS[sc.T_DP00])
 
     def calcD16(self):

@@ -26,9 +26,14 @@ def _need_cuda(t, name):
         raise ValueError("%s must be contiguous" % name)
 
 
-def forward_replay(flux, noise, tokens, dust=DUST_ON, precision="f64"):
+AUX_NAMES = ("logN2O2", "logN2S2", "N2S2", "R2", "R3", "R23", "Z_init_guess", "logq", "N2O2_root_hi", "N2O2_root_lo")
+
+
+def forward_replay(flux, noise, tokens, dust=DUST_ON, precision="f64", return_aux=False):
     """flux [11,G,N] f64 (cuda), noise [5,G,N] f64 or None ->
-    (Z [G,37,N] f64, present [G] int64 bit masks, trips [G,2] i32, ret [G] i32)."""
+    (Z [G,37,N] f64, present [G] int64 bit masks, trips [G,2] i32, ret [G] i32)
+    and, with return_aux, aux [G,10,N] f64: the intermediate quantities AUX_NAMES the reference keeps
+    as attributes of the diagnostics object (metscales.py:393-440, 468-489, 1112)."""
     L = _lib.lib()
     _need_cuda(flux, "flux")
     if flux.dtype != torch.float64 or flux.dim() != 3 or flux.shape[0] != NLINES:
@@ -47,13 +52,16 @@ def forward_replay(flux, noise, tokens, dust=DUST_ON, precision="f64"):
         ret = torch.zeros((G,), dtype=torch.int32, device=dev)
         nbytes = L.mcz_replay_scratch_bytes(G, N, prec)
         scratch = torch.empty((max(nbytes, 8),), dtype=torch.uint8, device=dev)
-        rc = L.mcz_forward_replay(flux.data_ptr(), noise.data_ptr() if noise is not None else None,
-                                  G, N, int(tokens), int(dust), prec, Z.data_ptr(), present.data_ptr(),
-                                  trips.data_ptr(), ret.data_ptr(), scratch.data_ptr(), nbytes,
-                                  _stream_ptr(dev))
-        _lib.check(rc, "mcz_forward_replay")
+        aux = torch.empty((G, len(AUX_NAMES), N), dtype=torch.float64, device=dev) if return_aux else None
+        rc = L.mcz_forward_replay_aux(flux.data_ptr(), noise.data_ptr() if noise is not None else None,
+                                      G, N, int(tokens), int(dust), prec, Z.data_ptr(), present.data_ptr(),
+                                      trips.data_ptr(), ret.data_ptr(), aux.data_ptr() if aux is not None else None,
+                                      scratch.data_ptr(), nbytes, _stream_ptr(dev))
+        _lib.check(rc, "mcz_forward_replay_aux")
         # scratch must outlive the kernel: tie its lifetime to the stream
         scratch.record_stream(torch.cuda.current_stream(dev))
+    if return_aux:
+        return Z, present, trips, ret, aux
     return Z, present, trips, ret
 
 

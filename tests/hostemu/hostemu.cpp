@@ -9,8 +9,9 @@
 using namespace mcz;
 
 template <typename R> struct ArrPut {
+  static constexpr bool WANT_AUX = false;
   double* Z; int N; int s;
-  void operator()(int key, R v) { Z[(size_t)key * N + s] = (double)v; }
+  void operator()(int key, R v) { if (key < NKEYS) Z[(size_t)key * N + s] = (double)v; }
 };
 
 template <typename R>

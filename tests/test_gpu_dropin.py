@@ -59,6 +59,54 @@ def test_calculation_matches_oracle_same_seed(mds, dust):
                 assert np.max(np.abs(a[fin] - b[fin])) < 1e-8, (g, k)       # bar: 1e-3 dex
         # calculation() sanitised the caller's arrays in place, like the reference (metallicity.py:96-99)
         assert all(np.all(v >= 0) for v in fluxi.values())
+        # the intermediate attributes the reference's always-run precompute leaves on the object
+        # (calcNIIOII, calcNIISII, calcR23, initialguess: metscales.py:393-440, 468-489) and self.logq
+        if ret != -1:
+            for name in ("logN2O2", "logN2S2", "N2S2", "R2", "R3", "R23", "Z_init_guess"):
+                a, b = getattr(scales, name), getattr(d, name, None)
+                assert (a is None) == (b is None), (g, name)
+                if a is not None:
+                    assert np.allclose(a, b, rtol=1e-9, atol=1e-9, equal_nan=True), (g, name)
+            if "KD02" in mds or "all" in mds:
+                if scales.hasN2 and scales.hasHa and d.logq is not None and np.ndim(d.logq):
+                    assert np.allclose(scales.logq, d.logq, rtol=1e-8, atol=1e-8, equal_nan=True), g
+            if scales.hasN2O2:
+                # the real roots of the [NII]/[OII] quartic, as np.roots lists them (descending)
+                coef = np.array(orc.N2O2_COEF, dtype=np.float64)
+                for i in (0, n // 2, n - 1):
+                    c = coef.copy(); c[0] -= d.logN2O2[i]
+                    r = np.roots(c[::-1]) if np.isfinite(c[0]) else np.array([])
+                    real = np.sort(r[np.abs(r.imag) == 0].real)[::-1]
+                    got = scales.N2O2_roots[i]
+                    if len(real) == 2 and np.all(np.isfinite(got)):
+                        # (the closed form is fitted for roots inside the KD02_N2O2 window [7.5, 9.4]; a
+                        # partner root outside it is good to ~1e-5)
+                        tol = np.where((real >= 7.5) & (real <= 9.4), 1e-7, 5e-5)
+                        assert np.all(np.abs(got - real) <= tol), (g, i, got, real)
+
+
+def test_calculation_log_lines_and_warnings():
+    """The log the reference's calculation() writes when nps == 1 (printsafemulti, metallicity.py:71-78):
+    "calculating X" per scale in dispatch order, and the KD02 / KK04 applicability warning of calcNIIOII
+    (metscales.py:405-414) for a measurement whose mean log([NII]/[OII]) is below -1.2."""
+    n = 200
+    np.random.seed(3)
+    sample = np.random.normal(0, 1, n)
+    low_m, low_e = synthetic_table(3, config=4)                 # row 2: the low-metallicity template
+    for row, expect_warning in ((0, False), (2, True)):
+        fluxi = measured_dict(low_m[row], low_e[row], sample)
+        log = io.StringIO()
+        scales = ms.diagnostics(n, log, 1)
+        metallicity.IGNOREDUST = False
+        metallicity.calculation(scales, fluxi, 3, "all", 1, log)
+        text = log.getvalue()
+        want = ["calculating E(B-V)", "calculating R23", "calculating D02", "calculating Z94", "calculating M91",
+                "calculating PP04", "calculating P10", "calculating M08", "calculating M13", "calculating KD02_N2O2",
+                "calculating KK04_N2Ha", "calculating KK04_R23", "calculating KD_combined"]
+        pos = [text.find(w) for w in want]
+        assert all(p >= 0 for p in pos) and pos == sorted(pos), text
+        assert ("should only be used for  log([NII]6564/[OII]3727) > -1.2" in text) == expect_warning
+        assert (np.mean(scales.logN2O2) < -1.2) == expect_warning
 
 
 def test_individual_calc_methods():
