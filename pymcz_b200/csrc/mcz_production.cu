@@ -17,6 +17,7 @@
 #include <float.h>
 #include <stdlib.h>
 #include <string.h>
+#include <stdio.h>
 #include <cooperative_groups.h>
 #include <atomic>
 #include <type_traits>
@@ -30,6 +31,7 @@ namespace mcz {
 static constexpr int PT = 576;            // threads per block: 18 warps
 static constexpr int PW = PT / 32;
 static constexpr int CAND_FLOATS = 128;   // per-warp candidate area (counter + 64-entry list)
+static constexpr int CL_GLIST_FLOATS = 192;   // cluster kernel: per-warp candidate list of the owner block (3 ranges x 64)
 static constexpr int CTRL_BYTES = 1024;
 static constexpr int MAX_DST = 8;                 // ranks of one node
 static constexpr uint32_t SEEN_KD = 1u << 8;     // ctrl->flags bits above the eight line flags: some sample has a KD02_N2O2 value
@@ -84,6 +86,12 @@ struct Ctrl {
   float2 redf[2 * PW];
   int acc[3][4];           // fixed-point block sums: two KK04 convergence measures x two trips per barrier
   unsigned chg[3];         // some sample's R23 loop state changed over the batch (rotates with acc)
+  // cluster kernel: the cluster-wide totals / flags, pushed by every block into every block's copy
+  int cacc[3][4];
+  unsigned cchg[3];
+  unsigned nanw[3];        // block: some logq of the batch is NaN;  cnan: cluster
+  unsigned cnan[3];
+  unsigned nan4;           // which loop / trip saw a NaN (rare path)
 };
 static_assert(sizeof(Ctrl) <= CTRL_BYTES, "control block too large");
 
@@ -135,6 +143,41 @@ __device__ __forceinline__ void block_sum2f(float& a, float& c, float2* buf, int
   phase ^= 1;
 }
 
+// ---- thread-block clusters: distributed shared memory ----------------------------------------
+// For N' > 2304 a galaxy is given to a CLUSTER of ceil(N' / 2304) thread blocks: block r holds samples
+// [2304 r, 2304 (r + 1)) in its own shared memory, exactly like the one-block kernel, and what the
+// path needs from the whole sample vector (the has* flags, the KK04 loop means per trip, the
+// histograms and candidates of the selection) is exchanged through the blocks' shared memories
+// (mapa / st|ld|red|atom.shared::cluster) between cluster barriers.
+__device__ __forceinline__ unsigned cl_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned cl_size() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned cl_id() { unsigned r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
+// shared-space address of the same variable in block `rank` of the cluster
+__device__ __forceinline__ unsigned cl_map(unsigned saddr, unsigned rank) {
+  unsigned r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ unsigned cl_map(const void* p, unsigned rank) { return cl_map((unsigned)__cvta_generic_to_shared(p), rank); }
+__device__ __forceinline__ void cl_st(unsigned addr, unsigned v) { asm volatile("st.shared::cluster.u32 [%0], %1;" :: "r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void cl_stf(unsigned addr, float v) { asm volatile("st.shared::cluster.f32 [%0], %1;" :: "r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ unsigned cl_ld(unsigned addr) { unsigned v; asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v; }
+__device__ __forceinline__ float cl_ldf(unsigned addr) { float v; asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory"); return v; }
+__device__ __forceinline__ void cl_red_add(unsigned addr, int v) { asm volatile("red.shared::cluster.add.s32 [%0], %1;" :: "r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void cl_red_or(unsigned addr, unsigned v) { asm volatile("red.shared::cluster.or.b32 [%0], %1;" :: "r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned cl_atom_add(unsigned addr, unsigned v) {
+  unsigned o;
+  asm volatile("atom.shared::cluster.add.u32 %0, [%1], %2;" : "=r"(o) : "r"(addr), "r"(v) : "memory");
+  return o;
+}
+// barrier over every thread of every block of the cluster; orders shared AND global memory accesses
+__device__ __forceinline__ void cl_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+template <bool CL> __device__ __forceinline__ void block_or_cluster_sync() {
+  if (CL) cl_sync(); else __syncthreads();
+}
+
 // Block-wide sums of the convergence measures in fixed point with FX_BITS fractional bits: the
 // thread's partial sum (<= 4 samples, each clamped to +-8 by the caller, which cannot change the
 // outcome of "mean > tol" since tol * N < 8) is rounded to 2^-FX_BITS, one REDUX per warp
@@ -145,6 +188,9 @@ __device__ __forceinline__ void block_sum2f(float& a, float& c, float2* buf, int
 // (7e-6 at 20 bits, against thresholds tol * N of 0.22 and 2.2): below the float32 rounding of the
 // per-sample terms themselves, so the integer total is an order-independent, deterministic
 // stand-in for the reference's float64 mean (metscales.py:1117, 1177).
+#ifndef MCZ_CLUSTER_DEFAULT
+#define MCZ_CLUSTER_DEFAULT 0
+#endif
 #ifndef MCZ_A_UNROLL
 #define MCZ_A_UNROLL 1
 #endif
@@ -155,49 +201,95 @@ static constexpr int A_UNROLL = MCZ_A_UNROLL;     // samples of a thread evaluat
 static constexpr float FX_SCALE = (float)(1 << MCZ_FX_BITS);
 static constexpr int FX_WARP_CLAMP = 64 << MCZ_FX_BITS;
 typedef int fx_t;
-__device__ __forceinline__ void fx_add(fx_t* a, int q) {
-  atomicAdd(a, max(-FX_WARP_CLAMP, min(FX_WARP_CLAMP, q)));
+__device__ __forceinline__ int fx_clamp(int q) { return max(-FX_WARP_CLAMP, min(FX_WARP_CLAMP, q)); }
+static constexpr int FX_BLOCK_CLAMP = 128 << MCZ_FX_BITS;     // cluster kernel: per-block totals, <= 8 of them in 32 bits
+// Cluster kernel, after the block-local sums: every block adds its (clamped) totals and flags to the
+// cluster accumulators of EVERY block of the cluster, then one cluster barrier; each block reads its
+// own copy.  nsum = how many of the four sums are in use.
+__device__ __forceinline__ void cluster_exchange(Ctrl* ctrl, int ph, int nx, unsigned csize) {
+  const int t = threadIdx.x;
+  __syncthreads();                       // the block's own totals are complete
+  if (t < 4) {
+    const int v = max(-FX_BLOCK_CLAMP, min(FX_BLOCK_CLAMP, ctrl->acc[ph][t]));
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(&ctrl->cacc[ph][t]);
+    for (unsigned r = 0; r < csize; ++r) cl_red_add(cl_map(sa, r), v);
+    ctrl->cacc[nx][t] = 0;
+  } else if (t == 32) {
+    if (ctrl->chg[ph]) {
+      const unsigned sa = (unsigned)__cvta_generic_to_shared(&ctrl->cchg[ph]);
+      for (unsigned r = 0; r < csize; ++r) cl_red_or(cl_map(sa, r), 1u);
+    }
+    ctrl->cchg[nx] = 0u;
+  } else if (t == 64) {
+    if (ctrl->nanw[ph]) {
+      const unsigned sa = (unsigned)__cvta_generic_to_shared(&ctrl->cnan[ph]);
+      for (unsigned r = 0; r < csize; ++r) cl_red_or(cl_map(sa, r), 1u);
+    }
+    ctrl->cnan[nx] = 0u;
+  }
+  cl_sync();
 }
+template <bool CL>
 __device__ __forceinline__ void block_sum2_fx(float s1, float s2, bool nan, Ctrl* ctrl, int& ph,
-                                              fx_t& t1, fx_t& t2, bool& anynan) {
+                                              fx_t& t1, fx_t& t2, bool& anynan, unsigned csize) {
   const int lane = threadIdx.x & 31;
   int q1 = __reduce_add_sync(0xffffffffu, __float2int_rn(s1 * FX_SCALE));
   int q2 = __reduce_add_sync(0xffffffffu, __float2int_rn(s2 * FX_SCALE));
+  const bool wnan = CL ? __any_sync(0xffffffffu, nan) : false;
   if (lane == 0) {
-    fx_add(&ctrl->acc[ph][0], q1);
-    fx_add(&ctrl->acc[ph][1], q2);
+    atomicAdd(&ctrl->acc[ph][0], fx_clamp(q1));
+    atomicAdd(&ctrl->acc[ph][1], fx_clamp(q2));
+    if (CL && wnan) ctrl->nanw[ph] = 1u;
   }
   const int nx = ph == 2 ? 0 : ph + 1;
   if (threadIdx.x < 4) ctrl->acc[nx][threadIdx.x] = 0;
-  if (threadIdx.x == 4) ctrl->chg[nx] = 0u;
-  anynan = __syncthreads_or(nan);
-  t1 = ctrl->acc[ph][0];
-  t2 = ctrl->acc[ph][1];
+  if (threadIdx.x == 4) { ctrl->chg[nx] = 0u; ctrl->nanw[nx] = 0u; }
+  if (CL) {
+    cluster_exchange(ctrl, ph, nx, csize);
+    anynan = ctrl->cnan[ph] != 0u;
+    t1 = ctrl->cacc[ph][0];
+    t2 = ctrl->cacc[ph][1];
+  } else {
+    anynan = __syncthreads_or(nan);
+    t1 = ctrl->acc[ph][0];
+    t2 = ctrl->acc[ph][1];
+  }
   ph = nx;
 }
 
 // Same for four sums (two loops x two trips per barrier); `nanbits` is OR-ed over the block.
 // `changed`: this thread's R23 loop state differs from the state before the batch; `anychanged`
-// is its OR over the block.
+// is its OR over the block (cluster).
+template <bool CL>
 __device__ __forceinline__ void block_sum4_fx(const float s[4], unsigned nanbits, bool changed, Ctrl* ctrl, int& ph,
-                                              fx_t t[4], bool& anynan, bool& anychanged) {
+                                              fx_t t[4], bool& anynan, bool& anychanged, unsigned csize) {
   const int lane = threadIdx.x & 31;
   int q[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) q[k] = __reduce_add_sync(0xffffffffu, __float2int_rn(s[k] * FX_SCALE));
   const bool wchg = __any_sync(0xffffffffu, changed);
+  const bool wnan = CL ? __any_sync(0xffffffffu, nanbits != 0u) : false;
   if (lane == 0) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) fx_add(&ctrl->acc[ph][k], q[k]);
+    for (int k = 0; k < 4; ++k) atomicAdd(&ctrl->acc[ph][k], fx_clamp(q[k]));
     if (wchg) ctrl->chg[ph] = 1u;
+    if (CL && wnan) ctrl->nanw[ph] = 1u;
   }
   const int nx = ph == 2 ? 0 : ph + 1;
   if (threadIdx.x < 4) ctrl->acc[nx][threadIdx.x] = 0;
-  if (threadIdx.x == 4) ctrl->chg[nx] = 0u;
-  anynan = __syncthreads_or(nanbits != 0u);
+  if (threadIdx.x == 4) { ctrl->chg[nx] = 0u; ctrl->nanw[nx] = 0u; }
+  if (CL) {
+    cluster_exchange(ctrl, ph, nx, csize);
+    anynan = ctrl->cnan[ph] != 0u;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) t[k] = ctrl->acc[ph][k];
-  anychanged = ctrl->chg[ph] != 0u;
+    for (int k = 0; k < 4; ++k) t[k] = ctrl->cacc[ph][k];
+    anychanged = ctrl->cchg[ph] != 0u;
+  } else {
+    anynan = __syncthreads_or(nanbits != 0u);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) t[k] = ctrl->acc[ph][k];
+    anychanged = ctrl->chg[ph] != 0u;
+  }
   ph = nx;
 }
 
@@ -250,14 +342,22 @@ __device__ unsigned long long g_col_cycles[2 * NKEYS];   // per key: cycles, max
 // SLOTS > 0: at most SLOTS samples per thread, loop state in registers, columns in shared memory.
 // SLOTS == 0: any N', columns / stash / loop state in the per-block global scratch.
 // WIDE: 32-bit histogram counters (columns of 65536 samples or more); global variant only.
-template <int SLOTS, bool WIDE>
+// CL: launched in clusters of ceil(N' / (SLOTS * PT)) blocks, one galaxy per CLUSTER: block r of the
+//     cluster holds samples [r SLOTS PT, (r + 1) SLOTS PT) of every column in its shared memory.
+template <int SLOTS, bool WIDE, bool CL>
 __global__ void __launch_bounds__(PT, 1)
 production_kernel(const __grid_constant__ ProdParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr bool GLOBAL = (SLOTS == 0);
+  static_assert(!CL || SLOTS > 0, "the cluster kernel keeps its columns in shared memory");
   Ctrl* ctrl = reinterpret_cast<Ctrl*>(smem);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int N = p.N, Npad = p.Npad;
+  const int Npad = p.Npad;                // samples a block holds per column (a multiple of 128)
+  const unsigned crank = CL ? cl_rank() : 0u, csize = CL ? cl_size() : 1u;
+  const int soff = CL ? (int)crank * SLOTS * PT : 0;        // global index of this block's first sample
+  // N: samples of the galaxy that THIS block holds (all of them without clusters); the loop
+  // tolerances and the percentile ranks use the galaxy's p.N
+  const int N = CL ? max(0, min(p.N - soff, SLOTS * PT)) : p.N;
 
   constexpr bool PACK16 = !WIDE;          // 16-bit packed histogram counters: columns of < 65536 samples
   constexpr size_t HIST_BYTES = FineHist<PACK16>::BYTES;
@@ -304,23 +404,42 @@ production_kernel(const __grid_constant__ ProdParams p) {
   // The next galaxy (queue ticket, its 22 input numbers, cleared flags) is fetched by the last warp
   // while the block is busy with phase D, so the loop top costs one barrier and no global latency.
   auto fetch_next = [&]() {
+    if (CL && crank != 0u) return;        // the cluster's first block takes the ticket and hands it to all
     long long gn = 0;
     if (lane == 0) gn = (long long)atomicAdd(p.counter, 1ull);
     gn = __shfl_sync(0xffffffffu, gn, 0);
+    float lv = 0.0f;
     if (gn < p.G) {
-      if (lane < NLINES) ctrl->line[lane] = p.meas[gn * NLINES + lane];
-      else if (lane < 2 * NLINES) ctrl->line[lane] = p.err[gn * NLINES + (lane - NLINES)];
+      if (lane < NLINES) lv = p.meas[gn * NLINES + lane];
+      else if (lane < 2 * NLINES) lv = p.err[gn * NLINES + (lane - NLINES)];
     }
-    if (lane == 0) {
-      ctrl->g = gn;
-      ctrl->flags = 0u; ctrl->acc[0][0] = 0; ctrl->acc[0][1] = 0; ctrl->acc[0][2] = 0; ctrl->acc[0][3] = 0;
-      ctrl->chg[0] = 0u;
+    if (CL) {
+      for (unsigned r = 0; r < csize; ++r) {
+        if (lane < 2 * NLINES) cl_stf(cl_map(&ctrl->line[lane], r), lv);
+        if (lane == 0) {
+          const unsigned ga = cl_map(&ctrl->g, r);
+          cl_st(ga, (unsigned)(unsigned long long)gn);
+          cl_st(ga + 4u, (unsigned)((unsigned long long)gn >> 32));
+          cl_st(cl_map(&ctrl->flags, r), 0u);
+          cl_st(cl_map(&ctrl->nan4, r), 0u);
+          for (int k = 0; k < 4; ++k) { cl_st(cl_map(&ctrl->acc[0][k], r), 0u); cl_st(cl_map(&ctrl->cacc[0][k], r), 0u); }
+          cl_st(cl_map(&ctrl->chg[0], r), 0u); cl_st(cl_map(&ctrl->cchg[0], r), 0u);
+          cl_st(cl_map(&ctrl->nanw[0], r), 0u); cl_st(cl_map(&ctrl->cnan[0], r), 0u);
+        }
+      }
+    } else {
+      if (lane < 2 * NLINES) ctrl->line[lane] = lv;
+      if (lane == 0) {
+        ctrl->g = gn;
+        ctrl->flags = 0u; ctrl->acc[0][0] = 0; ctrl->acc[0][1] = 0; ctrl->acc[0][2] = 0; ctrl->acc[0][3] = 0;
+        ctrl->chg[0] = 0u;
+      }
     }
   };
   if (warp == PW - 1) fetch_next();
 
   for (;;) {
-    __syncthreads();
+    block_or_cluster_sync<CL>();
     const long long g = ctrl->g;
     if (g >= p.G) {
       if (p.ndst > 1) __threadfence_system();    // result rows written into other GPUs' tables
@@ -369,9 +488,9 @@ production_kernel(const __grid_constant__ ProdParams p) {
           const int s = i * PT + tid;
           if (s < N) {
             float z[16];
-            if (MODE == 1) draw_normals_c<7u>((uint32_t)s, gg, p, z);
-            else if (MODE == 2) draw_normals_c<6u>((uint32_t)s, gg, p, z);
-            else draw_normals((uint32_t)s, gg, p, z);
+            if (MODE == 1) draw_normals_c<7u>((uint32_t)(soff + s), gg, p, z);
+            else if (MODE == 2) draw_normals_c<6u>((uint32_t)(soff + s), gg, p, z);
+            else draw_normals((uint32_t)(soff + s), gg, p, z);
             float f[NUSED], e[5];
 #pragma unroll
             for (int u = 0; u < NUSED; ++u) {
@@ -406,16 +525,22 @@ production_kernel(const __grid_constant__ ProdParams p) {
       else if (full && p.tok == T_KD02 && p.calls == 6u) pass(std::integral_constant<int, 2>());
       else pass(std::integral_constant<int, 0>());
       seen = __reduce_or_sync(0xffffffffu, seen);
-      if (lane == 0 && seen) atomicOr(&ctrl->flags, seen);
-      __syncthreads();
+      if (lane == 0 && seen) {
+        if (CL) {
+          for (unsigned r = 0; r < csize; ++r) cl_red_or(cl_map(&ctrl->flags, r), seen);
+        } else {
+          atomicOr(&ctrl->flags, seen);
+        }
+      }
+      block_or_cluster_sync<CL>();
       const uint32_t all = ctrl->flags;
       const uint32_t actual = all & F_ALL;
       anykd = (all & SEEN_KD) != 0u;          // some sample has a KD02_N2O2 value (start of the N2Ha loop)
       if (actual == flags) break;
       flags = actual;               // deterministic samples: the second pass reproduces `actual`
-      __syncthreads();              // (rare path) drop the KD bit of the discarded pass
+      block_or_cluster_sync<CL>();  // (rare path) drop the KD bit of the discarded pass
       if (tid == 0) ctrl->flags = actual;
-      __syncthreads();
+      block_or_cluster_sync<CL>();
     }
     const uint64_t pm = present_mask(flags, p.tok);
     const bool ok = minimum_ok(flags);
@@ -435,7 +560,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
       const int sl_kd = p.slot_of_key[K_KD02_N2O2], sl_m91 = p.slot_of_key[K_M91];
       bool act1 = has_kn && o3o2, act2 = has_kr;
       // mean > tol  <=>  sum > tol * N  (NaN sum compares false: the loop stops, as in numpy)
-      const float tol1 = 1.0e-3f * (float)N, tol2 = 1.0e-4f * (float)N;
+      const float tol1 = 1.0e-3f * (float)p.N, tol2 = 1.0e-4f * (float)p.N;
       if constexpr (!GLOBAL) {
         // Loop state: 11 registers per sample; the four R23 branch constants of each sample live
         // in shared memory, in the space of the (now dead) stash.  Slots without a sample get
@@ -485,7 +610,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
           for (int i = 0; i < SLOTS; ++i) Z1[i] = cA[i] - 7.37177f * cB[i];
         }
         // thresholds tol * N in the same fixed point (exact: N * 2^FX_BITS / 1000 in float64)
-        const fx_t itol1 = (fx_t)(1.0e-3 * (double)N * (double)FX_SCALE), itol2 = (fx_t)(1.0e-4 * (double)N * (double)FX_SCALE);
+        const fx_t itol1 = (fx_t)(1.0e-3 * (double)p.N * (double)FX_SCALE), itol2 = (fx_t)(1.0e-4 * (double)p.N * (double)FX_SCALE);
         int ph = 0;
         // Two trips per barrier: trips a and b are computed back to back, their four sums are
         // reduced together, then the reference's loop conditions are replayed trip by trip.  If a
@@ -539,7 +664,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
           }
           fx_t t4[4];
           bool anynan, anychanged;
-          block_sum4_fx(sm4, bad ? 1u : 0u, changed, ctrl, ph, t4, anynan, anychanged);
+          block_sum4_fx<CL>(sm4, bad ? 1u : 0u, changed, ctrl, ph, t4, anynan, anychanged, csize);
           unsigned nb = 0u;
           if (anynan) {
             // rare: which loop / trip saw the NaN first (a NaN mean stops that loop, as in numpy).  A NaN
@@ -550,8 +675,18 @@ production_kernel(const __grid_constant__ ProdParams p) {
               if (act1) nanb |= ((lq1a[i] != lq1a[i]) ? 1u : 0u) | ((lq1[i] != lq1[i]) ? 2u : 0u);
               if (act2) nanb |= ((lq2a[i] != lq2a[i]) ? 4u : 0u) | ((lq2[i] != lq2[i]) ? 8u : 0u);
             }
+            if (CL) {
+              nanb = __reduce_or_sync(0xffffffffu, nanb);
+              if (lane == 0 && nanb)
+                for (unsigned r = 0; r < csize; ++r) cl_red_or(cl_map(&ctrl->nan4, r), nanb);
+              cl_sync();
+              nb = ctrl->nan4;
+              cl_sync();                    // everyone has read it: clear for the next use
+              if (tid == 0) ctrl->nan4 = 0u;
+            } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) nb |= __syncthreads_or((nanb >> k) & 1u) ? (1u << k) : 0u;
+              for (int k = 0; k < 4; ++k) nb |= __syncthreads_or((nanb >> k) & 1u) ? (1u << k) : 0u;
+            }
           }
           if (act1) {                                                     // metscales.py:1111,1117
             ++ii1;
@@ -616,7 +751,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
             }
             fx_t tm, tdummy;
             bool nandummy;
-            block_sum2_fx(sm, 0.0f, false, ctrl, ph, tm, tdummy, nandummy);
+            block_sum2_fx<CL>(sm, 0.0f, false, ctrl, ph, tm, tdummy, nandummy, csize);
             if (tm > 4 * itol1) { executed1 = ii1; ii1 = 100; act1 = false; }
           }
         }
@@ -802,7 +937,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
         }
       }
     }
-    __syncthreads();     // all columns final; the stash is dead from here (selection reuses it)
+    block_or_cluster_sync<CL>();     // all columns final; the stash is dead from here (selection reuses it)
 
     MCZ_T(tD0);
     // ---- optional per-sample output (pickle / --asciidistrib path) ----------------------------
@@ -810,13 +945,13 @@ production_kernel(const __grid_constant__ ProdParams p) {
       for (int k = 0; k < NKEYS; ++k) {
         const int sl = p.slot_of_key[k];
         const bool live = ((pm >> k) & 1ull) && sl >= 0;
-        float* dst = p.Z + ((long long)g * NKEYS + k) * N;
+        float* dst = p.Z + ((long long)g * NKEYS + k) * p.N + soff;
         for (int s = tid; s < N; s += PT) dst[s] = live ? vals[(long long)sl * Npad + s] : Math<float>::nan();
       }
     }
 
     // ---- phase D: percentiles, one warp per stored column -------------------------------------
-    if (tid < NKEYS) {
+    if (crank == 0u && tid < NKEYS) {
       const int k = tid, sl = p.slot_of_key[k];
       const bool pres = (pm >> k) & 1ull;
       if (!(pres && sl >= 0)) {
@@ -828,7 +963,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
         }
       }
     }
-    if (tid == 0) {
+    if (crank == 0u && tid == 0) {
       atomicAdd(&p.stats[0], 1ull);
       atomicAdd(&p.stats[1], (unsigned long long)(executed1 < 0 ? ii1 : executed1));
       atomicAdd(&p.stats[2], (unsigned long long)(executed2 < 0 ? ii2 : executed2));
@@ -839,6 +974,47 @@ production_kernel(const __grid_constant__ ProdParams p) {
       if (p.ret) p.ret[g] = ok ? 0 : -1;
     }
     if (warp == PW - 1) fetch_next();    // (the lines / ticket of this galaxy were read into registers in phase A)
+    if constexpr (CL) {
+      // one warp of EVERY block per column, the stages in lock step across the cluster (ClusterSel)
+      float* glist = st3 + SLOTS * PT + warp * CL_GLIST_FLOATS;
+      unsigned* gcount = reinterpret_cast<unsigned*>(cand) + 1;
+      const int niter = (p.nstore + PW - 1) / PW;
+      const int ncol_pad = (int)csize * Npad;
+      for (int it = 0; it < niter; ++it) {
+        const int sl = it * PW + warp;
+        const bool has = sl < p.nstore;
+        const int k = has ? p.key_of_slot[sl] : 0;
+        const bool live = has && ((pm >> k) & 1ull);
+        const unsigned owner = (unsigned)sl % csize;
+        const float* col = vals + (long long)(has ? sl : 0) * Npad;
+        float* gcol = p.gscratch + ((long long)cl_id() * p.nstore + (has ? sl : 0)) * ncol_pad;
+        ClusterSel<SLOTS * PT / 128> cs;
+        cs.stage0(col, hist, cand, gcount, crank, live);
+        cl_sync();
+        cs.stage1(hist, crank, csize);
+        cl_sync();
+        cs.stage2(col, Npad, hist, cand, glist, gcount, owner, crank, gcol, soff);
+        __threadfence();
+        cl_sync();
+        if (live && crank == owner) {
+          float pc[3];
+          int nv, stt;
+          cs.stage3(Npad, hist, cand, glist, gcol, ncol_pad, pc, nv, stt);
+          if (lane == 0) {
+            atomicAdd(&p.stats[5], 1ull);
+            if (cs.fallback) atomicAdd(&p.stats[6], 1ull);
+            const long long o = (p.row0 + g) * NKEYS + k;
+            for (int q = 0; q < p.ndst; ++q) {
+              p.status[q][o] = (signed char)stt;
+              p.nvalid[q][o] = nv;
+              p.pct[q][3 * o] = pc[0];
+              p.pct[q][3 * o + 1] = pc[1];
+              p.pct[q][3 * o + 2] = pc[2];
+            }
+          }
+        }
+      }
+    } else
     for (int sl = warp; sl < p.nstore; sl += PW) {
       const int k = p.key_of_slot[sl];
       if (!((pm >> k) & 1ull)) continue;
@@ -939,6 +1115,7 @@ static uint32_t philox_calls(uint32_t tok, int correlated, int deterministic) {
 }
 
 struct ProdPlan {
+  int cluster;    // > 1: one galaxy per cluster of this many blocks (columns in distributed shared memory)
   bool global;
   bool wide;      // global variant with 32-bit histogram counters (Npad >= 65536)
   int scap;       // global variant: samples with their loop state in shared memory
@@ -951,7 +1128,7 @@ struct ProdPlan {
 // count, the "227 KB of dynamic shared memory" opt-in of every kernel (a function attribute is
 // per device) and the cooperative grid limit of the wide kernel are cached per device ordinal.
 static constexpr int MAX_DEVICES = 64;
-enum KernelId { KID_PROD_SHARED = 0, KID_PROD_GLOBAL, KID_PROD_GLOBAL_WIDE, KID_WIDE, KID_SELECT, KID_COUNT };
+enum KernelId { KID_PROD_SHARED = 0, KID_PROD_GLOBAL, KID_PROD_GLOBAL_WIDE, KID_PROD_CLUSTER, KID_WIDE, KID_SELECT, KID_COUNT };
 struct DeviceState {
   std::atomic<int> sms{0};
   std::atomic<int> attr_done[KID_COUNT];
@@ -985,6 +1162,40 @@ template <class K> static int ensure_smem_attr(K kernel, KernelId id, int bytes)
   return 0;
 }
 
+// how many clusters of `csz` blocks of the cluster kernel can be resident at once on this device
+// (0: the device / driver refuses the shape); cached per device and cluster size
+static int max_active_clusters(int csz, size_t smem) {
+  static std::atomic<int> cache[MAX_DEVICES][9];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= MAX_DEVICES) dev = 0;
+  const int c = cache[dev][csz].load();
+  if (c != 0) return c < 0 ? 0 : c;
+  int n = 0;
+  if (ensure_smem_attr(production_kernel<4, false, true>, KID_PROD_CLUSTER, 227 * 1024) == 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)csz * 64u);
+    cfg.blockDim = dim3(PT);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)csz; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    if (cudaOccupancyMaxActiveClusters(&n, production_kernel<4, false, true>, &cfg) != cudaSuccess) { n = 0; cudaGetLastError(); }
+  } else {
+    cudaGetLastError();
+  }
+  cache[dev][csz].store(n > 0 ? n : -1);
+  return n > 0 ? n : 0;
+}
+
+// MCZ_CLUSTER=1 / 0 forces the cluster kernel on / off for the shapes it covers; default: see DESIGN.md
+static bool cluster_wanted(const char* env) {
+  if (env && env[0] == '0') return false;
+  if (env && env[0] == '1') return true;
+  return MCZ_CLUSTER_DEFAULT != 0;
+}
+
 static ProdPlan make_plan(long long G, long long N, int nstore) {
   ProdPlan pl;
   // shared-memory variant: fixed column stride of 4*PT samples; layout = control block, columns,
@@ -995,6 +1206,25 @@ static ProdPlan make_plan(long long G, long long N, int nstore) {
   pl.global = !(N <= 4ll * PT && smem_local <= 227ull * 1024);
   pl.wide = false;
   pl.scap = 0;
+  pl.cluster = 1;
+  // Longer columns, up to 8 x 2304 samples: a cluster of ceil(N' / 2304) blocks per galaxy, each block
+  // laid out like the one-block kernel plus the owner's candidate lists (MCZ_CLUSTER=0: never)
+  const size_t smem_cluster = smem_local + (size_t)PW * CL_GLIST_FLOATS * sizeof(float);
+  const long long csz = (N + 4ll * PT - 1) / (4ll * PT);
+  const char* envc = getenv("MCZ_CLUSTER");
+  if (pl.global && csz >= 2 && csz <= 8 && smem_cluster <= 227ull * 1024 && cluster_wanted(envc)) {
+    const int nclus = max_active_clusters((int)csz, smem_cluster);
+    if (nclus > 0) {
+      pl.global = false;
+      pl.cluster = (int)csz;
+      pl.Npad = 4 * PT;
+      pl.smem = smem_cluster;
+      pl.per_block_floats = 0;
+      const long long nc = G < nclus ? (G > 0 ? G : 1) : nclus;
+      pl.grid = (int)(nc * csz);
+      return pl;
+    }
+  }
   if (!pl.global) {
     pl.Npad = 4 * PT;
     pl.smem = smem_local;
@@ -1018,7 +1248,7 @@ static ProdPlan make_plan(long long G, long long N, int nstore) {
 
 // The launch statistics live in the header of the caller's scratch buffer (no process-wide state):
 // bytes [64, 128) = galaxies, N2Ha trips executed, R23 trips executed, N2Ha proven-divergence exits,
-// R23 periodic-state exits, 3 spare.
+// R23 periodic-state exits, cluster kernel: columns selected, of which by the whole-column path; 1 spare.
 int read_launch_stats(const void* scratch_d, unsigned long long* out8, cudaStream_t stream) {
   int rc = check_cuda(cudaMemcpyAsync(out8, reinterpret_cast<const unsigned char*>(scratch_d) + SCRATCH_STATS_OFF,
                                       8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream), "read launch stats");
@@ -1065,6 +1295,8 @@ size_t production_scratch_bytes(long long G, long long n_draw, uint32_t tok) {
   build_slots(tok, p);
   const ProdPlan pl = make_plan(G, n_draw, p.nstore);
   size_t need = SCRATCH_HEADER + (size_t)pl.grid * (size_t)pl.per_block_floats * sizeof(float);
+  if (pl.cluster > 1)     // the fallback columns of every cluster: nstore x (cluster x 2304) floats
+    need = SCRATCH_HEADER + (size_t)(pl.grid / pl.cluster) * (size_t)p.nstore * (size_t)pl.cluster * (size_t)pl.Npad * sizeof(float);
   if (use_wide(G, n_draw, nullptr)) {
     const size_t w = wide_scratch_bytes(n_draw, p.nstore);
     if (w > need) need = w;
@@ -1078,6 +1310,7 @@ const char* production_kernel_name(long long G, long long n_draw, uint32_t tok) 
   build_slots(tok, p);
   if (use_wide(G, n_draw, nullptr)) return "wide_kernel";
   const ProdPlan pl = make_plan(G, n_draw, p.nstore);
+  if (pl.cluster > 1) return "production_kernel<4,0,cluster>";
   if (!pl.global) return "production_kernel<4,0>";
   return pl.wide ? "production_kernel<0,1>" : "production_kernel<0,0>";
 }
@@ -1120,15 +1353,31 @@ int launch_production(const float* meas, const float* err, long long G, long lon
   if ((ws && ws->world > 1) || use_wide(G, n_draw, Z)) return launch_wide(p, scratch, stream, ws);
   p.gscratch = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(scratch) + SCRATCH_HEADER);
   p.gscratch_per_block = pl.per_block_floats;
-  if (!pl.global) {
-    if ((rc = ensure_smem_attr(production_kernel<4, false>, KID_PROD_SHARED, 227 * 1024))) return rc;
-    production_kernel<4, false><<<pl.grid, PT, pl.smem, stream>>>(p);
+  if (getenv("MCZ_DEBUG_PLAN"))
+    fprintf(stderr, "mcz plan: cluster %d global %d wide %d grid %d smem %zu Npad %d\n", pl.cluster, (int)pl.global, (int)pl.wide,
+            pl.grid, pl.smem, pl.Npad);
+  if (pl.cluster > 1) {
+    if ((rc = ensure_smem_attr(production_kernel<4, false, true>, KID_PROD_CLUSTER, 227 * 1024))) return rc;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)pl.grid);
+    cfg.blockDim = dim3(PT);
+    cfg.dynamicSmemBytes = pl.smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)pl.cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    rc = check_cuda(cudaLaunchKernelEx(&cfg, production_kernel<4, false, true>, p), "cluster kernel launch");
+    if (rc) return rc;
+  } else if (!pl.global) {
+    if ((rc = ensure_smem_attr(production_kernel<4, false, false>, KID_PROD_SHARED, 227 * 1024))) return rc;
+    production_kernel<4, false, false><<<pl.grid, PT, pl.smem, stream>>>(p);
   } else if (!pl.wide) {
-    if ((rc = ensure_smem_attr(production_kernel<0, false>, KID_PROD_GLOBAL, 227 * 1024))) return rc;
-    production_kernel<0, false><<<pl.grid, PT, pl.smem, stream>>>(p);
+    if ((rc = ensure_smem_attr(production_kernel<0, false, false>, KID_PROD_GLOBAL, 227 * 1024))) return rc;
+    production_kernel<0, false, false><<<pl.grid, PT, pl.smem, stream>>>(p);
   } else {
-    if ((rc = ensure_smem_attr(production_kernel<0, true>, KID_PROD_GLOBAL_WIDE, 227 * 1024))) return rc;
-    production_kernel<0, true><<<pl.grid, PT, pl.smem, stream>>>(p);
+    if ((rc = ensure_smem_attr(production_kernel<0, true, false>, KID_PROD_GLOBAL_WIDE, 227 * 1024))) return rc;
+    production_kernel<0, true, false><<<pl.grid, PT, pl.smem, stream>>>(p);
   }
   count_launch();
   return check_cuda(cudaGetLastError(), "production_kernel launch");

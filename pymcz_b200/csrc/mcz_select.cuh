@@ -48,7 +48,9 @@ template <bool PACK16> struct FineHist {
   static constexpr int WORDS = PACK16 ? FB / 2 : FB;
   // + 32 spare words, one per lane: the streaming pass sends the increment of a sample that must not
   // be counted (NaN, inf, padding) there instead of making the atomic conditional
-  static constexpr int BYTES = WORDS * 4 + 128;
+  // + 4 words for the cluster kernel's exchange: [WORDS + 32] the block's count of the repeated value,
+  // [WORDS + 33] the block's column sum (float bits)
+  static constexpr int BYTES = WORDS * 4 + 128 + 16;
   static __device__ __forceinline__ void zero(unsigned* h, int lane) {
 #pragma unroll
     for (int i = 0; i < WORDS / 32; ++i) h[i * 32 + lane] = 0u;
@@ -421,10 +423,10 @@ __device__ void select_in_interval(const SelWarp& w, float lo, float hi, unsigne
 // Also reports a heavily repeated value of the prefix (>= 5 equal samples out of 64), e.g. the
 // E(B-V) = 1e-5 clamp: the histogram pass counts such a value with a vote instead of one shared
 // atomic per sample (same-address atomics serialise).
-__device__ __forceinline__ bool subsample_range(const float* __restrict__ v, int lane, float& scale, float& nLs,
-                                                bool& has_tie, float& tie) {
+// (a, b: samples `lane` and `lane + 32` of the column)
+__device__ __forceinline__ bool subsample_range_ab(float a, float b, int lane, float& scale, float& nLs,
+                                                   bool& has_tie, float& tie) {
   const float pinf = __int_as_float(0x7f800000);
-  float a = v[lane], b = v[lane + 32];
   a = finite_f(a) ? a : pinf;
   b = finite_f(b) ? b : pinf;
   const int m = __popc(__ballot_sync(0xffffffffu, a < pinf)) + __popc(__ballot_sync(0xffffffffu, b < pinf));
@@ -460,6 +462,11 @@ __device__ __forceinline__ bool subsample_range(const float* __restrict__ v, int
   scale = 1.0f / (H - L);               // u = saturate((x - L) / (H - L)), see fine_tbits
   nLs = -L * scale;
   return finite_f(scale) && finite_f(nLs) && scale > 0.0f;
+}
+
+__device__ __forceinline__ bool subsample_range(const float* __restrict__ v, int lane, float& scale, float& nLs,
+                                                bool& has_tie, float& tie) {
+  return subsample_range_ab(v[lane], v[lane + 32], lane, scale, nLs, has_tie, tie);
 }
 
 // ---- the selection of one column, in stages --------------------------------------------------
@@ -980,5 +987,188 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
   pct[0] = (float)(ts1 - ts0); pct[1] = (float)(clock64() - ts4); pct[2] = (float)(clock64() - ts0);   // range, finish, total
 #endif
 }
+
+// ---- cluster kernel: the selection of one column whose samples are spread over the blocks ------
+// Block r of the cluster holds piece r (Npad samples, NaN beyond the galaxy's N') of every column.
+// Warp w of EVERY block works on column slot w; the stages are separated by cluster barriers that
+// all warps of all blocks execute (ClusterSel::stage*), so the caller runs them in lock step:
+//   stage0  range from the column's first 64 samples (they live in block 0: read through DSMEM; if they
+//           give none -- an all-NaN column, typically -- everything goes to one bin);
+//           pass H over the block's own piece into the block's own histogram;
+//   -- barrier --
+//   stage1  merge of the histograms IN PLACE: block r sums words [r W/C, (r+1) W/C) of all blocks'
+//           tables and writes the totals back into every table (only block r ever touches that share
+//           anywhere, so no second buffer is needed); the counts of the repeated value and the column
+//           sums are exchanged through the spare words;
+//   -- barrier --
+//   stage2  every block makes the SAME plan from its (now global) table; pass G over the block's
+//           own piece, the members appended to the candidate list of the column's OWNER block
+//           (slot mod cluster size) with remote atomics;
+//   -- barrier --
+//   stage3  the owner sorts the candidates and interpolates, exactly as the one-block kernel does.
+// A column that needs the general path (a crowded range, a target in an end bin) is instead copied to a global scratch column by all blocks in stage 2
+// and handed, in stage 3, to the one-block selection (warp_percentiles) by its owner: rare, and
+// every special case keeps the code path that the adversarial tests cover.
+template <int NG> struct ClusterSel {
+  typedef FineHist<true> FH;
+  // per-warp state carried across the barriers
+  bool live, fallback, has_tie;
+  float scale, nLs, tie, sum_total;
+  unsigned ntie_total;
+  SelPlan P;
+
+  __device__ __forceinline__ void stage0(const float* v, unsigned* hist, float* cand, unsigned* gcount, unsigned crank,
+                                         bool is_live) {
+    const int lane = threadIdx.x & 31;
+    live = is_live;
+    fallback = false; has_tie = false; scale = 0.0f; nLs = 0.0f; tie = 0.0f; sum_total = 0.0f; ntie_total = 0u;
+    if (lane == 0) *gcount = 0u;                       // (only the owner's counter is used; appends come after two barriers)
+    (void)cand;
+    if (!live) return;
+    // first 64 samples of the column: block 0's piece
+    float a, b;
+    if (crank == 0u) { a = v[lane]; b = v[lane + 32]; }
+    else { const unsigned ra = cl_map(v, 0u); a = cl_ldf(ra + 4u * (unsigned)lane); b = cl_ldf(ra + 4u * (unsigned)(lane + 32)); }
+    // No usable range from the first 64 samples (usually: the column has no finite value at all):
+    // one bin for everything.  The merged count then says "empty" at once; a column that does hold
+    // finite values becomes one crowded bin and takes the whole-column path.
+    if (!subsample_range_ab(a, b, lane, scale, nLs, has_tie, tie)) { scale = 0.0f; nLs = 0.5f; has_tie = false; }
+    FH::zero(hist, lane);
+    const unsigned hist_sa = (unsigned)__cvta_generic_to_shared(hist);
+    const unsigned lane_sa = hist_sa + 4u * (unsigned)(FH::WORDS + lane);
+    float sum = 0.0f;
+    int ntie = 0;
+#pragma unroll 2
+    for (int s0 = 4 * lane; s0 < NG * 128; s0 += 128) {
+      const float4 x4 = *reinterpret_cast<const float4*>(v + s0);
+      const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool is_tie = has_tie && xs[j] == tie;
+        const bool fin = finite_f(xs[j]);
+        ntie += is_tie ? 1 : 0;
+        sum += fin ? xs[j] : 0.0f;
+        FH::add_t(hist_sa, lane_sa, fine_tbits(xs[j], scale, nLs), fin && !is_tie);
+      }
+    }
+    ntie = __reduce_add_sync(0xffffffffu, ntie);
+    sum = warp_sum(sum);
+    __syncwarp();
+    if (lane == 0) {
+      if (ntie > 0) FH::add_n(hist, fine_index(tie, scale, nLs), (unsigned)ntie);
+      hist[FH::WORDS + 32] = (unsigned)ntie;
+      hist[FH::WORDS + 33] = __float_as_uint(sum);
+    }
+  }
+
+  __device__ __forceinline__ void stage1(unsigned* hist, unsigned crank, unsigned csize) {
+    const int lane = threadIdx.x & 31;
+    if (!live || fallback) return;
+    const unsigned hs = (unsigned)__cvta_generic_to_shared(hist);
+    // the exchange words first (stage 2 needs the totals; they are outside every share)
+    unsigned nt = 0u;
+    float sm = 0.0f;
+    for (unsigned r = 0; r < csize; ++r) {            // same order in every block: same float total
+      const unsigned ra = cl_map(hs + 4u * (unsigned)(FH::WORDS + 32), r);
+      nt += cl_ld(ra);
+      sm += __uint_as_float(cl_ld(ra + 4u));
+    }
+    ntie_total = nt;
+    sum_total = sm;
+    // this block's share of the table: totals over all blocks, written back into every table
+    const int per = (FH::WORDS + (int)csize - 1) / (int)csize;
+    const int w0 = (int)crank * per, w1 = min(FH::WORDS, w0 + per);
+    for (int w = w0 + lane; w < w1; w += 32) {
+      unsigned tot = 0u;
+      for (unsigned r = 0; r < csize; ++r) tot += cl_ld(cl_map(hs + 4u * (unsigned)w, r));   // packed 16-bit pairs add without carry (< 65536 samples)
+      for (unsigned r = 0; r < csize; ++r) cl_st(cl_map(hs + 4u * (unsigned)w, r), tot);
+    }
+  }
+
+  // pass G of the block's piece; members go to the owner block's list
+  __device__ __forceinline__ void stage2(const float* v, int Npad, unsigned* hist, float* cand, float* glist, unsigned* gcount,
+                                         unsigned owner, unsigned crank, float* gcol, int soff) {
+    const int lane = threadIdx.x & 31;
+    if (!live) return;
+    if (!fallback) {
+      SelWarp w;
+      w.v = v; w.Npad = Npad; w.hist = hist; w.lane = lane;
+      w.ccount = reinterpret_cast<unsigned*>(cand); w.clist = cand + 32; w.glist = glist;
+      w.scale = scale; w.nLs = nLs; w.ngroups = Npad / 128; w.nmine = Npad;
+      sel_make_plan<true>(w, P, has_tie, tie, has_tie ? fine_index(tie, scale, nLs) : 0, ntie_total);
+      if (P.n == 0) return;                          // no finite value anywhere: the owner reports "empty"
+      bool general = P.crowded[0] || P.crowded[1] || P.crowded[2];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+        if (r < P.nr && (P.rlo[r] == 0 || P.rhi[r] == FB - 1)) general = true;
+      if (general) fallback = true;
+    }
+    if (fallback) {
+      // the block's piece of the column -> global scratch column of the cluster (owner selects it whole)
+      for (int s = lane; s < Npad; s += 32) gcol[soff + s] = v[s];
+      return;
+    }
+    int tlo[3];
+    unsigned tsp[3];
+    sel_tests(P, true, tlo, tsp);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) tlo[r] += FINE_BIAS;
+    const float skip = P.tie;                         // NaN unless the repeated value is merged back by rank
+    const unsigned cnt_ra = cl_map(gcount, owner), list_ra = cl_map(glist, owner);
+    constexpr int CH = 6;
+#pragma unroll 1
+    for (int g0 = 0; g0 < NG; g0 += CH) {
+      unsigned mask = 0u;
+#pragma unroll
+      for (int i = 0; i < CH; ++i) {
+        if (g0 + i < NG) {
+          const float4 x4 = *reinterpret_cast<const float4*>(v + 4 * lane + 128 * (g0 + i));
+          const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int f = fine_tbits(xs[j], scale, nLs);
+            const bool hit = ((unsigned)(f - tlo[0]) <= tsp[0]) || ((unsigned)(f - tlo[1]) <= tsp[1]) ||
+                             ((unsigned)(f - tlo[2]) <= tsp[2]);
+            mask |= (hit && xs[j] != skip) ? (1u << (4 * i + j)) : 0u;
+          }
+        }
+      }
+      if (mask) {
+        unsigned pos = cl_atom_add(cnt_ra, (unsigned)__popc(mask));
+        do {
+          const int b = __ffs(mask) - 1;
+          mask &= mask - 1u;
+          cl_stf(list_ra + 4u * min(pos, 191u), v[4 * lane + 128 * (g0 + (b >> 2)) + (b & 3)]);   // (<= 192 by the plan)
+          ++pos;
+        } while (mask);
+      }
+    }
+  }
+
+  // owner only: the percentiles of the column
+  __device__ __forceinline__ void stage3(int Npad, unsigned* hist, float* cand, float* glist, float* gcol, int ncol_pad,
+                                         float pct[3], int& nvalid, int& status) {
+    const int lane = threadIdx.x & 31;
+    pct[0] = pct[1] = pct[2] = Math<float>::nan();
+    nvalid = 0;
+    status = ST_EMPTY;
+    if (fallback) {                                   // the whole column, by the one-block code
+      warp_percentiles<true, 0>(gcol, ncol_pad, hist, cand, pct, nvalid, status);
+      return;
+    }
+    nvalid = P.n;
+    if (P.n == 0) return;                                                             // mcz.py:277-280
+    if (!(sum_total > 0.0f)) { status = ST_NONPOS; return; }                          // mcz.py:282-285
+    status = ST_OK;
+    SelWarp w;
+    w.v = nullptr; w.Npad = Npad; w.hist = hist; w.lane = lane;
+    w.ccount = reinterpret_cast<unsigned*>(cand); w.clist = cand + 32; w.glist = glist;
+    w.scale = scale; w.nLs = nLs; w.ngroups = 0; w.nmine = 0;
+    const float pinf = __int_as_float(0x7f800000), ninf = __int_as_float(0xff800000);
+    const float bmn[3] = {pinf, pinf, pinf}, bmx[3] = {ninf, ninf, ninf};
+    const unsigned nmin[3] = {0u, 0u, 0u};
+    sel_finish<true>(w, P, bmn, bmx, nmin, pct);
+  }
+};
 
 }  // namespace mcz

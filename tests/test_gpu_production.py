@@ -204,19 +204,69 @@ def test_flag_fallback_and_missing_lines():
     assert np.max(np.abs(Z[both] - Zo[both])) < 1e-3
 
 
-def test_large_nsample_global_variant():
-    """N' = 11000 (configs 3/5 shape) runs the global-scratch instantiation."""
-    meas, err = synthetic_table(100, config=3)
-    n = 11000
-    pct, nvalid, status, trips, ret, Z = run_prod(meas, err, n, seed=5, goff=0)
-    Zo, po, trips_o = oracle_on_kernel_samples(meas, err, n, 5, 0, "all", True, False)
-    compare_with_oracle(Z, status, trips, Zo, po, trips_o, what="N'=11000")
+def _check_long_columns(n, ngal, mds, seed=5):
+    meas, err = synthetic_table(ngal, config=3)
+    pct, nvalid, status, trips, ret, Z = run_prod(meas, err, n, mds, seed=seed, goff=0)
+    Zo, po, trips_o = oracle_on_kernel_samples(meas, err, n, seed, 0, mds, True, False)
+    compare_with_oracle(Z, status, trips, Zo, po, trips_o, what="N'=%d %s" % (n, mds))
     for g in range(meas.shape[0]):
         for j in range(sc.NKEYS):
+            col = Z[g, j][np.isfinite(Z[g, j])]
+            if status[g, j] == sc.ST_ABSENT:
+                continue
+            assert nvalid[g, j] == col.size, (g, sc.KEYS[j])
             if status[g, j] == sc.ST_OK:
-                fin = Z[g, j][np.isfinite(Z[g, j])]
-                want = np.percentile(fin.astype(np.float64), [50, 16, 84]).astype(np.float32)
+                want = np.percentile(col.astype(np.float64), [50, 16, 84]).astype(np.float32)
                 assert np.array_equal(pct[g, j], want), (g, sc.KEYS[j])
+            elif col.size:
+                assert status[g, j] == sc.ST_NONPOS and not (np.sum(col.astype(np.float64)) > 0)
+    return pct, nvalid, status, trips
+
+
+@pytest.mark.parametrize("n,ngal,mds", [(11000, 120, "all"), (11000, 120, "KD02"), (2305, 60, "all"), (4608, 60, "all"),
+                                        (7000, 60, "all"), (18432, 40, "KD02")])
+def test_cluster_kernel_long_columns(n, ngal, mds):
+    """2304 < N' <= 8 x 2304 (configs 3 and 5 are N' = 11000): one galaxy per thread-block CLUSTER, the
+    columns in distributed shared memory.  Per-sample values, masks and trip counts against the oracle
+    on the kernel's own samples; the percentile table against numpy on the kernel's own columns; and the
+    same tables as the global-scratch variant (MCZ_CLUSTER=0) wherever the trip counts agree."""
+    from pymcz_b200 import _lib
+    import os
+    tok, _, _ = sc.parse_md(mds)
+    old = os.environ.get("MCZ_CLUSTER")
+    try:
+        os.environ["MCZ_CLUSTER"] = "1"
+        assert b"cluster" in _lib.lib().mcz_production_kernel_name(ngal, n, tok)
+        pct, nvalid, status, trips = _check_long_columns(n, ngal, mds)
+        os.environ["MCZ_CLUSTER"] = "0"
+        assert b"cluster" not in _lib.lib().mcz_production_kernel_name(ngal, n, tok)
+        meas, err = synthetic_table(ngal, config=3)
+        ref = run_prod(meas, err, n, mds, seed=5, goff=0, samples=False)
+    finally:
+        if old is None:
+            del os.environ["MCZ_CLUSTER"]
+        else:
+            os.environ["MCZ_CLUSTER"] = old
+    same = np.all(trips == ref[3], axis=1)
+    assert same.mean() >= 0.98
+    assert np.array_equal(status, ref[2])
+    assert np.array_equal(nvalid[same], ref[1][same])
+    assert np.allclose(pct[same], ref[0][same], rtol=0, atol=1e-5, equal_nan=True)
+
+
+@pytest.mark.parametrize("n,ngal", [(22000, 12), (11000, 100)])
+def test_large_nsample_global_variant(n, ngal):
+    """N' = 22000 (config 2 shape) and 11000 (configs 3 / 5) on the global-scratch instantiation."""
+    import os
+    old = os.environ.get("MCZ_CLUSTER")
+    os.environ["MCZ_CLUSTER"] = "0"
+    try:
+        _check_long_columns(n, ngal, "all")
+    finally:
+        if old is None:
+            del os.environ["MCZ_CLUSTER"]
+        else:
+            os.environ["MCZ_CLUSTER"] = old
 
 
 def test_deterministic_single_evaluation():
