@@ -989,20 +989,33 @@ production_kernel(const __grid_constant__ ProdParams p) {
         const float* col = vals + (long long)(has ? sl : 0) * Npad;
         float* gcol = p.gscratch + ((long long)cl_id() * p.nstore + (has ? sl : 0)) * ncol_pad;
         ClusterSel<SLOTS * PT / 128> cs;
-        cs.stage0(col, hist, cand, gcount, crank, live);
+        cs.init(col, Npad, hist, cand, glist, gcount, live);
+        cs.range(crank);
+        cs.histogram(live);
         cl_sync();
-        cs.stage1(hist, crank, csize);
+        cs.merge(live, crank, csize);
         cl_sync();
-        cs.stage2(col, Npad, hist, cand, glist, gcount, owner, crank, gcol, soff);
+        cs.plan_and_gather(live, false, gcount, owner, gcol, soff);
+        // second round, if any column of the galaxy asks for it: every block holds the same columns and
+        // makes the same plans, so this block-level vote is the same in every block of the cluster
+        if (__syncthreads_or(live && cs.refine)) {
+          const bool again = live && cs.refine;
+          cs.histogram(again);
+          cl_sync();
+          cs.merge(again, crank, csize);
+          cl_sync();
+          cs.plan_and_gather(again, true, gcount, owner, gcol, soff);
+        }
         __threadfence();
         cl_sync();
         if (live && crank == owner) {
           float pc[3];
           int nv, stt;
-          cs.stage3(Npad, hist, cand, glist, gcol, ncol_pad, pc, nv, stt);
+          cs.finish(cand, gcol, ncol_pad, pc, nv, stt);
           if (lane == 0) {
             atomicAdd(&p.stats[5], 1ull);
             if (cs.fallback) atomicAdd(&p.stats[6], 1ull);
+            if (cs.refine) atomicAdd(&p.stats[7], 1ull);
             const long long o = (p.row0 + g) * NKEYS + k;
             for (int q = 0; q < p.ndst; ++q) {
               p.status[q][o] = (signed char)stt;
@@ -1402,6 +1415,8 @@ struct WideCtl {
   unsigned nan[3];                // NaN bits of the KK04 sums, rotating with sums[]
   long long sums[3][4];           // fixed point, 18 fractional bits, per-sample rounding (wfx)
   double colsum[NKEYS];           // per slot: sum of the finite values (sum <= 0 test, mcz.py:282-285)
+  unsigned umaxo[NKEYS];          // per slot: max of the ordered bit patterns of the finite values ...
+  unsigned nmino[NKEYS];          // ... and max of their complements (= ~min): the radix select skips the common prefix
 };
 static_assert(sizeof(WideCtl) <= 4096, "wide control block too large");
 
@@ -1735,12 +1750,62 @@ wide_kernel(const __grid_constant__ ProdParams p) {
       for (int t = 0; t < 6; ++t) { tpre[h][t] = 0u; trk[h][t] = 0u; }
     }
     unsigned short* rh = reinterpret_cast<unsigned short*>(hist);      // [6][256] 16-bit counters
+    // The finite values of a column share their leading bits (sign, exponent, often the first
+    // mantissa bits): a digit taken there puts every sample into one or two bins, and the shared-
+    // memory atomics of a warp serialise on them.  So the extremes of the ordered bit patterns are
+    // reduced first (one pass, one barrier), the common prefix is taken as known, and the 8-bit
+    // rounds start at the first bit in which the extremes differ: usually three well-spread rounds
+    // instead of four, the first two of which were all conflicts.
+    int Tbits[2] = {0, 0};      // bits still to resolve per slot
 #pragma unroll 1
-    for (int round = 0; round < 4; ++round) {
-      const int shift = 24 - 8 * round;
+    for (int h = 0; h < 2; ++h) {
+      if (!live[h]) continue;
+      const int sl = warp + h * PW;
+      const float* col = vals + (long long)sl * Npad;
+      unsigned lmax = 0u, lnmin = 0u;
+      for (int g0 = g_lo; g0 < g_hi; ++g0) {
+        const float4 x4 = *reinterpret_cast<const float4*>(col + 4 * lane + 128 * g0);
+        const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const unsigned u = finite_f(xs[j]) ? ordered_bits(xs[j]) : 0u;
+          lmax = max(lmax, u);
+          lnmin = max(lnmin, u ? ~u : 0u);
+        }
+      }
+      lmax = __reduce_max_sync(0xffffffffu, lmax);
+      lnmin = __reduce_max_sync(0xffffffffu, lnmin);
+      if (lane == 0 && lmax)
+        for (int r = 0; r < W; ++r) {
+          atomicMax_system(reinterpret_cast<unsigned*>(peer(&ctl->umaxo[sl], r)), lmax);
+          atomicMax_system(reinterpret_cast<unsigned*>(peer(&ctl->nmino[sl], r)), lnmin);
+        }
+    }
+    xsync();
+    int Rmax = 1;
+    for (int sl = 0; sl < p.nstore; ++sl) {
+      const unsigned umx = *reinterpret_cast<volatile unsigned*>(&ctl->umaxo[sl]);
+      const unsigned umn = ~*reinterpret_cast<volatile unsigned*>(&ctl->nmino[sl]);
+      const int T = umx ? 32 - __clz(umx ^ umn) : 0;
+      Rmax = max(Rmax, (T + 7) / 8);
+      if (sl == warp || sl == warp + PW) {
+        const int h = sl == warp ? 0 : 1;
+        if (!umx) live[h] = false;                       // no finite value in the column
+        Tbits[h] = T;
+        const unsigned pre = T >= 32 ? 0u : (umx >> T);
+#pragma unroll
+        for (int t = 0; t < 6; ++t) tpre[h][t] = pre;
+      }
+    }
+#pragma unroll 1
+    for (int round = 0; round < Rmax; ++round) {
 #pragma unroll 1
       for (int h = 0; h < 2; ++h) {
-        if (!live[h]) continue;
+        if (!live[h] || (round > 0 && 8 * round >= Tbits[h])) continue;
+        // this round resolves bits [lo, hi) of the patterns; everything above hi is in tpre
+        const int hi = Tbits[h] - 8 * round, lo = max(hi - 8, 0);
+        const int shift = lo;
+        const unsigned dmask = (1u << (hi - lo)) - 1u;      // (a column of equal values: hi = lo = 0, one bin)
         const int sl = warp + h * PW;
         const float* col = vals + (long long)sl * Npad;
         // distinct prefixes among the six targets (ascending ranks -> non-decreasing prefixes)
@@ -1766,12 +1831,12 @@ wide_kernel(const __grid_constant__ ProdParams p) {
             if (!finite_f(x)) continue;
             if (round == 0) sum += x;
             const unsigned u = ordered_bits(x);
-            const unsigned pre = round == 0 ? 0u : (u >> (shift + 8));
+            const unsigned pre = hi >= 32 ? 0u : (u >> hi);
             int which = -1;
 #pragma unroll
             for (int i = 0; i < 6; ++i) if (i < nu && uq[i] == pre) which = i;
             if (which >= 0) {
-              const unsigned bin = (u >> shift) & 255u;
+              const unsigned bin = (u >> shift) & dmask;
               const unsigned idx = (unsigned)which * 256u + bin;
               atomicAdd(hist + (idx >> 1), 1u << ((idx & 1u) << 4));
             }
@@ -1795,7 +1860,8 @@ wide_kernel(const __grid_constant__ ProdParams p) {
       xsync();
 #pragma unroll 1
       for (int h = 0; h < 2; ++h) {
-        if (!live[h]) continue;
+        if (!live[h] || (round > 0 && 8 * round >= Tbits[h])) continue;
+        const int hi = Tbits[h] - 8 * round, lo = max(hi - 8, 0);
         const int sl = warp + h * PW;
         const unsigned* gh = ghist + (((long long)round * p.nstore + sl) * 6) * 256;
         unsigned uq[6];
@@ -1846,7 +1912,7 @@ wide_kernel(const __grid_constant__ ProdParams p) {
           }
           const unsigned gbin = __shfl_sync(0xffffffffu, 8u * (unsigned)lane + bin, ol);
           const unsigned gbefore = __shfl_sync(0xffffffffu, before, ol);
-          tpre[h][t] = (tpre[h][t] << 8) | gbin;
+          tpre[h][t] = (hi - lo >= 32 ? 0u : (tpre[h][t] << (hi - lo))) | gbin;
           trk[h][t] = r - gbefore;
         }
       }

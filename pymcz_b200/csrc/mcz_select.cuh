@@ -173,6 +173,10 @@ struct SelWarp {
   float* glist;            // 192 candidates of pass G; aliases hist, which the plan has consumed by then
   int lane;
   float scale, nLs;        // fine index of the first round
+  // cluster kernel, second round: the (at most three) target ranges of the first round are
+  // subdivided into RSUB bins each (see fine_tbits_w); rnr = 0: plain first-round index
+  int rnr, rflo[3], rfhi[3];
+  float rmul[3];
 #ifdef MCZ_COLTIME_DUMP
   mutable int dbg;
 #endif
@@ -192,6 +196,35 @@ __device__ __forceinline__ int fine_tbits(float x, float scale, float nLs) {
 }
 __device__ __forceinline__ int fine_index(float x, float scale, float nLs) {
   return fine_tbits(x, scale, nLs) - FINE_BIAS;
+}
+
+// Second-round index of the cluster kernel.  Layout of the 1024 bins, RSUB = 339 per range:
+//   [0] below range 0 | [1, RSUB] range 0 | [RSUB+1] between | [RSUB+2, 2 RSUB+1] range 1 | [2 RSUB+2]
+//   between | [2 RSUB+3, 3 RSUB+2] range 2 | [3 RSUB+3] above.  Inside a range the position is
+//   u * 1023 - (lo - 0.5) in [0, width), u the saturated first-round coordinate, cut into RSUB
+//   pieces: monotone in x like the first-round index, ~340 / width times finer.
+static constexpr int RSUB = 339;
+__device__ __forceinline__ int fine_tbits_w(const SelWarp& w, float x) {
+  const int tb = fine_tbits(x, w.scale, w.nLs);
+  if (w.rnr == 0) return tb;
+  const int f1 = tb - FINE_BIAS;
+  float u;
+  asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(u) : "f"(x), "f"(w.scale), "f"(w.nLs));
+  int idx = 0;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    if (r < w.rnr) {
+      const int base = r * (RSUB + 1);
+      if (f1 > w.rfhi[r]) idx = base + RSUB + 1;
+      else if (f1 >= w.rflo[r]) {
+        const float v = fmaf(u, (float)(FB - 1), 0.5f - (float)w.rflo[r]);
+        int sub = __float2int_rd(v * w.rmul[r]);
+        sub = sub < 0 ? 0 : (sub > RSUB - 1 ? RSUB - 1 : sub);
+        idx = base + 1 + sub;
+      }
+    }
+  }
+  return idx + FINE_BIAS;
 }
 
 // After pass H: every lane gets its exclusive prefix over lanes (32 bins per lane) and its total.
@@ -639,7 +672,7 @@ __device__ __forceinline__ void sel_finish(const SelWarp& w, const SelPlan& P, c
         for (unsigned i0 = 0; i0 < P.ncand; i0 += 32u) {
           const unsigned i = i0 + (unsigned)lane;
           const float x = w.glist[i & 255u];
-          const bool in = i < P.ncand && (unsigned)(fine_index(x, w.scale, w.nLs) - lo_t) <= sp_t;
+          const bool in = i < P.ncand && (unsigned)(fine_tbits_w(w, x) - FINE_BIAS - lo_t) <= sp_t;
           const unsigned m = __ballot_sync(0xffffffffu, in);
           if (in) w.clist[(c + __popc(m & lt)) & 63u] = x;
           c += __popc(m);
@@ -737,6 +770,7 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
   const int lane = threadIdx.x & 31;
   SelWarp w;
   w.v = v; w.Npad = Npad; w.hist = hist; w.lane = lane;
+  w.rnr = 0;
   w.ccount = reinterpret_cast<unsigned*>(cand);
   w.clist = cand + 32;
   w.glist = reinterpret_cast<float*>(hist);
@@ -1012,35 +1046,55 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
 template <int NG> struct ClusterSel {
   typedef FineHist<true> FH;
   // per-warp state carried across the barriers
-  bool live, fallback, has_tie;
-  float scale, nLs, tie, sum_total;
+  bool live, fallback, has_tie, refine, gathered, norange;
+  float tie, sum_total, gmin, gmax;
   unsigned ntie_total;
+  SelWarp w;
   SelPlan P;
 
-  __device__ __forceinline__ void stage0(const float* v, unsigned* hist, float* cand, unsigned* gcount, unsigned crank,
-                                         bool is_live) {
+  __device__ __forceinline__ void init(const float* v, int Npad, unsigned* hist, float* cand, float* glist, unsigned* gcount,
+                                       bool is_live) {
     const int lane = threadIdx.x & 31;
     live = is_live;
-    fallback = false; has_tie = false; scale = 0.0f; nLs = 0.0f; tie = 0.0f; sum_total = 0.0f; ntie_total = 0u;
-    if (lane == 0) *gcount = 0u;                       // (only the owner's counter is used; appends come after two barriers)
-    (void)cand;
+    fallback = false; has_tie = false; refine = false; gathered = false; norange = false;
+    tie = 0.0f; sum_total = 0.0f; ntie_total = 0u; gmin = 0.0f; gmax = 0.0f;
+    w.v = v; w.Npad = Npad; w.hist = hist; w.lane = lane;
+    w.ccount = reinterpret_cast<unsigned*>(cand); w.clist = cand + 32; w.glist = glist;
+    w.scale = 0.0f; w.nLs = 0.5f; w.ngroups = Npad / 128; w.nmine = Npad; w.rnr = 0;
+    if (lane == 0) *gcount = 0u;          // (only the owner's counter is used; appends come after two barriers)
+  }
+
+  // range of the first round from the column's first 64 samples (block 0's piece)
+  __device__ __forceinline__ void range(unsigned crank) {
     if (!live) return;
-    // first 64 samples of the column: block 0's piece
+    const int lane = w.lane;
     float a, b;
-    if (crank == 0u) { a = v[lane]; b = v[lane + 32]; }
-    else { const unsigned ra = cl_map(v, 0u); a = cl_ldf(ra + 4u * (unsigned)lane); b = cl_ldf(ra + 4u * (unsigned)(lane + 32)); }
-    // No usable range from the first 64 samples (usually: the column has no finite value at all):
-    // one bin for everything.  The merged count then says "empty" at once; a column that does hold
-    // finite values becomes one crowded bin and takes the whole-column path.
-    if (!subsample_range_ab(a, b, lane, scale, nLs, has_tie, tie)) { scale = 0.0f; nLs = 0.5f; has_tie = false; }
+    if (crank == 0u) { a = w.v[lane]; b = w.v[lane + 32]; }
+    else { const unsigned ra = cl_map(w.v, 0u); a = cl_ldf(ra + 4u * (unsigned)lane); b = cl_ldf(ra + 4u * (unsigned)(lane + 32)); }
+    // No usable range from the first 64 samples (usually: the column has no finite value at all, or
+    // it is one repeated value, which `has_tie` then covers): one bin for everything in the first
+    // round, which also reduces the exact min / max of the column.  The merged count says "empty" at
+    // once; a column that does hold a spread of finite values gets its real histogram in the second
+    // round, over the exact range.
+    if (!subsample_range_ab(a, b, lane, w.scale, w.nLs, has_tie, tie)) { w.scale = 0.0f; w.nLs = 0.5f; norange = true; }
+  }
+
+  // pass H over the block's own piece with the current index (first round, or second if w.rnr > 0)
+  __device__ __forceinline__ void histogram(bool active) {
+    if (!active) return;
+    const int lane = w.lane;
+    unsigned* hist = w.hist;
     FH::zero(hist, lane);
     const unsigned hist_sa = (unsigned)__cvta_generic_to_shared(hist);
     const unsigned lane_sa = hist_sa + 4u * (unsigned)(FH::WORDS + lane);
     float sum = 0.0f;
     int ntie = 0;
+    const float pinf = __int_as_float(0x7f800000), ninf = __int_as_float(0xff800000);
+    float mn = pinf, mx = ninf;
+    const bool track = norange && !refine;      // (first round of a column without a range: its exact extremes)
 #pragma unroll 2
     for (int s0 = 4 * lane; s0 < NG * 128; s0 += 128) {
-      const float4 x4 = *reinterpret_cast<const float4*>(v + s0);
+      const float4 x4 = *reinterpret_cast<const float4*>(w.v + s0);
       const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -1048,64 +1102,103 @@ template <int NG> struct ClusterSel {
         const bool fin = finite_f(xs[j]);
         ntie += is_tie ? 1 : 0;
         sum += fin ? xs[j] : 0.0f;
-        FH::add_t(hist_sa, lane_sa, fine_tbits(xs[j], scale, nLs), fin && !is_tie);
+        if (track) { mn = fminf(mn, fin ? xs[j] : pinf); mx = fmaxf(mx, fin ? xs[j] : ninf); }
+        FH::add_t(hist_sa, lane_sa, fine_tbits_w(w, xs[j]), fin && !is_tie);
       }
     }
     ntie = __reduce_add_sync(0xffffffffu, ntie);
     sum = warp_sum(sum);
+    if (track) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      }
+    }
     __syncwarp();
     if (lane == 0) {
-      if (ntie > 0) FH::add_n(hist, fine_index(tie, scale, nLs), (unsigned)ntie);
+      if (ntie > 0) FH::add_n(hist, fine_tbits_w(w, tie) - FINE_BIAS, (unsigned)ntie);
       hist[FH::WORDS + 32] = (unsigned)ntie;
       hist[FH::WORDS + 33] = __float_as_uint(sum);
+      hist[FH::WORDS + 34] = __float_as_uint(mn);
+      hist[FH::WORDS + 35] = __float_as_uint(mx);
     }
   }
 
-  __device__ __forceinline__ void stage1(unsigned* hist, unsigned crank, unsigned csize) {
-    const int lane = threadIdx.x & 31;
-    if (!live || fallback) return;
-    const unsigned hs = (unsigned)__cvta_generic_to_shared(hist);
-    // the exchange words first (stage 2 needs the totals; they are outside every share)
+  // merge of the blocks' tables, in place
+  __device__ __forceinline__ void merge(bool active, unsigned crank, unsigned csize) {
+    if (!active) return;
+    const int lane = w.lane;
+    const unsigned hs = (unsigned)__cvta_generic_to_shared(w.hist);
+    // the exchange words first (they are outside every share)
     unsigned nt = 0u;
-    float sm = 0.0f;
+    float sm = 0.0f, mn = __int_as_float(0x7f800000), mx = __int_as_float(0xff800000);
     for (unsigned r = 0; r < csize; ++r) {            // same order in every block: same float total
       const unsigned ra = cl_map(hs + 4u * (unsigned)(FH::WORDS + 32), r);
       nt += cl_ld(ra);
       sm += __uint_as_float(cl_ld(ra + 4u));
+      if (norange && !refine) { mn = fminf(mn, cl_ldf(ra + 8u)); mx = fmaxf(mx, cl_ldf(ra + 12u)); }
     }
     ntie_total = nt;
     sum_total = sm;
+    if (norange && !refine) { gmin = mn; gmax = mx; }
     // this block's share of the table: totals over all blocks, written back into every table
     const int per = (FH::WORDS + (int)csize - 1) / (int)csize;
     const int w0 = (int)crank * per, w1 = min(FH::WORDS, w0 + per);
-    for (int w = w0 + lane; w < w1; w += 32) {
+    for (int i = w0 + lane; i < w1; i += 32) {
+      unsigned part[8];
+#pragma unroll
+      for (unsigned r = 0; r < 8u; ++r) part[r] = r < csize ? cl_ld(cl_map(hs + 4u * (unsigned)i, r)) : 0u;   // (all loads in flight at once)
       unsigned tot = 0u;
-      for (unsigned r = 0; r < csize; ++r) tot += cl_ld(cl_map(hs + 4u * (unsigned)w, r));   // packed 16-bit pairs add without carry (< 65536 samples)
-      for (unsigned r = 0; r < csize; ++r) cl_st(cl_map(hs + 4u * (unsigned)w, r), tot);
+#pragma unroll
+      for (unsigned r = 0; r < 8u; ++r) tot += part[r];                   // packed 16-bit pairs: no carry (< 65536 samples)
+      for (unsigned r = 0; r < csize; ++r) cl_st(cl_map(hs + 4u * (unsigned)i, r), tot);
     }
   }
 
-  // pass G of the block's piece; members go to the owner block's list
-  __device__ __forceinline__ void stage2(const float* v, int Npad, unsigned* hist, float* cand, float* glist, unsigned* gcount,
-                                         unsigned owner, unsigned crank, float* gcol, int soff) {
-    const int lane = threadIdx.x & 31;
-    if (!live) return;
-    if (!fallback) {
-      SelWarp w;
-      w.v = v; w.Npad = Npad; w.hist = hist; w.lane = lane;
-      w.ccount = reinterpret_cast<unsigned*>(cand); w.clist = cand + 32; w.glist = glist;
-      w.scale = scale; w.nLs = nLs; w.ngroups = Npad / 128; w.nmine = Npad;
-      sel_make_plan<true>(w, P, has_tie, tie, has_tie ? fine_index(tie, scale, nLs) : 0, ntie_total);
-      if (P.n == 0) return;                          // no finite value anywhere: the owner reports "empty"
-      bool general = P.crowded[0] || P.crowded[1] || P.crowded[2];
+  // plan from the merged table; then pass G (members to the owner's list), or the decision to
+  // refine (first round only), or the whole-column path
+  __device__ __forceinline__ void plan_and_gather(bool active, bool second, unsigned* gcount, unsigned owner, float* gcol, int soff) {
+    if (!active) return;
+    const int lane = w.lane;
+    sel_make_plan<true>(w, P, has_tie, tie, has_tie ? fine_tbits_w(w, tie) - FINE_BIAS : 0, ntie_total);
+    if (P.n == 0) { gathered = true; return; }          // no finite value anywhere: the owner reports "empty"
+    bool crowded = P.crowded[0] || P.crowded[1] || P.crowded[2], edge = false;
 #pragma unroll
-      for (int r = 0; r < 3; ++r)
-        if (r < P.nr && (P.rlo[r] == 0 || P.rhi[r] == FB - 1)) general = true;
-      if (general) fallback = true;
+    for (int r = 0; r < 3; ++r)
+      if (r < P.nr && (P.rlo[r] == 0 || P.rhi[r] == FB - 1)) edge = true;
+    if (!second && norange && crowded && gmax > gmin) {
+      // second round over the exact range of the column (as exact_range() of the one-block selection)
+      refine = true;
+      const float d = (gmax - gmin) * (2.0f / (float)(FB - 4));
+      const float qlo = gmin - d, qhi = gmax + d;
+      w.scale = 1.0f / (qhi - qlo);
+      w.nLs = -qlo * w.scale;
+      if (!finite_f(w.scale) || !finite_f(w.nLs) || !(w.scale > 0.0f)) { w.scale = 0.0f; w.nLs = 0.5f; }
+      return;
     }
-    if (fallback) {
-      // the block's piece of the column -> global scratch column of the cluster (owner selects it whole)
-      for (int s = lane; s < Npad; s += 32) gcol[soff + s] = v[s];
+    if (!second && crowded && !edge) {
+      // second round: subdivide the target ranges (every block takes the same decision from the same table)
+      refine = true;
+      w.rnr = P.nr;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        w.rflo[r] = r < P.nr ? P.rlo[r] : 0;
+        w.rfhi[r] = r < P.nr ? P.rhi[r] : 0;
+        w.rmul[r] = r < P.nr ? (float)RSUB / (float)(P.rhi[r] - P.rlo[r] + 1) : 0.0f;
+      }
+      return;
+    }
+    if (crowded || edge) {
+      // whole-column path: the block's piece -> global scratch column of the cluster (the owner selects it)
+      fallback = true;
+#ifdef MCZ_DEBUG_FALLBACK
+      if (lane == 0 && owner == cl_rank())
+        printf("fallback second=%d n=%d nr=%d edge=%d crowded=%d%d%d rM=%u %u %u rlo=%d %d %d rhi=%d %d %d tie=%d ntie=%u has_tie=%d scale=%g\n", (int)second, P.n, P.nr, (int)edge,
+               (int)P.crowded[0], (int)P.crowded[1], (int)P.crowded[2], P.rM[0], P.rM[1], P.rM[2], P.rlo[0], P.rlo[1], P.rlo[2],
+               P.rhi[0], P.rhi[1], P.rhi[2], P.tie_range, ntie_total, (int)has_tie, (double)w.scale);
+#endif
+      for (int s = lane; s < w.Npad; s += 32) gcol[soff + s] = w.v[s];
       return;
     }
     int tlo[3];
@@ -1114,56 +1207,61 @@ template <int NG> struct ClusterSel {
 #pragma unroll
     for (int r = 0; r < 3; ++r) tlo[r] += FINE_BIAS;
     const float skip = P.tie;                         // NaN unless the repeated value is merged back by rank
-    const unsigned cnt_ra = cl_map(gcount, owner), list_ra = cl_map(glist, owner);
+    const unsigned cnt_ra = cl_map(gcount, owner), list_ra = cl_map(w.glist, owner);
     constexpr int CH = 6;
-#pragma unroll 1
-    for (int g0 = 0; g0 < NG; g0 += CH) {
-      unsigned mask = 0u;
+    constexpr int NCH = (NG + CH - 1) / CH;
+    unsigned m[NCH];
 #pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      unsigned mask = 0u;
+#pragma unroll 2
       for (int i = 0; i < CH; ++i) {
-        if (g0 + i < NG) {
-          const float4 x4 = *reinterpret_cast<const float4*>(v + 4 * lane + 128 * (g0 + i));
+        if (c * CH + i < NG) {
+          const float4 x4 = *reinterpret_cast<const float4*>(w.v + 4 * lane + 128 * (c * CH + i));
           const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const int f = fine_tbits(xs[j], scale, nLs);
+            const int f = fine_tbits_w(w, xs[j]);
             const bool hit = ((unsigned)(f - tlo[0]) <= tsp[0]) || ((unsigned)(f - tlo[1]) <= tsp[1]) ||
                              ((unsigned)(f - tlo[2]) <= tsp[2]);
-            mask |= (hit && xs[j] != skip) ? (1u << (4 * i + j)) : 0u;
+            mask |= (hit && finite_f(xs[j]) && xs[j] != skip) ? (1u << (4 * i + j)) : 0u;
           }
         }
       }
-      if (mask) {
-        unsigned pos = cl_atom_add(cnt_ra, (unsigned)__popc(mask));
-        do {
+      m[c] = mask;
+    }
+    unsigned mine = 0u;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) mine += (unsigned)__popc(m[c]);
+    if (mine) {                                        // one remote atomic per lane that holds members
+      unsigned pos = cl_atom_add(cnt_ra, mine);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        unsigned mask = m[c];
+        while (mask) {
           const int b = __ffs(mask) - 1;
           mask &= mask - 1u;
-          cl_stf(list_ra + 4u * min(pos, 191u), v[4 * lane + 128 * (g0 + (b >> 2)) + (b & 3)]);   // (<= 192 by the plan)
+          cl_stf(list_ra + 4u * min(pos, (unsigned)(3 * 64 - 1)), w.v[4 * lane + 128 * (c * CH + (b >> 2)) + (b & 3)]);   // (<= 192 by the plan)
           ++pos;
-        } while (mask);
+        }
       }
     }
+    gathered = true;
   }
 
   // owner only: the percentiles of the column
-  __device__ __forceinline__ void stage3(int Npad, unsigned* hist, float* cand, float* glist, float* gcol, int ncol_pad,
-                                         float pct[3], int& nvalid, int& status) {
-    const int lane = threadIdx.x & 31;
+  __device__ __forceinline__ void finish(float* cand, float* gcol, int ncol_pad, float pct[3], int& nvalid, int& status) {
     pct[0] = pct[1] = pct[2] = Math<float>::nan();
     nvalid = 0;
     status = ST_EMPTY;
     if (fallback) {                                   // the whole column, by the one-block code
-      warp_percentiles<true, 0>(gcol, ncol_pad, hist, cand, pct, nvalid, status);
+      warp_percentiles<true, 0>(gcol, ncol_pad, w.hist, cand, pct, nvalid, status);
       return;
     }
     nvalid = P.n;
     if (P.n == 0) return;                                                             // mcz.py:277-280
     if (!(sum_total > 0.0f)) { status = ST_NONPOS; return; }                          // mcz.py:282-285
     status = ST_OK;
-    SelWarp w;
-    w.v = nullptr; w.Npad = Npad; w.hist = hist; w.lane = lane;
-    w.ccount = reinterpret_cast<unsigned*>(cand); w.clist = cand + 32; w.glist = glist;
-    w.scale = scale; w.nLs = nLs; w.ngroups = 0; w.nmine = 0;
     const float pinf = __int_as_float(0x7f800000), ninf = __int_as_float(0xff800000);
     const float bmn[3] = {pinf, pinf, pinf}, bmx[3] = {ninf, ninf, ninf};
     const unsigned nmin[3] = {0u, 0u, 0u};
