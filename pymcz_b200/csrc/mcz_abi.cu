@@ -250,6 +250,7 @@ int mcz_ctx_run_host(mcz_ctx* c, const float* meas_h, const float* err_h, long l
   if ((size_t)G > c->cap_g) {
     cudaFree(c->meas); cudaFree(c->err); cudaFree(c->pct); cudaFree(c->nvalid); cudaFree(c->trips);
     cudaFree(c->ret); cudaFree(c->status);
+    c->meas = c->err = c->pct = nullptr; c->nvalid = c->trips = c->ret = nullptr; c->status = nullptr;
     c->cap_g = 0;
     const size_t g = (size_t)G;
     if ((rc = check_cuda(cudaMalloc(&c->meas, g * NLINES * 4), "malloc"))) return rc;
@@ -264,6 +265,7 @@ int mcz_ctx_run_host(mcz_ctx* c, const float* meas_h, const float* err_h, long l
   const size_t need = production_scratch_bytes(G, n_draw, tokens);
   if (need > c->cap_scratch) {
     cudaFree(c->scratch);
+    c->scratch = nullptr;
     c->cap_scratch = 0;
     if ((rc = check_cuda(cudaMalloc(&c->scratch, need), "malloc scratch"))) return rc;
     c->cap_scratch = need;
@@ -277,21 +279,23 @@ int mcz_ctx_run_host(mcz_ctx* c, const float* meas_h, const float* err_h, long l
   // chunk (641 B per galaxy) go back over PCIe on the copy stream while the next chunk computes.
   long long nchunk = G / 16384;
   nchunk = nchunk < 1 ? 1 : (nchunk > 8 ? 8 : nchunk);
+  // (an error below leaves copies into the caller's buffers in flight: drain both streams before returning)
+  auto fail = [&](int code) { cudaStreamSynchronize(st); cudaStreamSynchronize(cp); return code; };
   for (long long k = 0; k < nchunk; ++k) {
     const long long lo = G * k / nchunk, hi = G * (k + 1) / nchunk, n = hi - lo;
     rc = launch_production(c->meas + lo * NLINES, c->err + lo * NLINES, n, n_draw, tokens, dust, seed,
                            galaxy_offset + (unsigned long long)lo, sample_mode, deterministic,
                            c->pct + lo * NKEYS * 3, c->nvalid + lo * NKEYS, c->status + lo * NKEYS,
                            c->trips + lo * 2, c->ret + lo, nullptr, c->scratch, c->cap_scratch, st);
-    if (rc) return rc;
-    if ((rc = check_cuda(cudaEventRecord(c->chunk_done[k], st), "event record"))) return rc;
-    if ((rc = check_cuda(cudaStreamWaitEvent(cp, c->chunk_done[k], 0), "stream wait"))) return rc;
+    if (rc) return fail(rc);
+    if ((rc = check_cuda(cudaEventRecord(c->chunk_done[k], st), "event record"))) return fail(rc);
+    if ((rc = check_cuda(cudaStreamWaitEvent(cp, c->chunk_done[k], 0), "stream wait"))) return fail(rc);
     const size_t m = (size_t)n;
-    if ((rc = check_cuda(cudaMemcpyAsync(pct_h + lo * NKEYS * 3, c->pct + lo * NKEYS * 3, m * NKEYS * 3 * 4, cudaMemcpyDeviceToHost, cp), "D2H pct"))) return rc;
-    if ((rc = check_cuda(cudaMemcpyAsync(nvalid_h + lo * NKEYS, c->nvalid + lo * NKEYS, m * NKEYS * 4, cudaMemcpyDeviceToHost, cp), "D2H nvalid"))) return rc;
-    if ((rc = check_cuda(cudaMemcpyAsync(status_h + lo * NKEYS, c->status + lo * NKEYS, m * NKEYS, cudaMemcpyDeviceToHost, cp), "D2H status"))) return rc;
-    if (trips_h && (rc = check_cuda(cudaMemcpyAsync(trips_h + lo * 2, c->trips + lo * 2, m * 2 * 4, cudaMemcpyDeviceToHost, cp), "D2H trips"))) return rc;
-    if (ret_h && (rc = check_cuda(cudaMemcpyAsync(ret_h + lo, c->ret + lo, m * 4, cudaMemcpyDeviceToHost, cp), "D2H ret"))) return rc;
+    if ((rc = check_cuda(cudaMemcpyAsync(pct_h + lo * NKEYS * 3, c->pct + lo * NKEYS * 3, m * NKEYS * 3 * 4, cudaMemcpyDeviceToHost, cp), "D2H pct"))) return fail(rc);
+    if ((rc = check_cuda(cudaMemcpyAsync(nvalid_h + lo * NKEYS, c->nvalid + lo * NKEYS, m * NKEYS * 4, cudaMemcpyDeviceToHost, cp), "D2H nvalid"))) return fail(rc);
+    if ((rc = check_cuda(cudaMemcpyAsync(status_h + lo * NKEYS, c->status + lo * NKEYS, m * NKEYS, cudaMemcpyDeviceToHost, cp), "D2H status"))) return fail(rc);
+    if (trips_h && (rc = check_cuda(cudaMemcpyAsync(trips_h + lo * 2, c->trips + lo * 2, m * 2 * 4, cudaMemcpyDeviceToHost, cp), "D2H trips"))) return fail(rc);
+    if (ret_h && (rc = check_cuda(cudaMemcpyAsync(ret_h + lo, c->ret + lo, m * 4, cudaMemcpyDeviceToHost, cp), "D2H ret"))) return fail(rc);
   }
   if ((rc = check_cuda(cudaStreamSynchronize(st), "stream sync"))) return rc;
   return check_cuda(cudaStreamSynchronize(cp), "copy stream sync");

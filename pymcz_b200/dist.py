@@ -156,6 +156,7 @@ class _HostPath:
         self.cap = 0
         self.out = None
         self.gathered = {}              # G_total -> GatheredTables (symmetric-memory rendezvous is slow: keep)
+        self.copy_stream = None
 
     def tables(self, G):
         from ._scales import NKEYS
@@ -284,19 +285,43 @@ def production_table(meas, err, n_draw, tokens, dust, seed, correlated=False, de
         # (cached tables: no rank's kernel may write into a peer's table while that peer still
         # copies the previous call's rows out -- the same 4-byte all-reduce, ahead of the kernel)
         gt.wait()
-        if hi > lo:
-            _, _, _, trips, ret, _ = ops.forward_production(
-                m, e, n_draw, tokens, dust, seed, galaxy_offset=lo, correlated=correlated,
-                deterministic=deterministic, gather=gt)
-        else:
-            trips = torch.empty((0, 2), dtype=torch.int32, device=device)
-            ret = torch.empty((0,), dtype=torch.int32, device=device)
-        gt.wait()
-        small = gather_tables(dict(trips=trips, ret=ret), G)
-        t = _host_path(device).tables(max(G, 1))
-        for k, src in (("pct", gt.pct), ("nvalid", gt.nvalid), ("status", gt.status),
-                       ("trips", small["trips"]), ("ret", small["ret"])):
-            t[k][:G].copy_(src[:G], non_blocking=True)
+        hp = _host_path(device)
+        t = hp.tables(max(G, 1))
+        # The shard runs as up to 4 launches; after each one (and the barrier that says every rank's
+        # launch of that chunk has landed its rows everywhere) the rows of that chunk -- of EVERY
+        # rank's shard -- go down to the host on a second stream while the next chunk computes.
+        per = hi - lo
+        K = 4 if G >= 4 * 16384 * world else 1
+        if hp.copy_stream is None:
+            hp.copy_stream = torch.cuda.Stream(device)
+        trips_l = torch.empty((per, 2), dtype=torch.int32, device=device)
+        ret_l = torch.empty((per,), dtype=torch.int32, device=device)
+        ws_cache = {}
+        for k in range(K):
+            a, b = lo + per * k // K, lo + per * (k + 1) // K
+            if b > a:
+                ws = ws_cache.get(b - a)
+                if ws is None:
+                    ws = ws_cache[b - a] = ops.ProductionWorkspace(b - a, n_draw, tokens, device)
+                _, _, _, tr, rt, _ = ops.forward_production(
+                    m[a - lo:b - lo], e[a - lo:b - lo], n_draw, tokens, dust, seed, galaxy_offset=a,
+                    correlated=correlated, deterministic=deterministic, gather=gt, row0=a, workspace=ws)
+                trips_l[a - lo:b - lo].copy_(tr)
+                ret_l[a - lo:b - lo].copy_(rt)
+            gt.wait()
+            done_ev = torch.cuda.Event()
+            done_ev.record()
+            with torch.cuda.stream(hp.copy_stream):
+                hp.copy_stream.wait_event(done_ev)
+                for q in range(world):
+                    qlo, qhi = shard_bounds(G, world, q)
+                    ra, rb = qlo + (qhi - qlo) * k // K, qlo + (qhi - qlo) * (k + 1) // K
+                    if rb > ra:
+                        for name, src in (("pct", gt.pct), ("nvalid", gt.nvalid), ("status", gt.status)):
+                            t[name][ra:rb].copy_(src[ra:rb], non_blocking=True)
+        small = gather_tables(dict(trips=trips_l, ret=ret_l), G)
+        t["trips"][:G].copy_(small["trips"][:G], non_blocking=True)
+        t["ret"][:G].copy_(small["ret"][:G], non_blocking=True)
         torch.cuda.synchronize(device)
         out = {k: v[:G].numpy() for k, v in t.items()}
         out["Z"] = None

@@ -118,14 +118,15 @@ class ProductionWorkspace:
 
 def forward_production(meas, err, n_draw, tokens, dust=DUST_ON, seed=0xB200, galaxy_offset=0,
                        correlated=False, deterministic=False, return_samples=False, workspace=None,
-                       gather=None):
+                       gather=None, row0=None):
     """meas, err [G,11] f32 (cuda) -> (pct [G,37,3] f32, nvalid [G,37] i32, status [G,37] i8,
     trips [G,2] i32, ret [G] i32, Z [G,37,n_draw] f32 or None).  Enqueues on the current stream.
 
     gather: a dist.GatheredTables.  The kernel then writes this rank's result rows straight into
     every rank's full tables (rows gather.row0 ...) over NVLink peer mappings instead of the
     workspace's local pct/nvalid/status, which are returned untouched; call gather.wait() before
-    reading the tables."""
+    reading the tables.  row0: first row of this launch in the gathered tables (default: the rank's
+    first row; a shard run as several launches passes each chunk's own)."""
     L = _lib.lib()
     _need_cuda(meas, "meas")
     _need_cuda(err, "err")
@@ -147,7 +148,8 @@ def forward_production(meas, err, n_draw, tokens, dust=DUST_ON, seed=0xB200, gal
             rc = L.mcz_forward_production_gather(
                 meas.data_ptr(), err.data_ptr(), G, int(n_draw), int(tokens), int(dust), int(seed),
                 int(galaxy_offset), 1 if correlated else 0, 1 if deterministic else 0,
-                gather.world, int(gather.row0), gather.pct_ptrs, gather.nvalid_ptrs, gather.status_ptrs,
+                gather.world, int(gather.row0 if row0 is None else row0), gather.pct_ptrs, gather.nvalid_ptrs,
+                gather.status_ptrs,
                 ws.trips.data_ptr(), ws.ret.data_ptr(), ws.scratch.data_ptr(), ws.scratch_bytes + 0,
                 _stream_ptr(dev))
             _lib.check(rc, "mcz_forward_production_gather")
