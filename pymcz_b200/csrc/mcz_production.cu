@@ -65,6 +65,8 @@ struct ProdParams {
   float* Z;
   int nstore;
   int scap;                                // global variant: samples whose KK04 loop state lives in shared memory
+  int bsm;                                 // global variant: the inputs and the state of the KK04 loops fit in shared memory
+  int cper, cng;                           // cluster kernel: samples per block, 128-sample groups streamed per block
   signed char slot_of_key[NKEYS];
   signed char key_of_slot[NKEYS];
   int col_off[NKEYS];                      // slot * Npad (float index of the column), -1 if not stored
@@ -79,6 +81,10 @@ struct ProdParams {
 };
 
 struct Ctrl {
+  // cluster kernel: exchange of the per-block KK04 sums.  Two barriers / slot sets, used alternately;
+  // xslot[p][r] = what block r sent: four fixed-point sums, "changed" flag, NaN flag (8 words, 32 bytes)
+  unsigned long long xbar[2];
+  int xslot[2][8][8];
   long long g;
   uint32_t flags;
   int any_valid_kd;
@@ -86,12 +92,10 @@ struct Ctrl {
   float2 redf[2 * PW];
   int acc[3][4];           // fixed-point block sums: two KK04 convergence measures x two trips per barrier
   unsigned chg[3];         // some sample's R23 loop state changed over the batch (rotates with acc)
-  // cluster kernel: the cluster-wide totals / flags, pushed by every block into every block's copy
-  int cacc[3][4];
-  unsigned cchg[3];
-  unsigned nanw[3];        // block: some logq of the batch is NaN;  cnan: cluster
-  unsigned cnan[3];
+  unsigned nanw[3];        // cluster kernel: some logq of the batch is NaN in this block
   unsigned nan4;           // which loop / trip saw a NaN (rare path)
+  unsigned long long* poison_word;
+  int cl_soff, cl_n;       // cluster kernel: this block's first sample and sample count
 };
 static_assert(sizeof(Ctrl) <= CTRL_BYTES, "control block too large");
 
@@ -170,6 +174,65 @@ __device__ __forceinline__ unsigned cl_atom_add(unsigned addr, unsigned v) {
   asm volatile("atom.shared::cluster.add.u32 %0, [%1], %2;" : "=r"(o) : "r"(addr), "r"(v) : "memory");
   return o;
 }
+// mbarriers (shared memory, 8 bytes) with transaction counts: the receiving end of the asynchronous
+// remote stores / reductions below.  A barrier is initialised with ONE expected arrival -- the
+// receiver's own arrive.expect_tx(bytes) -- and its phase completes when that arrival has happened
+// and `bytes` of remote data have landed (data that lands before the expect_tx just drives the
+// transaction count negative for a while).
+__device__ __forceinline__ void mbar_init(unsigned a, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(a), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx_arrive(unsigned a, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned a, unsigned parity) {
+  unsigned ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+  return ok != 0u;
+}
+// Wait for phase `parity` of a local barrier.  A protocol error (the blocks of a cluster disagreeing
+// on what comes next) would otherwise hang the GPU: after ~1 s the wait gives up, raises the poison
+// flag in the launch statistics (checked by the host) and every later wait returns at once.
+__device__ __noinline__ void mbar_wait_slow(unsigned a, unsigned parity, unsigned long long* poison_word, unsigned where) {
+  const long long t0 = clock64();
+  for (;;) {
+    if ((*reinterpret_cast<volatile unsigned long long*>(poison_word) >> 63) != 0ull) return;
+    for (int it = 0; it < 16; ++it)
+      if (mbar_try_wait(a, parity)) return;
+    if (clock64() - t0 > 1000000000ll) {
+      const unsigned long long old = atomicOr(poison_word, 1ull << 63);
+      if (!(old >> 63)) atomicOr(poison_word, (unsigned long long)where << 56);      // who gave up first
+      return;
+    }
+  }
+}
+__device__ __forceinline__ void mbar_wait(unsigned a, unsigned parity, unsigned long long* poison_word, unsigned where) {
+#pragma unroll 1
+  for (int it = 0; it < 64; ++it)
+    if (mbar_try_wait(a, parity)) return;
+  mbar_wait_slow(a, parity, poison_word, where);
+}
+// asynchronous remote stores / reductions (shared::cluster addresses) that signal `mbar` (a
+// shared::cluster address in the SAME block as the data) with the number of bytes written
+__device__ __forceinline__ void st_async_v4(unsigned addr, unsigned a, unsigned b, unsigned c, unsigned d, unsigned mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+               :: "r"(addr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void st_async_u32(unsigned addr, unsigned a, unsigned mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" :: "r"(addr), "r"(a), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void red_async_add(unsigned addr, unsigned a, unsigned mbar) {
+  asm volatile("red.async.relaxed.cluster.mbarrier::complete_tx::bytes.shared::cluster.add.u32 [%0], %1, [%2];"
+               :: "r"(addr), "r"(a), "r"(mbar) : "memory");
+}
+// byte offsets inside a warp's 512-byte candidate area: counters, the three barriers of the selection
+// protocol (ClusterCol), the command from the owner, the 64-entry list of select_in_interval, and
+// what each block reports with its table (count of the repeated value, sum, min, max)
+struct ClMail {
+  static constexpr unsigned CCOUNT = 0, GCOUNT = 4, MB_MERGE = 8, MB_CMD = 16, MB_GATHER = 24, CMD = 32, PAR = 96, CLIST = 128, STAT = 384;
+};
 // barrier over every thread of every block of the cluster; orders shared AND global memory accesses
 __device__ __forceinline__ void cl_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -203,35 +266,47 @@ static constexpr int FX_WARP_CLAMP = 64 << MCZ_FX_BITS;
 typedef int fx_t;
 __device__ __forceinline__ int fx_clamp(int q) { return max(-FX_WARP_CLAMP, min(FX_WARP_CLAMP, q)); }
 static constexpr int FX_BLOCK_CLAMP = 128 << MCZ_FX_BITS;     // cluster kernel: per-block totals, <= 8 of them in 32 bits
-// Cluster kernel, after the block-local sums: every block adds its (clamped) totals and flags to the
-// cluster accumulators of EVERY block of the cluster, then one cluster barrier; each block reads its
-// own copy.  nsum = how many of the four sums are in use.
-__device__ __forceinline__ void cluster_exchange(Ctrl* ctrl, int ph, int nx, unsigned csize) {
+// Cluster kernel, after the block-local sums: thread r of every block sends the block's (clamped)
+// totals and flags to block r of the cluster with two asynchronous 16-byte stores that signal the
+// receiver's barrier; every thread then waits on its own block's barrier and adds up what the
+// blocks sent.  No cluster barrier: ~one DSMEM flight per exchange, and the blocks only wait for data.
+// `xq` counts the exchanges (the same in every thread of the cluster): barrier q & 1, phase (q >> 1) & 1.
+struct ClusterX {
+  unsigned xq;
+};
+__device__ __forceinline__ void cluster_exchange(Ctrl* ctrl, int ph, ClusterX& cx, int tot[4], bool& anychg, bool& anynan) {
   const int t = threadIdx.x;
+  const unsigned q = cx.xq++, pb = q & 1u, par = (q >> 1) & 1u;
+  const unsigned bar = (unsigned)__cvta_generic_to_shared(&ctrl->xbar[pb]);
+  const unsigned csize = cl_size();
   __syncthreads();                       // the block's own totals are complete
-  if (t < 4) {
-    const int v = max(-FX_BLOCK_CLAMP, min(FX_BLOCK_CLAMP, ctrl->acc[ph][t]));
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(&ctrl->cacc[ph][t]);
-    for (unsigned r = 0; r < csize; ++r) cl_red_add(cl_map(sa, r), v);
-    ctrl->cacc[nx][t] = 0;
+  if (t < (int)csize) {
+    int v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = max(-FX_BLOCK_CLAMP, min(FX_BLOCK_CLAMP, ctrl->acc[ph][k]));
+    const unsigned dst = cl_map((unsigned)__cvta_generic_to_shared(&ctrl->xslot[pb][cl_rank()][0]), (unsigned)t);
+    const unsigned rbar = cl_map(bar, (unsigned)t);
+    st_async_v4(dst, (unsigned)v[0], (unsigned)v[1], (unsigned)v[2], (unsigned)v[3], rbar);
+    st_async_v4(dst + 16u, ctrl->chg[ph], ctrl->nanw[ph], 0u, 0u, rbar);
   } else if (t == 32) {
-    if (ctrl->chg[ph]) {
-      const unsigned sa = (unsigned)__cvta_generic_to_shared(&ctrl->cchg[ph]);
-      for (unsigned r = 0; r < csize; ++r) cl_red_or(cl_map(sa, r), 1u);
-    }
-    ctrl->cchg[nx] = 0u;
-  } else if (t == 64) {
-    if (ctrl->nanw[ph]) {
-      const unsigned sa = (unsigned)__cvta_generic_to_shared(&ctrl->cnan[ph]);
-      for (unsigned r = 0; r < csize; ++r) cl_red_or(cl_map(sa, r), 1u);
-    }
-    ctrl->cnan[nx] = 0u;
+    mbar_expect_tx_arrive(bar, csize * 32u);
   }
-  cl_sync();
+  mbar_wait(bar, par, ctrl->poison_word, 1u);
+  int s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+  unsigned c = 0u, n = 0u;
+  for (unsigned r = 0; r < csize; ++r) {
+    const int4 a = *reinterpret_cast<const int4*>(&ctrl->xslot[pb][r][0]);
+    const int2 b = *reinterpret_cast<const int2*>(&ctrl->xslot[pb][r][4]);
+    s0 += a.x; s1 += a.y; s2 += a.z; s3 += a.w;
+    c |= (unsigned)b.x; n |= (unsigned)b.y;
+  }
+  tot[0] = s0; tot[1] = s1; tot[2] = s2; tot[3] = s3;
+  anychg = c != 0u;
+  anynan = n != 0u;
 }
 template <bool CL>
 __device__ __forceinline__ void block_sum2_fx(float s1, float s2, bool nan, Ctrl* ctrl, int& ph,
-                                              fx_t& t1, fx_t& t2, bool& anynan, unsigned csize) {
+                                              fx_t& t1, fx_t& t2, bool& anynan, ClusterX& cx) {
   const int lane = threadIdx.x & 31;
   int q1 = __reduce_add_sync(0xffffffffu, __float2int_rn(s1 * FX_SCALE));
   int q2 = __reduce_add_sync(0xffffffffu, __float2int_rn(s2 * FX_SCALE));
@@ -245,10 +320,11 @@ __device__ __forceinline__ void block_sum2_fx(float s1, float s2, bool nan, Ctrl
   if (threadIdx.x < 4) ctrl->acc[nx][threadIdx.x] = 0;
   if (threadIdx.x == 4) { ctrl->chg[nx] = 0u; ctrl->nanw[nx] = 0u; }
   if (CL) {
-    cluster_exchange(ctrl, ph, nx, csize);
-    anynan = ctrl->cnan[ph] != 0u;
-    t1 = ctrl->cacc[ph][0];
-    t2 = ctrl->cacc[ph][1];
+    int tot[4];
+    bool chg;
+    cluster_exchange(ctrl, ph, cx, tot, chg, anynan);
+    t1 = tot[0];
+    t2 = tot[1];
   } else {
     anynan = __syncthreads_or(nan);
     t1 = ctrl->acc[ph][0];
@@ -262,7 +338,7 @@ __device__ __forceinline__ void block_sum2_fx(float s1, float s2, bool nan, Ctrl
 // is its OR over the block (cluster).
 template <bool CL>
 __device__ __forceinline__ void block_sum4_fx(const float s[4], unsigned nanbits, bool changed, Ctrl* ctrl, int& ph,
-                                              fx_t t[4], bool& anynan, bool& anychanged, unsigned csize) {
+                                              fx_t t[4], bool& anynan, bool& anychanged, ClusterX& cx) {
   const int lane = threadIdx.x & 31;
   int q[4];
 #pragma unroll
@@ -279,11 +355,7 @@ __device__ __forceinline__ void block_sum4_fx(const float s[4], unsigned nanbits
   if (threadIdx.x < 4) ctrl->acc[nx][threadIdx.x] = 0;
   if (threadIdx.x == 4) { ctrl->chg[nx] = 0u; ctrl->nanw[nx] = 0u; }
   if (CL) {
-    cluster_exchange(ctrl, ph, nx, csize);
-    anynan = ctrl->cnan[ph] != 0u;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) t[k] = ctrl->cacc[ph][k];
-    anychanged = ctrl->cchg[ph] != 0u;
+    cluster_exchange(ctrl, ph, cx, t, anychanged, anynan);
   } else {
     anynan = __syncthreads_or(nanbits != 0u);
 #pragma unroll
@@ -321,6 +393,9 @@ template <bool SHARED> __device__ __forceinline__ void store_f32(float* gptr, ui
   else *gptr = v;
 }
 
+__device__ unsigned long long g_phase_cycles[8];
+__device__ unsigned long long g_col_cycles[2 * NKEYS];   // per key: cycles, max-cycles accumulators (cluster kernel: per stage)
+
 }  // namespace mcz
 #include "mcz_select.cuh"
 namespace mcz {
@@ -328,8 +403,6 @@ namespace mcz {
 // optional phase timing (build with -DMCZ_PHASE_TIMING): cycles summed over blocks, read back with
 // mcz_debug_phase_cycles: [0] galaxies, [1] phase A, [2] phases B+C, [3] phase D own work (mean
 // over the 18 warps), [4] phase D wall (start of D to the block barrier), [5] other
-__device__ unsigned long long g_phase_cycles[8];
-__device__ unsigned long long g_col_cycles[2 * NKEYS];   // per key: cycles, max-cycles accumulators
 #ifdef MCZ_PHASE_TIMING
 #define MCZ_T(var) const long long var = clock64()
 #define MCZ_TADD(idx, val) do { if (tid == 0) atomicAdd(&g_phase_cycles[idx], (unsigned long long)(val)); } while (0)
@@ -353,11 +426,24 @@ production_kernel(const __grid_constant__ ProdParams p) {
   Ctrl* ctrl = reinterpret_cast<Ctrl*>(smem);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int Npad = p.Npad;                // samples a block holds per column (a multiple of 128)
-  const unsigned crank = CL ? cl_rank() : 0u, csize = CL ? cl_size() : 1u;
-  const int soff = CL ? (int)crank * SLOTS * PT : 0;        // global index of this block's first sample
-  // N: samples of the galaxy that THIS block holds (all of them without clusters); the loop
+  // cluster kernel: the samples are split evenly, block r holds [r cper, (r + 1) cper) of every column
+  // (cper <= SLOTS * PT) and streams cng = ceil(cper / 128) groups of 128 in the selection passes.
+  // The block's rank, first sample (SOFF) and sample count (NLOC) are re-read where they are needed
+  // (special registers / control block) instead of living in registers across the KK04 loops.
+  // NLOC: samples of the galaxy that THIS block holds (all of them without clusters); the loop
   // tolerances and the percentile ranks use the galaxy's p.N
-  const int N = CL ? max(0, min(p.N - soff, SLOTS * PT)) : p.N;
+#define CRANK (CL ? cl_rank() : 0u)
+#define CSIZE (CL ? cl_size() : 1u)
+#define SOFF (CL ? ctrl->cl_soff : 0)
+#define NLOC (CL ? ctrl->cl_n : p.N)
+  if (CL && threadIdx.x == 0) {
+    const int so = (int)cl_rank() * p.cper;
+    ctrl->cl_soff = so;
+    ctrl->cl_n = max(0, min(p.N - so, p.cper));
+  }
+  const int Nfill = CL ? p.cng * 128 : Npad;                // [NLOC, Nfill) of every column is NaN
+  ClusterX cx;
+  cx.xq = 0u;
 
   constexpr bool PACK16 = !WIDE;          // 16-bit packed histogram counters: columns of < 65536 samples
   constexpr size_t HIST_BYTES = FineHist<PACK16>::BYTES;
@@ -374,6 +460,14 @@ production_kernel(const __grid_constant__ ProdParams p) {
     giter = st3 + Npad;
     work = smem + CTRL_BYTES;
     sstate = reinterpret_cast<float*>(work + (size_t)PW * (HIST_BYTES + CAND_FLOATS * sizeof(float)));
+    if (p.bsm) {
+      // the three carry values of every sample live in shared memory (over the selection work area,
+      // which is dead between two phases D); the flag word stays in the global scratch
+      const int Nq = (p.N + 3) & ~3;
+      st0 = reinterpret_cast<float*>(smem + CTRL_BYTES);
+      st1 = st0 + Nq;
+      st2 = st1 + Nq;
+    }
   } else {
     // Shared-memory variant (Npad == SLOTS*PT always).  The histograms are live from phase B on
     // (they are filled while the KK04 loops wait on their barriers), so the per-sample scratch
@@ -404,7 +498,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
   // The next galaxy (queue ticket, its 22 input numbers, cleared flags) is fetched by the last warp
   // while the block is busy with phase D, so the loop top costs one barrier and no global latency.
   auto fetch_next = [&]() {
-    if (CL && crank != 0u) return;        // the cluster's first block takes the ticket and hands it to all
+    if (CL && CRANK != 0u) return;        // the cluster's first block takes the ticket and hands it to all
     long long gn = 0;
     if (lane == 0) gn = (long long)atomicAdd(p.counter, 1ull);
     gn = __shfl_sync(0xffffffffu, gn, 0);
@@ -414,6 +508,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
       else if (lane < 2 * NLINES) lv = p.err[gn * NLINES + (lane - NLINES)];
     }
     if (CL) {
+      const unsigned csize = CSIZE;
       for (unsigned r = 0; r < csize; ++r) {
         if (lane < 2 * NLINES) cl_stf(cl_map(&ctrl->line[lane], r), lv);
         if (lane == 0) {
@@ -422,9 +517,9 @@ production_kernel(const __grid_constant__ ProdParams p) {
           cl_st(ga + 4u, (unsigned)((unsigned long long)gn >> 32));
           cl_st(cl_map(&ctrl->flags, r), 0u);
           cl_st(cl_map(&ctrl->nan4, r), 0u);
-          for (int k = 0; k < 4; ++k) { cl_st(cl_map(&ctrl->acc[0][k], r), 0u); cl_st(cl_map(&ctrl->cacc[0][k], r), 0u); }
-          cl_st(cl_map(&ctrl->chg[0], r), 0u); cl_st(cl_map(&ctrl->cchg[0], r), 0u);
-          cl_st(cl_map(&ctrl->nanw[0], r), 0u); cl_st(cl_map(&ctrl->cnan[0], r), 0u);
+          for (int k = 0; k < 4; ++k) cl_st(cl_map(&ctrl->acc[0][k], r), 0u);
+          cl_st(cl_map(&ctrl->chg[0], r), 0u);
+          cl_st(cl_map(&ctrl->nanw[0], r), 0u);
         }
       }
     } else {
@@ -436,6 +531,24 @@ production_kernel(const __grid_constant__ ProdParams p) {
       }
     }
   };
+  if constexpr (CL) {
+    // barriers of the KK04 exchange (control block) and of the selection protocol (every warp's
+    // candidate area): one expected arrival each, the receiver's own arrive.expect_tx
+    if (tid == 0) {
+      mbar_init((unsigned)__cvta_generic_to_shared(&ctrl->xbar[0]), 1u);
+      mbar_init((unsigned)__cvta_generic_to_shared(&ctrl->xbar[1]), 1u);
+      ctrl->poison_word = p.stats + 7;
+    }
+    if (lane == 0) {
+      const unsigned ca = (unsigned)__cvta_generic_to_shared(cand);
+      mbar_init(ca + ClMail::MB_MERGE, 1u);
+      mbar_init(ca + ClMail::MB_CMD, 1u);
+      mbar_init(ca + ClMail::MB_GATHER, 1u);
+      reinterpret_cast<unsigned*>(cand)[ClMail::PAR / 4] = 0u;
+    }
+    mbar_fence_init();
+    cl_sync();                  // every block of the cluster runs and has its barriers before any remote access
+  }
   if (warp == PW - 1) fetch_next();
 
   for (;;) {
@@ -484,6 +597,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
         const uint32_t tk = MODE == 1 ? (uint32_t)T_ALL : (MODE == 2 ? (uint32_t)T_KD02 : p.tok);
         const int dm = MODE ? 0 : de;
 #pragma unroll A_UNROLL
+        const int N = NLOC, soff = SOFF;
         for (int i = 0; i < nsl; ++i) {
           const int s = i * PT + tid;
           if (s < N) {
@@ -516,7 +630,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
             store_f32<!GLOBAL>(st1 + s, st1_sa + 4u * (unsigned)s, c.n2ha);
             store_f32<!GLOBAL>(st2 + s, st2_sa + 4u * (unsigned)s, c.x);
             store_f32<!GLOBAL>(st3 + s, st3_sa + 4u * (unsigned)s, __uint_as_float(c.aux));
-          } else if (s < Npad) {
+          } else if (s < Nfill) {
             for (int sl = 0; sl < p.nstore; ++sl) vals[(long long)sl * Npad + s] = Math<float>::nan();
           }
         }
@@ -527,7 +641,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
       seen = __reduce_or_sync(0xffffffffu, seen);
       if (lane == 0 && seen) {
         if (CL) {
-          for (unsigned r = 0; r < csize; ++r) cl_red_or(cl_map(&ctrl->flags, r), seen);
+          for (unsigned r = 0, csize = CSIZE; r < csize; ++r) cl_red_or(cl_map(&ctrl->flags, r), seen);
         } else {
           atomicOr(&ctrl->flags, seen);
         }
@@ -578,7 +692,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
           num0[i] = 0.0f; num1[i] = 0.0f; den0[i] = 1.0f; den1[i] = 0.0f; cA[i] = 0.0f; cB[i] = 0.0f;
           Z1[i] = 0.0f; lq1[i] = 0.0f; Z2[i] = 0.0f; lq2[i] = 0.0f; aux[i] = 2u;
           tU0[i] = 0.0f; tU1[i] = 0.0f; tL0[i] = 0.0f; tL1[i] = 0.0f;
-          if (s < N) {
+          if (s < NLOC) {
             Carry<float> c;
             c.y = st0[s]; c.n2ha = st1[s]; c.x = st2[s];
             c.aux = __float_as_uint(st3[s]);
@@ -603,7 +717,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
         // start of the N2Ha loop: 8.6 if KD02_N2O2 is None or all-NaN (metscales.py:1097-1103)
         if (!anykd) {
 #pragma unroll
-          for (int i = 0; i < SLOTS; ++i) if (i * PT + tid < N) Z1[i] = 8.6f;
+          for (int i = 0; i < SLOTS; ++i) if (i * PT + tid < NLOC) Z1[i] = 8.6f;
         }
         if (has_kn && !o3o2) {                                          // metscales.py:1122-1126
 #pragma unroll
@@ -664,7 +778,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
           }
           fx_t t4[4];
           bool anynan, anychanged;
-          block_sum4_fx<CL>(sm4, bad ? 1u : 0u, changed, ctrl, ph, t4, anynan, anychanged, csize);
+          block_sum4_fx<CL>(sm4, bad ? 1u : 0u, changed, ctrl, ph, t4, anynan, anychanged, cx);
           unsigned nb = 0u;
           if (anynan) {
             // rare: which loop / trip saw the NaN first (a NaN mean stops that loop, as in numpy).  A NaN
@@ -678,7 +792,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
             if (CL) {
               nanb = __reduce_or_sync(0xffffffffu, nanb);
               if (lane == 0 && nanb)
-                for (unsigned r = 0; r < csize; ++r) cl_red_or(cl_map(&ctrl->nan4, r), nanb);
+                for (unsigned r = 0, csize = CSIZE; r < csize; ++r) cl_red_or(cl_map(&ctrl->nan4, r), nanb);
               cl_sync();
               nb = ctrl->nan4;
               cl_sync();                    // everyone has read it: clear for the next use
@@ -751,7 +865,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
             }
             fx_t tm, tdummy;
             bool nandummy;
-            block_sum2_fx<CL>(sm, 0.0f, false, ctrl, ph, tm, tdummy, nandummy, csize);
+            block_sum2_fx<CL>(sm, 0.0f, false, ctrl, ph, tm, tdummy, nandummy, cx);
             if (tm > 4 * itol1) { executed1 = ii1; ii1 = 100; act1 = false; }
           }
         }
@@ -762,7 +876,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
 #pragma unroll
         for (int i = 0; i < SLOTS; ++i) {
           const int s = i * PT + tid;
-          if (s < N) {
+          if (s < NLOC) {
             SlotPut<!GLOBAL> put{vals + s, p.col_off, vals_sa + 4u * (unsigned)s};
             const float kd = has_kd ? vals[sl_kd * Npad + s] : Math<float>::nan();
             const float m91 = vals[sl_m91 * Npad + s];
@@ -775,6 +889,173 @@ production_kernel(const __grid_constant__ ProdParams p) {
             st0[s] = Math<float>::nan(); st1[s] = Math<float>::nan(); st2[s] = Math<float>::nan();
           }
         }
+      } else if (p.bsm) {
+        // Loop inputs and state in shared memory, 20 bytes + 1 bit per sample: logO3O2, logN2Ha, logR23
+        // (written there by phase A), the last logq of the two loops, and "Z_init_guess <= 8.4".  The ten
+        // constants of the two maps are recomputed from the three inputs in every two-trip batch
+        // (~35 FMAs) and the running Z is recomputed from logq (Z = A - logq B, or the R23 branch
+        // polynomial: exactly the expression that produced it), so a batch reads and writes shared
+        // memory only -- except logq after the first trip of the pair, which goes to the global
+        // scratch in case the loop turns out to have ended there (write-only until then).
+        // Until a loop has run its first batch, its logq array holds the INITIAL Z instead
+        // (metscales.py:1097-1106, 1156-1163) and the previous logq is the constant 0 / 100.
+        const int N = p.N;
+        const int Nq = (N + 3) & ~3;
+        float* sQ1 = st2 + Nq;
+        float* sQ2 = sQ1 + Nq;
+        unsigned* sLow = reinterpret_cast<unsigned*>(sQ2 + Nq);
+        float* Fa1 = giter + 4ll * Npad;          // fields 14, 15 of the scratch: logq after the first trip
+        float* Fa2 = giter + 5ll * Npad;
+        auto consts = [&](int s, IterState<float>& st) {
+          Carry<float> c;
+          c.y = st0[s]; c.n2ha = st1[s]; c.x = st2[s];
+          c.aux = __float_as_uint(st3[s]);
+          make_iter<float>(c, 0.0f, st);
+        };
+        bool any = false;
+        for (int s0 = warp * 32; s0 < N; s0 += PT) {
+          const int s = s0 + lane;
+          const bool in = s < N;
+          const uint32_t aux = in ? __float_as_uint(st3[s]) : 2u;
+          const float kd = (in && has_kd) ? vals[(long long)sl_kd * Npad + s] : Math<float>::nan();
+          any = any || (in && !Math<float>::isnan(kd));
+          const unsigned low = __ballot_sync(0xffffffffu, in && (aux & AUX_ZI_MASK) <= 1u);
+          if (lane == 0) sLow[s0 >> 5] = low;
+          if (in) {
+            const uint32_t zi = aux & AUX_ZI_MASK;
+            sQ1[s] = kd;
+            sQ2[s] = zi == 0u ? 8.2f : (zi == 1u ? 8.4f : 8.7f);                          // metscales.py:1156
+          }
+        }
+        const bool allnan = !__syncthreads_or(any);
+        if (allnan || (has_kn && !o3o2)) {
+          for (int s = tid; s < N; s += PT) {
+            float z1 = allnan ? 8.6f : sQ1[s];                                            // metscales.py:1097-1103
+            if (has_kn && !o3o2) {                                                        // metscales.py:1122-1126
+              IterState<float> st;
+              iter_n2ha<float>(st1[s], st);
+              z1 = st.A - 7.37177f * st.B;
+            }
+            sQ1[s] = z1;
+          }
+        }
+        const bool ran1 = act1, ran2 = act2;
+        bool first = true;
+        while (act1 || act2) {
+          float sm4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+          unsigned nanb = 0u;
+#pragma unroll 2
+          for (int s = tid; s < N; s += PT) {
+            IterState<float> k;                       // only the constants of the loops still running
+            iter_logq<float>(st0[s], k);
+            const float num0 = k.num0, num1 = k.num1, den0 = k.den0, den1 = k.den1;
+            if (act1) {
+              iter_n2ha<float>(st1[s], k);
+              const float cA = k.A, cB = k.B;
+              const float q = sQ1[s];
+              const float Z1 = first ? q : cA - q * cB;
+              const float lq1 = first ? 0.0f : q;                                         // logq_save (:1106)
+              const float lq = (num0 + Z1 * num1) * fast_rcp(den0 + Z1 * den1);          // metscales.py:1112-1118
+              const float z = cA - lq * cB;
+              float d = fabsf(lq - lq1);
+              nanb |= (d != d) ? 1u : 0u;
+              sm4[0] += d;
+              const float lqb = (num0 + z * num1) * fast_rcp(den0 + z * den1);
+              d = fabsf(lqb - lq);
+              nanb |= (d != d) ? 2u : 0u;
+              sm4[1] += d;
+              sQ1[s] = lqb;
+              Fa1[s] = lq;
+            }
+            if (act2) {
+              iter_r23<float>(st2[s], k);
+              const float u0 = k.U0, u1 = k.U1, l0 = k.L0, l1 = k.L1;
+              const bool lowz = (sLow[s >> 5] >> (s & 31)) & 1u;
+              const float q = sQ2[s];
+              bool lower = lowz && (q >= 6.7f) && (q < 8.3f);
+              const float Z2 = first ? q : (lower ? l0 : u0) - q * (lower ? l1 : u1);
+              const float lq2 = first ? 100.0f : q;                                       // logqold (:1163)
+              const float lq = (num0 + Z2 * num1) * fast_rcp(den0 + Z2 * den1);          // metscales.py:1167-1178
+              lower = lowz && (lq >= 6.7f) && (lq < 8.3f);
+              const float z = (lower ? l0 : u0) - lq * (lower ? l1 : u1);
+              float d = lq2 - lq;
+              nanb |= (d != d) ? 4u : 0u;
+              sm4[2] += d;
+              const float lqb = (num0 + z * num1) * fast_rcp(den0 + z * den1);
+              d = lq - lqb;
+              nanb |= (d != d) ? 8u : 0u;
+              sm4[3] += d;
+              sQ2[s] = lqb;
+              Fa2[s] = lq;
+            }
+          }
+          first = false;
+          block_sum2f(sm4[0], sm4[1], ctrl->redf, phase);
+          block_sum2f(sm4[2], sm4[3], ctrl->redf, phase);
+          unsigned nb = 0u;
+          if (__syncthreads_or(nanb != 0u)) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) nb |= __syncthreads_or((nanb >> k) & 1u) ? (1u << k) : 0u;
+          }
+          if (act1) {                                                     // metscales.py:1111,1117
+            ++ii1;
+            if ((nb & 1u) || !(sm4[0] > tol1) || ii1 >= 100) {
+              act1 = false;       // ended after the first trip of the pair: put that logq back
+              for (int s = tid; s < N; s += PT) sQ1[s] = Fa1[s];
+            } else {
+              ++ii1;
+              act1 = !(nb & 2u) && (sm4[1] > tol1) && ii1 < 100;
+            }
+          }
+          if (act2) {                                                     // metscales.py:1166,1177
+            ++ii2;
+            if ((nb & 4u) || !(fabsf(sm4[2]) > tol2) || ii2 >= 100) {
+              act2 = false;
+              for (int s = tid; s < N; s += PT) sQ2[s] = Fa2[s];
+            } else {
+              ++ii2;
+              act2 = !(nb & 8u) && (fabsf(sm4[3]) > tol2) && ii2 < 100;
+            }
+          }
+          if (act1 && ii1 == DIVERGENCE_CHECK_TRIP) {
+            // proven-divergence exit, as in the register variant above (same bound, same threshold)
+            float sm = 0.0f, unused = 0.0f;
+            for (int s = tid; s < N; s += PT) {
+              IterState<float> k;
+              iter_logq<float>(st0[s], k);
+              iter_n2ha<float>(st1[s], k);
+              const float n0 = k.num0, n1 = k.num1, d0 = k.den0, d1 = k.den1, A = k.A, B = k.B;
+              const float al = n0 + A * n1, be = B * n1, ga = d0 + A * d1, de = B * d1;
+              const float bg = be + ga, disc = bg * bg - 4.0f * al * de;
+              float m = 0.0f;
+              if (disc < 0.0f) {
+                const float r = __fsqrt_rn(al * de - be * ga), ide = fast_rcp(de);
+                const float u1 = (ga + r) * ide, u2 = (ga - r) * ide;
+                const float q1 = (de * u1 - bg) * u1 + al, q2 = (de * u2 - bg) * u2 + al;
+                m = fminf(fabsf(q1), fabsf(q2)) * fast_rcp(r);
+              }
+              sm += (m == m) ? fminf(m, 8.0f) : 0.0f;
+            }
+            block_sum2f(sm, unused, ctrl->redf, phase);
+            if (sm > 4.0f * tol1) { executed1 = ii1; ii1 = 100; act1 = false; }
+          }
+        }
+        if (executed1 < 0) executed1 = ii1;
+        for (int s = tid; s < N; s += PT) {
+          IterState<float> st;
+          consts(s, st);
+          const float q1 = sQ1[s], q2 = sQ2[s];
+          st.Z1 = ran1 ? st.A - q1 * st.B : q1;
+          if (ran2) {
+            const bool lower = ((st.aux & AUX_ZI_MASK) <= 1u) && (q2 >= 6.7f) && (q2 < 8.3f);
+            st.Z2 = (lower ? st.L0 : st.U0) - q2 * (lower ? st.L1 : st.U1);
+            st.lq2 = q2;
+          }
+          SlotPut<!GLOBAL> put{vals + s, p.col_off, vals_sa + 4u * (unsigned)s};
+          const float kd = has_kd ? vals[(long long)sl_kd * Npad + s] : Math<float>::nan();
+          const float m91 = vals[(long long)sl_m91 * Npad + s];
+          phase_c<float>(st, pm, ii1 >= 100, ii2 >= 100, kd, m91, put);
+        }
       } else {
         // Memory-backed loop state.  The ten per-sample constants of the two maps are recomputed
         // from the four carry values (st0..st3: logO3O2, logN2Ha, logR23, flags) in every batch:
@@ -782,6 +1063,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
         // bandwidth.  The four values that change every trip (Z1, Z2, logq1, logq2 = fields 10..13)
         // live in shared memory for the first p.scap samples (a multiple of the block size, so
         // each pass of the sample loop is on one side), in the global scratch beyond.
+        const int N = p.N;
         float* F = giter - 10ll * Npad;          // only fields 10..15 exist (the constants are recomputed)
         const int scap = p.scap;
 #define LST(k, s) (*((s) < scap ? sstate + ((k) - 10) * scap + (s) : F + (long long)(k) * Npad + (s)))
@@ -937,6 +1219,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
         }
       }
     }
+    if (CL) FineHist<true>::zero(hist, lane);      // (the owner's table must be empty before any peer pushes into it)
     block_or_cluster_sync<CL>();     // all columns final; the stash is dead from here (selection reuses it)
 
     MCZ_T(tD0);
@@ -945,13 +1228,13 @@ production_kernel(const __grid_constant__ ProdParams p) {
       for (int k = 0; k < NKEYS; ++k) {
         const int sl = p.slot_of_key[k];
         const bool live = ((pm >> k) & 1ull) && sl >= 0;
-        float* dst = p.Z + ((long long)g * NKEYS + k) * p.N + soff;
-        for (int s = tid; s < N; s += PT) dst[s] = live ? vals[(long long)sl * Npad + s] : Math<float>::nan();
+        float* dst = p.Z + ((long long)g * NKEYS + k) * p.N + SOFF;
+        for (int s = tid, nloc = NLOC; s < nloc; s += PT) dst[s] = live ? vals[(long long)sl * Npad + s] : Math<float>::nan();
       }
     }
 
     // ---- phase D: percentiles, one warp per stored column -------------------------------------
-    if (crank == 0u && tid < NKEYS) {
+    if (CRANK == 0u && tid < NKEYS) {
       const int k = tid, sl = p.slot_of_key[k];
       const bool pres = (pm >> k) & 1ull;
       if (!(pres && sl >= 0)) {
@@ -963,7 +1246,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
         }
       }
     }
-    if (crank == 0u && tid == 0) {
+    if (CRANK == 0u && tid == 0) {
       atomicAdd(&p.stats[0], 1ull);
       atomicAdd(&p.stats[1], (unsigned long long)(executed1 < 0 ? ii1 : executed1));
       atomicAdd(&p.stats[2], (unsigned long long)(executed2 < 0 ? ii2 : executed2));
@@ -975,47 +1258,37 @@ production_kernel(const __grid_constant__ ProdParams p) {
     }
     if (warp == PW - 1) fetch_next();    // (the lines / ticket of this galaxy were read into registers in phase A)
     if constexpr (CL) {
-      // one warp of EVERY block per column, the stages in lock step across the cluster (ClusterSel)
+      // one warp of EVERY block per column; the warps of a column exchange tables, commands and
+      // candidates through the owner block's shared memory (ClusterCol), no cluster barrier
       float* glist = st3 + SLOTS * PT + warp * CL_GLIST_FLOATS;
-      unsigned* gcount = reinterpret_cast<unsigned*>(cand) + 1;
       const int niter = (p.nstore + PW - 1) / PW;
-      const int ncol_pad = (int)csize * Npad;
+      ClusterCol cc;
+      cc.crank = cl_rank(); cc.csize = cl_size(); cc.ng = p.cng;
+      cc.cand_sa = (unsigned)__cvta_generic_to_shared(cand);
+      cc.hist_sa = (unsigned)__cvta_generic_to_shared(hist);
+      cc.glist_sa = (unsigned)__cvta_generic_to_shared(glist);
+      cc.poison_word = p.stats + 7;
+      cc.par = reinterpret_cast<unsigned*>(cand)[ClMail::PAR / 4];     // phase parities of this warp's three barriers
       for (int it = 0; it < niter; ++it) {
+        if (it > 0) {            // more than 18 stored columns: the tables are reused
+          cl_sync();
+          FineHist<true>::zero(hist, lane);
+          cl_sync();
+        }
         const int sl = it * PW + warp;
         const bool has = sl < p.nstore;
         const int k = has ? p.key_of_slot[sl] : 0;
         const bool live = has && ((pm >> k) & 1ull);
-        const unsigned owner = (unsigned)sl % csize;
-        const float* col = vals + (long long)(has ? sl : 0) * Npad;
-        float* gcol = p.gscratch + ((long long)cl_id() * p.nstore + (has ? sl : 0)) * ncol_pad;
-        ClusterSel<SLOTS * PT / 128> cs;
-        cs.init(col, Npad, hist, cand, glist, gcount, live);
-        cs.range(crank);
-        cs.histogram(live);
-        cl_sync();
-        cs.merge(live, crank, csize);
-        cl_sync();
-        cs.plan_and_gather(live, false, gcount, owner, gcol, soff);
-        // second round, if any column of the galaxy asks for it: every block holds the same columns and
-        // makes the same plans, so this block-level vote is the same in every block of the cluster
-        if (__syncthreads_or(live && cs.refine)) {
-          const bool again = live && cs.refine;
-          cs.histogram(again);
-          cl_sync();
-          cs.merge(again, crank, csize);
-          cl_sync();
-          cs.plan_and_gather(again, true, gcount, owner, gcol, soff);
-        }
-        __threadfence();
-        cl_sync();
-        if (live && crank == owner) {
+        if (live) {
+          cc.owner = (unsigned)sl % cc.csize;
+          float* gcol = p.gscratch + ((long long)cl_id() * p.nstore + sl) * ((long long)cc.csize * p.cng * 128);
           float pc[3];
           int nv, stt;
-          cs.finish(cand, gcol, ncol_pad, pc, nv, stt);
-          if (lane == 0) {
+          cc.run(vals + (long long)sl * Npad, hist, cand, glist, gcol, pc, nv, stt);
+          if (cc.crank == cc.owner && lane == 0) {
             atomicAdd(&p.stats[5], 1ull);
-            if (cs.fallback) atomicAdd(&p.stats[6], 1ull);
-            if (cs.refine) atomicAdd(&p.stats[7], 1ull);
+            if (cc.did_fallback) atomicAdd(&p.stats[6], 1ull);
+            if (cc.did_refine) atomicAdd(&p.stats[7], 1ull);
             const long long o = (p.row0 + g) * NKEYS + k;
             for (int q = 0; q < p.ndst; ++q) {
               p.status[q][o] = (signed char)stt;
@@ -1027,6 +1300,8 @@ production_kernel(const __grid_constant__ ProdParams p) {
           }
         }
       }
+      __syncwarp();
+      if (lane == 0) reinterpret_cast<unsigned*>(cand)[ClMail::PAR / 4] = cc.par;
     } else
     for (int sl = warp; sl < p.nstore; sl += PW) {
       const int k = p.key_of_slot[sl];
@@ -1072,6 +1347,11 @@ production_kernel(const __grid_constant__ ProdParams p) {
 #endif
   }
 }
+
+#undef CRANK
+#undef CSIZE
+#undef SOFF
+#undef NLOC
 
 // ---- host side --------------------------------------------------------------------------------
 static void build_slots(uint32_t tok, ProdParams& p) {
@@ -1132,6 +1412,8 @@ struct ProdPlan {
   bool global;
   bool wide;      // global variant with 32-bit histogram counters (Npad >= 65536)
   int scap;       // global variant: samples with their loop state in shared memory
+  int bsm;        // global variant: loop inputs + state of all samples in shared memory (20 bytes + 1 bit each)
+  int cper, cng;  // cluster kernel: samples per block, 128-sample groups per block
   int Npad, grid;
   size_t smem;
   long long per_block_floats;
@@ -1219,22 +1501,41 @@ static ProdPlan make_plan(long long G, long long N, int nstore) {
   pl.global = !(N <= 4ll * PT && smem_local <= 227ull * 1024);
   pl.wide = false;
   pl.scap = 0;
+  pl.bsm = 0;
   pl.cluster = 1;
-  // Longer columns, up to 8 x 2304 samples: a cluster of ceil(N' / 2304) blocks per galaxy, each block
-  // laid out like the one-block kernel plus the owner's candidate lists (MCZ_CLUSTER=0: never)
+  pl.cper = 0; pl.cng = 0;
+  // Longer columns, up to 8 x 2304 samples: a cluster of blocks per galaxy, each block laid out like the
+  // one-block kernel plus the owner's candidate lists (MCZ_CLUSTER=0: never).  The cluster size is at
+  // least ceil(N' / 2304); a larger one can keep more SMs busy (clusters do not span GPCs: with 18 or
+  // 20 SMs per GPC, clusters of 5 use 130 of the 148 SMs, clusters of 6 use 144), so the size with the
+  // best modelled throughput is taken: resident clusters / (fixed cost + per-sample cost x samples per
+  // block), the two costs from the phase timings of the kernel.  MCZ_CLUSTER_SIZE=n forces a size.
   const size_t smem_cluster = smem_local + (size_t)PW * CL_GLIST_FLOATS * sizeof(float);
-  const long long csz = (N + 4ll * PT - 1) / (4ll * PT);
+  const long long cmin = (N + 4ll * PT - 1) / (4ll * PT);
   const char* envc = getenv("MCZ_CLUSTER");
-  if (pl.global && csz >= 2 && csz <= 8 && smem_cluster <= 227ull * 1024 && cluster_wanted(envc)) {
-    const int nclus = max_active_clusters((int)csz, smem_cluster);
-    if (nclus > 0) {
+  if (pl.global && cmin >= 2 && cmin <= 8 && smem_cluster <= 227ull * 1024 && cluster_wanted(envc)) {
+    const char* envs = getenv("MCZ_CLUSTER_SIZE");
+    const int forced = envs ? atoi(envs) : 0;
+    int best = 0, best_n = 0;
+    double best_rate = 0.0;
+    for (int c = (int)cmin; c <= 8; ++c) {
+      if (forced >= cmin && forced <= 8 && c != forced) continue;
+      const int n = max_active_clusters(c, smem_cluster);
+      if (n <= 0) continue;
+      const double per = (double)((N + c - 1) / c);
+      const double rate = (double)(G < n ? (G > 0 ? G : 1) : n) / (14000.0 + 17.0 * per);
+      if (rate > best_rate) { best_rate = rate; best = c; best_n = n; }
+    }
+    if (best > 0) {
       pl.global = false;
-      pl.cluster = (int)csz;
+      pl.cluster = best;
       pl.Npad = 4 * PT;
       pl.smem = smem_cluster;
       pl.per_block_floats = 0;
-      const long long nc = G < nclus ? (G > 0 ? G : 1) : nclus;
-      pl.grid = (int)(nc * csz);
+      pl.cper = (int)((N + best - 1) / best);
+      pl.cng = (pl.cper + 127) / 128;
+      const long long nc = G < best_n ? (G > 0 ? G : 1) : best_n;
+      pl.grid = (int)(nc * best);
       return pl;
     }
   }
@@ -1252,6 +1553,17 @@ static ProdPlan make_plan(long long G, long long N, int nstore) {
     const long long need = (N + PT - 1) / PT * PT;
     pl.scap = (int)(fit < need ? fit : need);
     pl.smem = base + (size_t)pl.scap * 16;
+    // N' <= ~11400 (configs 3 and 5): logO3O2, logN2Ha, logR23 and the two logq of EVERY sample (20 bytes)
+    // plus one flag bit fit in the 226 KB next to the control block -- the selection work area is dead
+    // while the loops run -- so the loops read nothing from global memory (MCZ_BSM=0: never)
+    const size_t nq = (size_t)((N + 3) / 4 * 4);
+    const size_t bsm_bytes = CTRL_BYTES + 20 * nq + 4 * ((nq + 31) / 32) + 16;
+    const char* envb = getenv("MCZ_BSM");
+    if (bsm_bytes <= 227ull * 1024 && !(envb && envb[0] == '0')) {
+      pl.bsm = 1;
+      pl.scap = 0;
+      pl.smem = bsm_bytes > base ? bsm_bytes : base;
+    }
     pl.per_block_floats = ((long long)nstore + 4 + 6) * pl.Npad;
   }
   const long long sms = num_sms();
@@ -1308,7 +1620,7 @@ size_t production_scratch_bytes(long long G, long long n_draw, uint32_t tok) {
   build_slots(tok, p);
   const ProdPlan pl = make_plan(G, n_draw, p.nstore);
   size_t need = SCRATCH_HEADER + (size_t)pl.grid * (size_t)pl.per_block_floats * sizeof(float);
-  if (pl.cluster > 1)     // the fallback columns of every cluster: nstore x (cluster x 2304) floats
+  if (pl.cluster > 1)     // the fallback columns of every cluster: nstore x (cluster x 2304) floats at most
     need = SCRATCH_HEADER + (size_t)(pl.grid / pl.cluster) * (size_t)p.nstore * (size_t)pl.cluster * (size_t)pl.Npad * sizeof(float);
   if (use_wide(G, n_draw, nullptr)) {
     const size_t w = wide_scratch_bytes(n_draw, p.nstore);
@@ -1340,7 +1652,7 @@ int launch_production(const float* meas, const float* err, long long G, long lon
   const ProdPlan pl = make_plan(G, n_draw, p.nstore);
   if (scratch_bytes < ((ws && ws->world > 1) ? wide_private_bytes(n_draw, tok) : production_scratch_bytes(G, n_draw, tok)))
     return set_error("mcz_forward_production: scratch too small");
-  p.meas = meas; p.err = err; p.G = G; p.N = (int)n_draw; p.Npad = pl.Npad; p.scap = pl.scap; p.tok = tok; p.dust = dust;
+  p.meas = meas; p.err = err; p.G = G; p.N = (int)n_draw; p.Npad = pl.Npad; p.scap = pl.scap; p.bsm = pl.bsm; p.cper = pl.cper; p.cng = pl.cng; p.tok = tok; p.dust = dust;
   p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32); p.goff = galaxy_offset;
   p.correlated = sample_mode == 1; p.deterministic = deterministic != 0;
   p.calls = philox_calls(tok, p.correlated, p.deterministic);
@@ -1382,6 +1694,11 @@ int launch_production(const float* meas, const float* err, long long G, long lon
     cfg.attrs = at; cfg.numAttrs = 1;
     rc = check_cuda(cudaLaunchKernelEx(&cfg, production_kernel<4, false, true>, p), "cluster kernel launch");
     if (rc) return rc;
+    if (getenv("MCZ_DEBUG_POISON")) {      // debugging aid: wait for the kernel and report a timed-out protocol wait
+      unsigned long long st[8];
+      if (read_launch_stats(scratch, st, stream) == 0 && (st[7] >> 63))
+        fprintf(stderr, "mcz cluster kernel: protocol wait timed out (where = %llu), results invalid\n", (st[7] >> 56) & 63ull);
+    }
   } else if (!pl.global) {
     if ((rc = ensure_smem_attr(production_kernel<4, false, false>, KID_PROD_SHARED, 227 * 1024))) return rc;
     production_kernel<4, false, false><<<pl.grid, PT, pl.smem, stream>>>(p);

@@ -1023,205 +1023,125 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
 }
 
 // ---- cluster kernel: the selection of one column whose samples are spread over the blocks ------
-// Block r of the cluster holds piece r (Npad samples, NaN beyond the galaxy's N') of every column.
-// Warp w of EVERY block works on column slot w; the stages are separated by cluster barriers that
-// all warps of all blocks execute (ClusterSel::stage*), so the caller runs them in lock step:
-//   stage0  range from the column's first 64 samples (they live in block 0: read through DSMEM; if they
-//           give none -- an all-NaN column, typically -- everything goes to one bin);
-//           pass H over the block's own piece into the block's own histogram;
-//   -- barrier --
-//   stage1  merge of the histograms IN PLACE: block r sums words [r W/C, (r+1) W/C) of all blocks'
-//           tables and writes the totals back into every table (only block r ever touches that share
-//           anywhere, so no second buffer is needed); the counts of the repeated value and the column
-//           sums are exchanged through the spare words;
-//   -- barrier --
-//   stage2  every block makes the SAME plan from its (now global) table; pass G over the block's
-//           own piece, the members appended to the candidate list of the column's OWNER block
-//           (slot mod cluster size) with remote atomics;
-//   -- barrier --
-//   stage3  the owner sorts the candidates and interpolates, exactly as the one-block kernel does.
-// A column that needs the general path (a crowded range, a target in an end bin) is instead copied to a global scratch column by all blocks in stage 2
-// and handed, in stage 3, to the one-block selection (warp_percentiles) by its owner: rare, and
-// every special case keeps the code path that the adversarial tests cover.
-template <int NG> struct ClusterSel {
+// Block r of the cluster holds piece r of every column (`ng` groups of 128 samples, NaN beyond the
+// block's share).  Warp w of EVERY block works on column slot w; one of the blocks is the column's
+// OWNER (slot mod cluster size).  The five or six warps of a column talk to each other through the
+// owner's shared memory with asynchronous DSMEM stores / reductions that signal mbarriers -- there is
+// no cluster-wide barrier inside the selection, so the columns of a galaxy proceed independently,
+// as in the one-block kernel:
+//   all     range from the column's first 64 samples (block 0's piece, read through DSMEM);
+//           pass H over the own piece into the own 1024-bin table;
+//   peers   push the table into the owner's (red.async.add, 2 KB) plus count of the repeated value, sum,
+//           extremes (st.async); wait for the owner's command;
+//   owner   waits until every peer's 2064 bytes have landed; plan from the merged table; command to
+//           the peers (64 bytes each): GATHER (ranges), REFINE (a second round with a finer index),
+//           FALLBACK (whole column through global memory) or NONE;
+//   all     pass G over the own piece: members appended to the owner's candidate list (remote atomic
+//           for the position, st.async for the values, counted in bytes by the owner's third barrier);
+//   owner   sorts the candidates and interpolates, exactly as the one-block kernel does.
+// A column with a crowded range gets ONE second round (the target ranges subdivided 339-fold, or the
+// exact range for a column whose first 64 samples gave none); if that is still not enough, every
+// block copies its piece to a global scratch column and the owner runs the one-block selection
+// (warp_percentiles) on it: rare, and every special case keeps the code the adversarial tests cover.
+enum { CLM_NONE = 0, CLM_GATHER = 1, CLM_REFINE_RANGE = 2, CLM_REFINE_SUB = 3, CLM_FALLBACK = 4 };
+static constexpr unsigned CL_CMD_BYTES = 64u;
+static constexpr unsigned CL_PUSH_BYTES = FineHist<true>::WORDS * 4u + 16u;
+
+// stage timers of the cluster selection (-DMCZ_PHASE_TIMING): cycles summed over columns into
+// g_col_cycles[stage] (owner) / g_col_cycles[16 + stage] (peers); [15] / [31] count the columns
+#ifdef MCZ_PHASE_TIMING
+#define CLT_MARK(stage) do { const long long now_ = clock64(); if (lane == 0) atomicAdd(&g_col_cycles[(own ? 0 : 16) + (stage)], (unsigned long long)(now_ - tmark_)); tmark_ = now_; } while (0)
+#define CLT_START() long long tmark_ = clock64(); if (lane == 0) atomicAdd(&g_col_cycles[(own ? 15 : 31)], 1ull)
+#else
+#define CLT_MARK(stage)
+#define CLT_START()
+#endif
+
+struct ClusterCol {
   typedef FineHist<true> FH;
-  // per-warp state carried across the barriers
-  bool live, fallback, has_tie, refine, gathered, norange;
-  float tie, sum_total, gmin, gmax;
-  unsigned ntie_total;
-  SelWarp w;
-  SelPlan P;
+  unsigned crank, csize, owner;
+  int ng;                       // groups of 128 samples every block streams
+  unsigned cand_sa, hist_sa, glist_sa;
+  unsigned long long* poison_word;
+  unsigned par;                 // bit 0: merge barrier, bit 1: command barrier, bit 2: gather barrier
+  // diagnostics
+  bool did_refine, did_fallback;
 
-  __device__ __forceinline__ void init(const float* v, int Npad, unsigned* hist, float* cand, float* glist, unsigned* gcount,
-                                       bool is_live) {
-    const int lane = threadIdx.x & 31;
-    live = is_live;
-    fallback = false; has_tie = false; refine = false; gathered = false; norange = false;
-    tie = 0.0f; sum_total = 0.0f; ntie_total = 0u; gmin = 0.0f; gmax = 0.0f;
-    w.v = v; w.Npad = Npad; w.hist = hist; w.lane = lane;
-    w.ccount = reinterpret_cast<unsigned*>(cand); w.clist = cand + 32; w.glist = glist;
-    w.scale = 0.0f; w.nLs = 0.5f; w.ngroups = Npad / 128; w.nmine = Npad; w.rnr = 0;
-    if (lane == 0) *gcount = 0u;          // (only the owner's counter is used; appends come after two barriers)
-  }
-
-  // range of the first round from the column's first 64 samples (block 0's piece)
-  __device__ __forceinline__ void range(unsigned crank) {
-    if (!live) return;
+  // pass H over the own piece with the current index of `w`; the table must be zero (or hold the
+  // peers' contributions: the owner's table is zeroed before anything can arrive)
+  __device__ __forceinline__ void histogram(const SelWarp& w, bool has_tie, float tie, bool track,
+                                            float& sum, unsigned& ntie, float& mn, float& mx) const {
     const int lane = w.lane;
-    float a, b;
-    if (crank == 0u) { a = w.v[lane]; b = w.v[lane + 32]; }
-    else { const unsigned ra = cl_map(w.v, 0u); a = cl_ldf(ra + 4u * (unsigned)lane); b = cl_ldf(ra + 4u * (unsigned)(lane + 32)); }
-    // No usable range from the first 64 samples (usually: the column has no finite value at all, or
-    // it is one repeated value, which `has_tie` then covers): one bin for everything in the first
-    // round, which also reduces the exact min / max of the column.  The merged count says "empty" at
-    // once; a column that does hold a spread of finite values gets its real histogram in the second
-    // round, over the exact range.
-    if (!subsample_range_ab(a, b, lane, w.scale, w.nLs, has_tie, tie)) { w.scale = 0.0f; w.nLs = 0.5f; norange = true; }
-  }
-
-  // pass H over the block's own piece with the current index (first round, or second if w.rnr > 0)
-  __device__ __forceinline__ void histogram(bool active) {
-    if (!active) return;
-    const int lane = w.lane;
-    unsigned* hist = w.hist;
-    FH::zero(hist, lane);
-    const unsigned hist_sa = (unsigned)__cvta_generic_to_shared(hist);
     const unsigned lane_sa = hist_sa + 4u * (unsigned)(FH::WORDS + lane);
-    float sum = 0.0f;
-    int ntie = 0;
     const float pinf = __int_as_float(0x7f800000), ninf = __int_as_float(0xff800000);
-    float mn = pinf, mx = ninf;
-    const bool track = norange && !refine;      // (first round of a column without a range: its exact extremes)
-#pragma unroll 2
-    for (int s0 = 4 * lane; s0 < NG * 128; s0 += 128) {
-      const float4 x4 = *reinterpret_cast<const float4*>(w.v + s0);
-      const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+    float sm = 0.0f;
+    int nt = 0;
+    mn = pinf; mx = ninf;
+    if (w.rnr == 0 && !track) {
+#pragma unroll 3
+      for (int g = 0; g < ng; ++g) {
+        const float4 x4 = *reinterpret_cast<const float4*>(w.v + 4 * lane + 128 * g);
+        const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const bool is_tie = has_tie && xs[j] == tie;
-        const bool fin = finite_f(xs[j]);
-        ntie += is_tie ? 1 : 0;
-        sum += fin ? xs[j] : 0.0f;
-        if (track) { mn = fminf(mn, fin ? xs[j] : pinf); mx = fmaxf(mx, fin ? xs[j] : ninf); }
-        FH::add_t(hist_sa, lane_sa, fine_tbits_w(w, xs[j]), fin && !is_tie);
+        for (int j = 0; j < 4; ++j) {
+          const bool is_tie = has_tie && xs[j] == tie;
+          const bool fin = finite_f(xs[j]);
+          nt += is_tie ? 1 : 0;
+          sm += fin ? xs[j] : 0.0f;
+          FH::add_t(hist_sa, lane_sa, fine_tbits(xs[j], w.scale, w.nLs), fin && !is_tie);
+        }
       }
-    }
-    ntie = __reduce_add_sync(0xffffffffu, ntie);
-    sum = warp_sum(sum);
-    if (track) {
+    } else {
+#pragma unroll 2
+      for (int g = 0; g < ng; ++g) {
+        const float4 x4 = *reinterpret_cast<const float4*>(w.v + 4 * lane + 128 * g);
+        const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const bool is_tie = has_tie && xs[j] == tie;
+          const bool fin = finite_f(xs[j]);
+          nt += is_tie ? 1 : 0;
+          sm += fin ? xs[j] : 0.0f;
+          mn = fminf(mn, fin ? xs[j] : pinf);
+          mx = fmaxf(mx, fin ? xs[j] : ninf);
+          FH::add_t(hist_sa, lane_sa, fine_tbits_w(w, xs[j]), fin && !is_tie);
+        }
+      }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
       }
     }
+    nt = __reduce_add_sync(0xffffffffu, nt);
+    sum = warp_sum(sm);
+    ntie = (unsigned)nt;
     __syncwarp();
-    if (lane == 0) {
-      if (ntie > 0) FH::add_n(hist, fine_tbits_w(w, tie) - FINE_BIAS, (unsigned)ntie);
-      hist[FH::WORDS + 32] = (unsigned)ntie;
-      hist[FH::WORDS + 33] = __float_as_uint(sum);
-      hist[FH::WORDS + 34] = __float_as_uint(mn);
-      hist[FH::WORDS + 35] = __float_as_uint(mx);
-    }
+    if (lane == 0 && nt > 0) FH::add_n(w.hist, fine_tbits_w(w, tie) - FINE_BIAS, (unsigned)nt);
+    __syncwarp();
   }
 
-  // merge of the blocks' tables, in place
-  __device__ __forceinline__ void merge(bool active, unsigned crank, unsigned csize) {
-    if (!active) return;
+  // pass G over the own piece: members of the (uncrowded) target ranges -> the owner's candidate list.
+  // Returns how many members this WARP appended.
+  __device__ __forceinline__ unsigned gather(const SelWarp& w, const int tlo_[3], const unsigned tsp[3], float skip) const {
     const int lane = w.lane;
-    const unsigned hs = (unsigned)__cvta_generic_to_shared(w.hist);
-    // the exchange words first (they are outside every share)
-    unsigned nt = 0u;
-    float sm = 0.0f, mn = __int_as_float(0x7f800000), mx = __int_as_float(0xff800000);
-    for (unsigned r = 0; r < csize; ++r) {            // same order in every block: same float total
-      const unsigned ra = cl_map(hs + 4u * (unsigned)(FH::WORDS + 32), r);
-      nt += cl_ld(ra);
-      sm += __uint_as_float(cl_ld(ra + 4u));
-      if (norange && !refine) { mn = fminf(mn, cl_ldf(ra + 8u)); mx = fmaxf(mx, cl_ldf(ra + 12u)); }
-    }
-    ntie_total = nt;
-    sum_total = sm;
-    if (norange && !refine) { gmin = mn; gmax = mx; }
-    // this block's share of the table: totals over all blocks, written back into every table
-    const int per = (FH::WORDS + (int)csize - 1) / (int)csize;
-    const int w0 = (int)crank * per, w1 = min(FH::WORDS, w0 + per);
-    for (int i = w0 + lane; i < w1; i += 32) {
-      unsigned part[8];
-#pragma unroll
-      for (unsigned r = 0; r < 8u; ++r) part[r] = r < csize ? cl_ld(cl_map(hs + 4u * (unsigned)i, r)) : 0u;   // (all loads in flight at once)
-      unsigned tot = 0u;
-#pragma unroll
-      for (unsigned r = 0; r < 8u; ++r) tot += part[r];                   // packed 16-bit pairs: no carry (< 65536 samples)
-      for (unsigned r = 0; r < csize; ++r) cl_st(cl_map(hs + 4u * (unsigned)i, r), tot);
-    }
-  }
-
-  // plan from the merged table; then pass G (members to the owner's list), or the decision to
-  // refine (first round only), or the whole-column path
-  __device__ __forceinline__ void plan_and_gather(bool active, bool second, unsigned* gcount, unsigned owner, float* gcol, int soff) {
-    if (!active) return;
-    const int lane = w.lane;
-    sel_make_plan<true>(w, P, has_tie, tie, has_tie ? fine_tbits_w(w, tie) - FINE_BIAS : 0, ntie_total);
-    if (P.n == 0) { gathered = true; return; }          // no finite value anywhere: the owner reports "empty"
-    bool crowded = P.crowded[0] || P.crowded[1] || P.crowded[2], edge = false;
-#pragma unroll
-    for (int r = 0; r < 3; ++r)
-      if (r < P.nr && (P.rlo[r] == 0 || P.rhi[r] == FB - 1)) edge = true;
-    if (!second && norange && crowded && gmax > gmin) {
-      // second round over the exact range of the column (as exact_range() of the one-block selection)
-      refine = true;
-      const float d = (gmax - gmin) * (2.0f / (float)(FB - 4));
-      const float qlo = gmin - d, qhi = gmax + d;
-      w.scale = 1.0f / (qhi - qlo);
-      w.nLs = -qlo * w.scale;
-      if (!finite_f(w.scale) || !finite_f(w.nLs) || !(w.scale > 0.0f)) { w.scale = 0.0f; w.nLs = 0.5f; }
-      return;
-    }
-    if (!second && crowded && !edge) {
-      // second round: subdivide the target ranges (every block takes the same decision from the same table)
-      refine = true;
-      w.rnr = P.nr;
-#pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        w.rflo[r] = r < P.nr ? P.rlo[r] : 0;
-        w.rfhi[r] = r < P.nr ? P.rhi[r] : 0;
-        w.rmul[r] = r < P.nr ? (float)RSUB / (float)(P.rhi[r] - P.rlo[r] + 1) : 0.0f;
-      }
-      return;
-    }
-    if (crowded || edge) {
-      // whole-column path: the block's piece -> global scratch column of the cluster (the owner selects it)
-      fallback = true;
-#ifdef MCZ_DEBUG_FALLBACK
-      if (lane == 0 && owner == cl_rank())
-        printf("fallback second=%d n=%d nr=%d edge=%d crowded=%d%d%d rM=%u %u %u rlo=%d %d %d rhi=%d %d %d tie=%d ntie=%u has_tie=%d scale=%g\n", (int)second, P.n, P.nr, (int)edge,
-               (int)P.crowded[0], (int)P.crowded[1], (int)P.crowded[2], P.rM[0], P.rM[1], P.rM[2], P.rlo[0], P.rlo[1], P.rlo[2],
-               P.rhi[0], P.rhi[1], P.rhi[2], P.tie_range, ntie_total, (int)has_tie, (double)w.scale);
-#endif
-      for (int s = lane; s < w.Npad; s += 32) gcol[soff + s] = w.v[s];
-      return;
-    }
+    const bool own = crank == owner;
     int tlo[3];
-    unsigned tsp[3];
-    sel_tests(P, true, tlo, tsp);
 #pragma unroll
-    for (int r = 0; r < 3; ++r) tlo[r] += FINE_BIAS;
-    const float skip = P.tie;                         // NaN unless the repeated value is merged back by rank
-    const unsigned cnt_ra = cl_map(gcount, owner), list_ra = cl_map(w.glist, owner);
-    constexpr int CH = 6;
-    constexpr int NCH = (NG + CH - 1) / CH;
+    for (int r = 0; r < 3; ++r) tlo[r] = tlo_[r] + FINE_BIAS;
+    constexpr int CH = 6, NCH = 3;                    // <= 18 groups
     unsigned m[NCH];
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       unsigned mask = 0u;
 #pragma unroll 2
       for (int i = 0; i < CH; ++i) {
-        if (c * CH + i < NG) {
+        if (c * CH + i < ng) {
           const float4 x4 = *reinterpret_cast<const float4*>(w.v + 4 * lane + 128 * (c * CH + i));
           const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const int f = fine_tbits_w(w, xs[j]);
+            const int f = w.rnr == 0 ? fine_tbits(xs[j], w.scale, w.nLs) : fine_tbits_w(w, xs[j]);
             const bool hit = ((unsigned)(f - tlo[0]) <= tsp[0]) || ((unsigned)(f - tlo[1]) <= tsp[1]) ||
                              ((unsigned)(f - tlo[2]) <= tsp[2]);
             mask |= (hit && finite_f(xs[j]) && xs[j] != skip) ? (1u << (4 * i + j)) : 0u;
@@ -1233,39 +1153,241 @@ template <int NG> struct ClusterSel {
     unsigned mine = 0u;
 #pragma unroll
     for (int c = 0; c < NCH; ++c) mine += (unsigned)__popc(m[c]);
-    if (mine) {                                        // one remote atomic per lane that holds members
-      unsigned pos = cl_atom_add(cnt_ra, mine);
+    if (mine) {
+      const unsigned cap = (unsigned)(CL_GLIST_FLOATS - 1);
+      if (own) {
+        unsigned pos = atomicAdd(w.ccount + 1, mine);               // (gcount)
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        unsigned mask = m[c];
-        while (mask) {
-          const int b = __ffs(mask) - 1;
-          mask &= mask - 1u;
-          cl_stf(list_ra + 4u * min(pos, (unsigned)(3 * 64 - 1)), w.v[4 * lane + 128 * (c * CH + (b >> 2)) + (b & 3)]);   // (<= 192 by the plan)
-          ++pos;
+        for (int c = 0; c < NCH; ++c) {
+          unsigned mask = m[c];
+          while (mask) {
+            const int b = __ffs(mask) - 1;
+            mask &= mask - 1u;
+            w.glist[min(pos, cap)] = w.v[4 * lane + 128 * (c * CH + (b >> 2)) + (b & 3)];
+            ++pos;
+          }
+        }
+      } else {
+        const unsigned o_gcount = cl_map(cand_sa + ClMail::GCOUNT, owner), o_glist = cl_map(glist_sa, owner);
+        const unsigned o_gather = cl_map(cand_sa + ClMail::MB_GATHER, owner);
+        unsigned pos = cl_atom_add(o_gcount, mine);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          unsigned mask = m[c];
+          while (mask) {
+            const int b = __ffs(mask) - 1;
+            mask &= mask - 1u;
+            st_async_u32(o_glist + 4u * min(pos, cap), __float_as_uint(w.v[4 * lane + 128 * (c * CH + (b >> 2)) + (b & 3)]), o_gather);
+            ++pos;
+          }
         }
       }
     }
-    gathered = true;
+    return (unsigned)__reduce_add_sync(0xffffffffu, (int)mine);
   }
 
-  // owner only: the percentiles of the column
-  __device__ __forceinline__ void finish(float* cand, float* gcol, int ncol_pad, float pct[3], int& nvalid, int& status) {
-    pct[0] = pct[1] = pct[2] = Math<float>::nan();
+  // The whole protocol for one column; every lane of the column's warp in every block calls it.
+  // col: the block's piece; hist / cand / glist: the warp's areas; gcol: the cluster's global scratch
+  // column (csize * ng * 128 floats).  The owner returns the statistics (is_owner = true).
+  __device__ void run(const float* col, unsigned* hist, float* cand, float* glist, float* gcol,
+                      float pct[3], int& nvalid, int& status) {
+    const int lane = threadIdx.x & 31;
+    const bool own = crank == owner;
+    const float nanf_ = Math<float>::nan();
+    pct[0] = pct[1] = pct[2] = nanf_;
     nvalid = 0;
     status = ST_EMPTY;
-    if (fallback) {                                   // the whole column, by the one-block code
-      warp_percentiles<true, 0>(gcol, ncol_pad, w.hist, cand, pct, nvalid, status);
+    did_refine = false; did_fallback = false;
+    SelWarp w;
+    w.v = col; w.Npad = ng * 128; w.hist = hist; w.lane = lane;
+    w.ccount = reinterpret_cast<unsigned*>(cand); w.clist = cand + 32; w.glist = glist;
+    w.scale = 0.0f; w.nLs = 0.5f; w.ngroups = ng; w.nmine = ng * 128; w.rnr = 0;
+    const unsigned mb_merge = cand_sa + ClMail::MB_MERGE, mb_cmd = cand_sa + ClMail::MB_CMD, mb_gather = cand_sa + ClMail::MB_GATHER;
+    unsigned* const cmdw = reinterpret_cast<unsigned*>(cand) + ClMail::CMD / 4;
+    unsigned* const statw = reinterpret_cast<unsigned*>(cand) + ClMail::STAT / 4;
+    if (lane == 0) w.ccount[1] = 0u;                   // gcount (appends come after two message flights)
+    CLT_START();
+    // ---- range of the first round from the column's first 64 samples (block 0's piece)
+    float a, b;
+    if (crank == 0u) { a = col[lane]; b = col[lane + 32]; }
+    else { const unsigned ra = cl_map(col, 0u); a = cl_ldf(ra + 4u * (unsigned)lane); b = cl_ldf(ra + 4u * (unsigned)(lane + 32)); }
+    bool has_tie;
+    float tie;
+    // No usable range (usually: no finite value at all, or one repeated value, which `has_tie` covers):
+    // one bin for everything in the first round, which also reduces the exact extremes of the column;
+    // a column that does hold a spread of finite values gets its histogram in the second round.
+    const bool norange = !subsample_range_ab(a, b, lane, w.scale, w.nLs, has_tie, tie);
+    if (norange) { w.scale = 0.0f; w.nLs = 0.5f; }
+    CLT_MARK(0);                                       // range
+    SelPlan P;
+    float sum_total = 0.0f;
+    for (int round = 0;; ++round) {
+      float sum, mn, mx;
+      unsigned ntie;
+      if (!own && round > 0) FH::zero(hist, lane);     // (first round: zeroed before the barrier that precedes the selection)
+      histogram(w, has_tie, tie, norange && round == 0, sum, ntie, mn, mx);
+      CLT_MARK(1);                                     // pass H
+      if (!own) {
+        // ---- peer: table and statistics to the owner, then wait for the command
+        const unsigned o_hist = cl_map(hist_sa, owner), o_merge = cl_map(mb_merge, owner);
+#pragma unroll
+        for (int i = 0; i < FH::WORDS / 32; ++i) red_async_add(o_hist + 4u * (unsigned)(i * 32 + lane), hist[i * 32 + lane], o_merge);
+        if (lane == 0) {
+          st_async_v4(cl_map(cand_sa + ClMail::STAT + 16u * crank, owner), ntie, __float_as_uint(sum), __float_as_uint(mn),
+                      __float_as_uint(mx), o_merge);
+          mbar_expect_tx_arrive(mb_cmd, CL_CMD_BYTES);
+        }
+        CLT_MARK(2);                                   // push
+        mbar_wait(mb_cmd, (par >> 1) & 1u, poison_word, 3u);
+        par ^= 2u;
+        CLT_MARK(3);                                   // wait for the command
+        const unsigned mode = cmdw[0];
+        if (mode == CLM_GATHER) {
+          int tlo[3];
+          unsigned tsp[3];
+#pragma unroll
+          for (int r = 0; r < 3; ++r) { tlo[r] = (int)cmdw[1 + r]; tsp[r] = cmdw[4 + r]; }
+          gather(w, tlo, tsp, __uint_as_float(cmdw[7]));
+          CLT_MARK(5);                                 // pass G
+          return;
+        }
+        if (mode == CLM_REFINE_RANGE) {
+          w.scale = __uint_as_float(cmdw[11]); w.nLs = __uint_as_float(cmdw[12]);
+          did_refine = true;
+          continue;
+        }
+        if (mode == CLM_REFINE_SUB) {
+          w.rnr = (int)cmdw[7];
+#pragma unroll
+          for (int r = 0; r < 3; ++r) { w.rflo[r] = (int)cmdw[1 + r]; w.rfhi[r] = (int)cmdw[4 + r]; w.rmul[r] = __uint_as_float(cmdw[8 + r]); }
+          did_refine = true;
+          continue;
+        }
+        if (mode == CLM_FALLBACK) {
+          for (int s = lane; s < ng * 128; s += 32) gcol[(int)crank * ng * 128 + s] = col[s];
+          __threadfence();
+          __syncwarp();
+          if (lane == 0) st_async_u32(cl_map(cand_sa + ClMail::STAT + 16u * crank, owner), 0u, cl_map(mb_gather, owner));
+          did_fallback = true;
+        }
+        return;                                        // CLM_NONE: nothing to gather
+      }
+      // ---- owner: merged table, plan, command
+      if (lane == 0) {
+        statw[4 * crank] = ntie; statw[4 * crank + 1] = __float_as_uint(sum);
+        statw[4 * crank + 2] = __float_as_uint(mn); statw[4 * crank + 3] = __float_as_uint(mx);
+        mbar_expect_tx_arrive(mb_merge, (csize - 1u) * CL_PUSH_BYTES);
+      }
+      mbar_wait(mb_merge, par & 1u, poison_word, 2u);
+      par ^= 1u;
+      CLT_MARK(3);                                     // wait for the peers' tables
+      __syncwarp();
+      unsigned ntie_total = 0u;
+      float gmin = __int_as_float(0x7f800000), gmax = __int_as_float(0xff800000);
+      sum_total = 0.0f;
+      for (unsigned r = 0; r < csize; ++r) {           // rank order: the same float total whoever owns the column
+        const uint4 sv = *reinterpret_cast<const uint4*>(statw + 4 * r);
+        ntie_total += sv.x;
+        sum_total += __uint_as_float(sv.y);
+        gmin = fminf(gmin, __uint_as_float(sv.z));
+        gmax = fmaxf(gmax, __uint_as_float(sv.w));
+      }
+      sel_make_plan<true>(w, P, has_tie, tie, has_tie ? fine_tbits_w(w, tie) - FINE_BIAS : 0, ntie_total);
+      unsigned mode = CLM_GATHER;
+      unsigned cw[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) cw[i] = 0u;
+      if (P.n == 0) {
+        mode = CLM_NONE;
+      } else {
+        const bool crowded = P.crowded[0] || P.crowded[1] || P.crowded[2];
+        bool edge = false;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+          if (r < P.nr && (P.rlo[r] == 0 || P.rhi[r] == FB - 1)) edge = true;      // NaN / inf index into the end bins
+        if (round == 0 && norange && crowded && gmax > gmin) {
+          // second round over the exact range of the column (as exact_range() of the one-block selection)
+          mode = CLM_REFINE_RANGE;
+          const float d = (gmax - gmin) * (2.0f / (float)(FB - 4));
+          const float qlo = gmin - d, qhi = gmax + d;
+          w.scale = 1.0f / (qhi - qlo);
+          w.nLs = -qlo * w.scale;
+          if (!finite_f(w.scale) || !finite_f(w.nLs) || !(w.scale > 0.0f)) { w.scale = 0.0f; w.nLs = 0.5f; }
+          cw[11] = __float_as_uint(w.scale); cw[12] = __float_as_uint(w.nLs);
+        } else if (round == 0 && crowded && !edge) {
+          // second round: the target ranges subdivided
+          mode = CLM_REFINE_SUB;
+          w.rnr = P.nr;
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            w.rflo[r] = r < P.nr ? P.rlo[r] : 0;
+            w.rfhi[r] = r < P.nr ? P.rhi[r] : 0;
+            w.rmul[r] = r < P.nr ? (float)RSUB / (float)(P.rhi[r] - P.rlo[r] + 1) : 0.0f;
+            cw[1 + r] = (unsigned)w.rflo[r]; cw[4 + r] = (unsigned)w.rfhi[r]; cw[8 + r] = __float_as_uint(w.rmul[r]);
+          }
+          cw[7] = (unsigned)w.rnr;
+        } else if (crowded || edge) {
+          mode = CLM_FALLBACK;
+        } else {
+          int tlo[3];
+          unsigned tsp[3];
+          sel_tests(P, true, tlo, tsp);
+#pragma unroll
+          for (int r = 0; r < 3; ++r) { cw[1 + r] = (unsigned)tlo[r]; cw[4 + r] = tsp[r]; }
+          cw[7] = __float_as_uint(P.tie);              // NaN unless the repeated value is merged back by rank
+        }
+      }
+      CLT_MARK(4);                                     // plan
+      cw[0] = mode;
+      if (mode == CLM_REFINE_RANGE || mode == CLM_REFINE_SUB) {
+        FH::zero(hist, lane);                          // before any peer can push its second-round table
+        did_refine = true;
+      }
+      __syncwarp();
+      if ((unsigned)lane < csize && (unsigned)lane != crank) {
+        const unsigned pc = cl_map(cand_sa + ClMail::CMD, (unsigned)lane), pm = cl_map(mb_cmd, (unsigned)lane);
+        st_async_v4(pc, cw[0], cw[1], cw[2], cw[3], pm);
+        st_async_v4(pc + 16u, cw[4], cw[5], cw[6], cw[7], pm);
+        st_async_v4(pc + 32u, cw[8], cw[9], cw[10], cw[11], pm);
+        st_async_v4(pc + 48u, cw[12], cw[13], cw[14], cw[15], pm);
+      }
+      if (mode == CLM_REFINE_RANGE || mode == CLM_REFINE_SUB) continue;
+      if (mode == CLM_NONE) return;                                                     // mcz.py:277-280
+      if (mode == CLM_FALLBACK) {
+        did_fallback = true;
+        for (int s = lane; s < ng * 128; s += 32) gcol[(int)crank * ng * 128 + s] = col[s];
+        if (lane == 0) mbar_expect_tx_arrive(mb_gather, 4u * (csize - 1u));
+        mbar_wait(mb_gather, (par >> 2) & 1u, poison_word, 5u);
+        par ^= 4u;
+        __threadfence();                               // (acquire side: drops stale L1 lines of the scratch column)
+        __syncwarp();
+        warp_percentiles<true, 0>(gcol, (int)csize * ng * 128, hist, cand, pct, nvalid, status);
+        CLT_MARK(8);                                   // whole-column path
+        return;
+      }
+      // ---- gather: own members, then wait for the peers' (counted in bytes)
+      {
+        int tlo[3];
+        unsigned tsp[3];
+        sel_tests(P, true, tlo, tsp);
+        const unsigned ownc = gather(w, tlo, tsp, P.tie);
+        CLT_MARK(5);                                   // pass G
+        if (lane == 0) mbar_expect_tx_arrive(mb_gather, 4u * (P.ncand - min(ownc, P.ncand)));
+        mbar_wait(mb_gather, (par >> 2) & 1u, poison_word, 4u);
+        par ^= 4u;
+        __syncwarp();
+        CLT_MARK(6);                                   // wait for the peers' candidates
+      }
+      nvalid = P.n;
+      if (!(sum_total > 0.0f)) { status = ST_NONPOS; return; }                          // mcz.py:282-285
+      status = ST_OK;
+      const float pinf = __int_as_float(0x7f800000), ninf = __int_as_float(0xff800000);
+      const float bmn[3] = {pinf, pinf, pinf}, bmx[3] = {ninf, ninf, ninf};
+      const unsigned nmin[3] = {0u, 0u, 0u};
+      sel_finish<true>(w, P, bmn, bmx, nmin, pct);
+      CLT_MARK(7);                                     // finish
       return;
     }
-    nvalid = P.n;
-    if (P.n == 0) return;                                                             // mcz.py:277-280
-    if (!(sum_total > 0.0f)) { status = ST_NONPOS; return; }                          // mcz.py:282-285
-    status = ST_OK;
-    const float pinf = __int_as_float(0x7f800000), ninf = __int_as_float(0xff800000);
-    const float bmn[3] = {pinf, pinf, pinf}, bmx[3] = {ninf, ninf, ninf};
-    const unsigned nmin[3] = {0u, 0u, 0u};
-    sel_finish<true>(w, P, bmn, bmx, nmin, pct);
   }
 };
 

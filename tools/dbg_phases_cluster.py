@@ -20,3 +20,11 @@ o = list(out); g = max(o[0], 1)
 print("kernel %s: galaxies(x blocks) %d, %.2f ms" % (L.mcz_production_kernel_name(G, N, tok).decode(), g, a.elapsed_time(b)))
 print("cycles per galaxy-block: A %.0f  B+C %.0f  D own %.0f  D wall %.0f  total %.0f | B prologue %.0f loops %.0f C %.0f" % (
     o[1]/g, o[2]/g, o[3]/g, o[4]/g, (o[1]+o[2]+o[4])/g, o[5]/g, o[6]/g, o[7]/g))
+cc = (ctypes.c_ulonglong * 74)()
+L.mcz_debug_col_cycles(cc, 1)
+cc = list(cc)
+names = ["range", "passH", "push", "wait1", "plan", "passG", "wait2", "finish", "wholecol"]
+for role, off in (("owner", 0), ("peer", 16)):
+    n = max(cc[off + 15], 1)
+    print("%s columns %d: " % (role, n) + "  ".join("%s %.0f" % (names[i], cc[off + i] / n) for i in range(9)) +
+          "  | total %.0f" % (sum(cc[off:off + 9]) / n))
