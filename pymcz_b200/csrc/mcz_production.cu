@@ -258,6 +258,10 @@ template <bool CL> __device__ __forceinline__ void block_or_cluster_sync() {
 #define MCZ_A_UNROLL 1
 #endif
 static constexpr int A_UNROLL = MCZ_A_UNROLL;     // samples of a thread evaluated side by side in phase A
+#ifndef MCZ_BSM_UNROLL
+#define MCZ_BSM_UNROLL 2
+#endif
+static constexpr int BSM_UNROLL = MCZ_BSM_UNROLL;   // samples of a thread evaluated side by side in the shared-memory KK04 loop
 #ifndef MCZ_FX_BITS
 #define MCZ_FX_BITS 20
 #endif
@@ -944,7 +948,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
         while (act1 || act2) {
           float sm4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
           unsigned nanb = 0u;
-#pragma unroll 2
+#pragma unroll BSM_UNROLL
           for (int s = tid; s < N; s += PT) {
             IterState<float> k;                       // only the constants of the loops still running
             iter_logq<float>(st0[s], k);
@@ -1311,7 +1315,11 @@ production_kernel(const __grid_constant__ ProdParams p) {
 #ifdef MCZ_PHASE_TIMING
       const long long tc0 = clock64();
 #endif
-      warp_percentiles<PACK16, GLOBAL ? 0 : SLOTS * PT / 128>(vals + (long long)sl * Npad, Npad, hist, cand, pc, nv, stt);
+      // (global variant: the gather pass prefetches through a per-warp ring behind the candidate areas --
+      // the space the KK04 loops used)
+      float* ring = GLOBAL ? reinterpret_cast<float*>(work + (size_t)PW * (HIST_BYTES + CAND_FLOATS * sizeof(float))) + warp * RING_FLOATS
+                           : nullptr;
+      warp_percentiles<PACK16, GLOBAL ? 0 : SLOTS * PT / 128>(vals + (long long)sl * Npad, Npad, hist, cand, pc, nv, stt, ring);
 #ifdef MCZ_PHASE_TIMING
       if (lane == 0) {
         const unsigned long long dt = (unsigned long long)(clock64() - tc0);
@@ -1556,13 +1564,16 @@ static ProdPlan make_plan(long long G, long long N, int nstore) {
     // N' <= ~11400 (configs 3 and 5): logO3O2, logN2Ha, logR23 and the two logq of EVERY sample (20 bytes)
     // plus one flag bit fit in the 226 KB next to the control block -- the selection work area is dead
     // while the loops run -- so the loops read nothing from global memory (MCZ_BSM=0: never)
+    // (phase D: a 9 KB prefetch ring per warp in the same space)
+    const size_t ring_bytes = base + (size_t)PW * RING_FLOATS * sizeof(float);
+    if (pl.smem < ring_bytes) pl.smem = ring_bytes;
     const size_t nq = (size_t)((N + 3) / 4 * 4);
     const size_t bsm_bytes = CTRL_BYTES + 20 * nq + 4 * ((nq + 31) / 32) + 16;
     const char* envb = getenv("MCZ_BSM");
     if (bsm_bytes <= 227ull * 1024 && !(envb && envb[0] == '0')) {
       pl.bsm = 1;
       pl.scap = 0;
-      pl.smem = bsm_bytes > base ? bsm_bytes : base;
+      pl.smem = bsm_bytes > ring_bytes ? bsm_bytes : ring_bytes;
     }
     pl.per_block_floats = ((long long)nstore + 4 + 6) * pl.Npad;
   }

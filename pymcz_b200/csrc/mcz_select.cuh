@@ -513,7 +513,8 @@ struct SelPlan {
   int rlo[3], rhi[3];      // fine-index range
   unsigned rE[3], rM[3];   // samples below the range / inside it
   int rq[3];               // range of pair q
-  bool crowded[3];         // more than 64 members: not gathered
+  bool crowded[3];         // too many members to gather: resolved by further rounds over the column
+  bool big[3];             // 65 .. BIG_MAX members: gathered, but selected by bisection instead of a 64-key sort
   unsigned need[3];        // members gathered for the range (0 if crowded)
   unsigned loff[3];        // where its candidates start in the sorted list (when not split)
   bool split;              // false: <= 64 candidates in all, one sort; true: one sort per range
@@ -525,7 +526,12 @@ struct SelPlan {
   float tie;
 };
 
-template <bool PACK16>
+// BIG (the long-column instantiations, N' > 2304): a range with 65 .. BIG_MAX members is still gathered,
+// as long as all candidates fit the 256-entry list, and its ranks are found by bisection on the list
+// (list_select) -- bins of a 1024-bin index hold five times more samples at N' = 11000 than at 2200, and
+// a range that is "crowded" costs further passes over the whole column.
+static constexpr unsigned BIG_MAX = 192u, LIST_CAP = 256u;
+template <bool PACK16, bool BIG = false>
 __device__ __forceinline__ void sel_make_plan(const SelWarp& w, SelPlan& P, bool has_tie, float tie, int ftie,
                                               unsigned ntie) {
   unsigned lex, ltot, un;
@@ -609,21 +615,29 @@ __device__ __forceinline__ void sel_make_plan(const SelWarp& w, SelPlan& P, bool
   // a range is gathered if it has at most 64 members (not counting the copies of the tie value);
   // the others are "crowded"
   unsigned ncand = 0;
+  bool anybig = false;
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
     P.crowded[r] = false;
+    P.big[r] = false;
     P.need[r] = 0u;
     if (r < nr) {
       const unsigned need = P.rM[r] - (r == P.tie_range ? P.ntie : 0u);
       if (need <= 64u) { P.need[r] = need; ncand += need; }
+      else if (BIG && need <= BIG_MAX) { P.need[r] = need; ncand += need; P.big[r] = true; anybig = true; }
       else P.crowded[r] = true;
     }
+  }
+  if (BIG && anybig && ncand > LIST_CAP) {            // the list cannot take them all: the big ranges are crowded after all
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+      if (P.big[r]) { P.big[r] = false; P.crowded[r] = true; ncand -= P.need[r]; P.need[r] = 0u; anybig = false; }
   }
   if (P.tie_range >= 0) {
     const bool cr = P.tie_range == 0 ? P.crowded[0] : (P.tie_range == 1 ? P.crowded[1] : P.crowded[2]);
     if (cr) { P.tie_range = -1; P.ntie = 0; P.tie = Math<float>::nan(); }   // still crowded: ties stay members
   }
-  P.split = ncand > 64u;
+  P.split = ncand > 64u || (BIG && anybig);
   P.loff[0] = 0u;
   P.loff[1] = P.need[0];
   P.loff[2] = P.need[0] + P.need[1];
@@ -641,11 +655,53 @@ __device__ __forceinline__ void sel_tests(const SelPlan& P, bool gathered, int t
   }
 }
 
+// Exact order statistics of the members of one range among the gathered candidates: x[i] = entry
+// i * 32 + lane of the list, bit i of `in` says whether it belongs to the range.  Returns the values of
+// 0-based ranks ra <= rb <= ra + 1 by MSB-first bisection on the order-preserving bit patterns,
+// starting below the common prefix of the members: ~20 steps of eight compares and one REDUX.
+__device__ __forceinline__ void list_select(const float x[8], unsigned in, unsigned ra, unsigned rb, float& outA, float& outB) {
+  unsigned u[8];
+  unsigned umin = 0xffffffffu, umax = 0u;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const bool m = (in >> i) & 1u;
+    u[i] = m ? ordered_bits(x[i]) : 0xffffffffu;        // never <= a bisection threshold (those have a zero bit)
+    umin = min(umin, u[i]);
+    umax = max(umax, m ? u[i] : 0u);
+  }
+  umin = __reduce_min_sync(0xffffffffu, umin);
+  umax = __reduce_max_sync(0xffffffffu, umax);
+  const unsigned diff = umin ^ umax;
+  const int top = diff ? 31 - __clz(diff) : -1;          // highest bit in which two members differ
+  unsigned K = top >= 31 ? 0u : (umax >> (top + 1)) << (top + 1);   // the common prefix
+  for (int b = top; b >= 0; --b) {
+    const unsigned T = K | ((1u << b) - 1u);             // keys with bit b clear (given the prefix so far)
+    int c = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c += (u[i] <= T) ? 1 : 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((unsigned)c <= ra) K |= 1u << b;
+  }
+  // K = key of rank ra; rank rb is the same value if enough members are <= K, else the next larger key
+  int cle = 0;
+  unsigned nxt = 0xffffffffu;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    cle += (u[i] <= K) ? 1 : 0;
+    nxt = min(nxt, u[i] > K ? u[i] : 0xffffffffu);
+  }
+  cle = __reduce_add_sync(0xffffffffu, cle);
+  nxt = __reduce_min_sync(0xffffffffu, nxt);
+  const unsigned KB = ((unsigned)cle > rb || nxt == 0xffffffffu) ? K : nxt;
+  outA = __uint_as_float(K >= 0x80000000u ? K - 0x80000000u : ((0x80000000u - K) | 0x80000000u));
+  outB = __uint_as_float(KB >= 0x80000000u ? KB - 0x80000000u : ((0x80000000u - KB) | 0x80000000u));
+}
+
 // Stage "finish": the gathered candidates are in w.glist (range r at P.loff[r], P.need[r] of them,
 // any order); sort them, read the order statistics, resolve crowded ranges, interpolate.
 // For crowded ranges the caller supplies the min / max of their members and how many equal the
 // min, and has compacted those members to the front of each lane's slots (w.nmine, w.ngroups).
-template <bool PACK16>
+template <bool PACK16, bool BIG = false>
 __device__ __forceinline__ void sel_finish(const SelWarp& w, const SelPlan& P, const float bmn[3],
                                            const float bmx[3], const unsigned nmin[3], float pct[3]) {
   const float pinf = __int_as_float(0x7f800000);
@@ -667,6 +723,49 @@ __device__ __forceinline__ void sel_finish(const SelWarp& w, const SelPlan& P, c
       const int lo_t = t == 0 ? P.rlo[0] : (t == 1 ? P.rlo[1] : P.rlo[2]);
       const unsigned sp_t = (unsigned)((t == 0 ? P.rhi[0] : (t == 1 ? P.rhi[1] : P.rhi[2])) - lo_t);
       const bool cr_t = t == 0 ? P.crowded[0] : (t == 1 ? P.crowded[1] : P.crowded[2]);
+      if (BIG && (t == 0 ? P.big[0] : (t == 1 ? P.big[1] : P.big[2]))) {
+        // a big range: its members stay where they are in the list; ranks by bisection
+        float x[8];
+        unsigned in = 0u;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const unsigned idx = (unsigned)(i * 32 + lane);
+          x[i] = w.glist[idx];
+          const bool m = idx < P.ncand && (unsigned)(fine_tbits_w(w, x[i]) - FINE_BIAS - lo_t) <= sp_t;
+          in |= m ? (1u << i) : 0u;
+        }
+        unsigned tless_b = 0;
+        if (P.tie_range == t) {
+          int c = 0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) c += (((in >> i) & 1u) && x[i] < P.tie) ? 1 : 0;
+          tless_b = (unsigned)__reduce_add_sync(0xffffffffu, c);
+        }
+        const unsigned E = t == 0 ? P.rE[0] : (t == 1 ? P.rE[1] : P.rE[2]);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          if (P.rq[q] != t) continue;
+          unsigned rho[2];
+          bool is_tie[2];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            rho[h] = P.rk[2 * q + h] - E;
+            is_tie[h] = false;
+            if (P.tie_range == t) {
+              if (rho[h] >= tless_b && rho[h] < tless_b + P.ntie) is_tie[h] = true;
+              else if (rho[h] >= tless_b + P.ntie) rho[h] -= P.ntie;
+            }
+          }
+          // (a rank that falls on the repeated value is not among the gathered members; the bisection
+          // then runs for the other rank of the pair)
+          const unsigned ra = is_tie[0] ? rho[1] : rho[0], rb = is_tie[1] ? ra : rho[1];
+          float va, vb;
+          list_select(x, in, ra, rb >= ra ? rb : ra, va, vb);
+          res[2 * q] = is_tie[0] ? P.tie : va;
+          res[2 * q + 1] = is_tie[1] ? P.tie : (is_tie[0] ? va : vb);
+        }
+        continue;
+      }
       unsigned c = 0;
       if (!cr_t) {
         for (unsigned i0 = 0; i0 < P.ncand; i0 += 32u) {
@@ -763,9 +862,12 @@ __device__ __forceinline__ bool exact_range(const SelWarp& w, float& scale, floa
 // v has Npad (multiple of 128) readable entries; entries in [N, Npad) are NaN.
 // hist: FineHist<PACK16>::WORDS words; cand: 128 floats.
 // NG: number of 128-sample groups when it is known at compile time (Npad == 128 * NG), else 0.
+// ring: optional staging area of the warp for long columns in global memory (RING_FLOATS floats, 16-byte
+// aligned): the gather pass then prefetches the column two chunks ahead with cp.async.
+static constexpr int RING_CH = 6, RING_SLOTS = 3, RING_FLOATS = RING_SLOTS * RING_CH * 128;
 template <bool PACK16, int NG>
 __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned* hist, float* cand,
-                                 float pct[3], int& nvalid, int& status) {
+                                 float pct[3], int& nvalid, int& status, float* ring = nullptr) {
   typedef FineHist<PACK16> FH;
   const int lane = threadIdx.x & 31;
   SelWarp w;
@@ -833,7 +935,8 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
   }
   MCZ_TS(ts2);
   SelPlan P;
-  sel_make_plan<PACK16>(w, P, has_tie, tie, has_tie ? fine_index(tie, scale, nLs) : 0, ntie_total);
+  constexpr bool BIG = NG == 0;         // the long-column instantiations
+  sel_make_plan<PACK16, BIG>(w, P, has_tie, tie, has_tie ? fine_index(tie, scale, nLs) : 0, ntie_total);
   const float skip = P.tie;           // NaN unless a tie value is merged back by rank (never equal then)
   nvalid = P.n;
   if (P.n == 0) { sel_count(SEL_TRIVIAL); status = ST_EMPTY; return; }              // mcz.py:277-280
@@ -911,6 +1014,63 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
         }
         done = true;
       }
+    }
+    if (NG == 0 && ring != nullptr) {
+      // Long column in global memory: the lane's own 16-byte pieces of the next two chunks are in flight
+      // (cp.async into the lane's slots of the ring) while it tests the current one; nobody else reads
+      // those slots, so no synchronisation beyond the lane's own wait_group is needed.
+      static_assert(CH == RING_CH, "ring layout");
+      const unsigned ring_sa = (unsigned)__cvta_generic_to_shared(ring) + 16u * (unsigned)lane;
+      const int nchunks = (ngroups + CH - 1) / CH;
+      auto issue = [&](int c, int slot) {
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+          const int g = c * CH + i;
+          if (g < ngroups)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(ring_sa + (unsigned)((slot * CH + i) * 512)),
+                         "l"(v + 4 * lane + 128 * g) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      };
+      issue(0, 0);
+      issue(1, 1);
+      int slot = 0;
+#pragma unroll 1
+      for (int c = 0; c < nchunks; ++c) {
+        const int nslot = slot == 0 ? 2 : slot - 1;          // the slot of chunk c + 2 = the one chunk c - 1 used
+        issue(c + 2, nslot);                                 // (past the end: an empty group keeps the count uniform)
+        asm volatile("cp.async.wait_group 2;" ::: "memory");
+        unsigned mask = 0u;
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+          if (c * CH + i < ngroups) {
+            float4 x4;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x4.x), "=f"(x4.y), "=f"(x4.z), "=f"(x4.w)
+                         : "r"(ring_sa + (unsigned)((slot * CH + i) * 512)) : "memory");
+            const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float x = xs[j];
+              const int f = fine_tbits(x, scale, nLs);            // non-finite x: an end bin, no member here
+              const bool hit = ((unsigned)(f - tlo[0]) <= tsp[0]) || ((unsigned)(f - tlo[1]) <= tsp[1]) ||
+                               ((unsigned)(f - tlo[2]) <= tsp[2]);
+              mask |= (hit && x != skip) ? (1u << (4 * i + j)) : 0u;
+            }
+          }
+        }
+        if (mask) {
+          unsigned pos = atomicAdd(w.ccount, (unsigned)__popc(mask));
+          do {
+            const int b = __ffs(mask) - 1;
+            mask &= mask - 1u;
+            w.glist[pos & 255u] = v[4 * lane + 128 * (c * CH + (b >> 2)) + (b & 3)];
+            ++pos;
+          } while (mask);
+        }
+        slot = slot == 2 ? 0 : slot + 1;
+      }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      done = true;
     }
     if (!done)
 #pragma unroll 1
@@ -1011,7 +1171,7 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
   w.dbg = (P.crowded[0] ? 1 : 0) | (P.crowded[1] ? 2 : 0) | (P.crowded[2] ? 4 : 0) | (P.tie_range >= 0 ? 8 : 0) |
           (has_tie ? 16 : 0) | (P.nr << 5);
 #endif
-  sel_finish<PACK16>(w, P, bmn, bmx, nmin, pct);
+  sel_finish<PACK16, BIG>(w, P, bmn, bmx, nmin, pct);
 #ifdef MCZ_COLTIME_DUMP
   nvalid |= w.dbg << 16;
 #endif

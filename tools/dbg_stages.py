@@ -4,14 +4,21 @@ import sys, numpy as np, torch
 sys.path.insert(0, '.')
 from pymcz_b200 import _scales as sc, ops
 from pymcz_b200.synth import synthetic_table
-G = 2960
-meas, err = synthetic_table(125000, config=4, start=0, stop=G)
+N = int(sys.argv[2]) if len(sys.argv) > 2 else 2200
+G = int(sys.argv[3]) if len(sys.argv) > 3 else 2960
+if N <= 2304:
+    meas, err = synthetic_table(125000, config=4, start=0, stop=G)
+else:
+    meas, err = synthetic_table(G, config=3)
 m = torch.from_numpy(meas).cuda(); e = torch.from_numpy(err).cuda()
-ws = ops.ProductionWorkspace(G, 2200, sc.T_ALL, m.device)
-ops.forward_production(m, e, 2200, sc.T_ALL, workspace=ws); torch.cuda.synchronize()
-pct, nv, st, tr, ret, Z = ops.forward_production(m, e, 2200, sc.T_ALL, workspace=ws)
+ws = ops.ProductionWorkspace(G, N, sc.T_ALL, m.device)
+ops.forward_production(m, e, N, sc.T_ALL, workspace=ws); torch.cuda.synchronize()
+pct, nv, st, tr, ret, Z = ops.forward_production(m, e, N, sc.T_ALL, workspace=ws)
 torch.cuda.synchronize()
 t = pct.cpu().numpy().astype(np.float64); st = st.cpu().numpy()
 ok = st == 0
-print(sys.argv[1:], "mean over OK columns:", [round(float(t[:, :, i][ok].mean())) for i in range(3)],
+print(sys.argv[1:2], N, "mean over OK columns:", [round(float(t[:, :, i][ok].mean())) for i in range(3)],
       "median:", [round(float(np.median(t[:, :, i][ok]))) for i in range(3)])
+for i in range(3):
+    v = t[:, :, i][ok]
+    print("  stage %d: p10 %.0f p50 %.0f p90 %.0f p99 %.0f max %.0f" % (i, *np.percentile(v, [10, 50, 90, 99]), v.max()))
