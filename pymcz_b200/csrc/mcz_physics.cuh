@@ -158,7 +158,17 @@ template <typename R> MCZ_HD void kd02_n2o2_real_roots(R L, R& hi, R& lo) {
   // (the fitted t(s) covers the window of KD02_N2O2 only: outside it the roots are not reported)
   if (L > R(RT_N2O2_F_HI)) return;
   hi = R(RT_N2O2_X0) + rt_n2o2_t<R>(s);
-  lo = R(RT_N2O2_X0) + rt_n2o2_t<R>(-s);
+  // The partner root lies below the window for most L (t(-s) is fitted for -s >= -0.39 only): Newton
+  // on t sqrt(h(t)) = -s from the fitted value inside the fit's domain, from -s / sqrt(h(0)) outside.
+  R t = (-s >= R(RT_N2O2_SEG0_MID) - R(1.0) / R(RT_N2O2_SEG0_RHALF)) ? rt_n2o2_t<R>(-s) : -s / Math<R>::sqrt(R(RT_N2O2_H0));
+#pragma unroll 1
+  for (int it = 0; it < 8; ++it) {
+    const R h = R(RT_N2O2_H0) + t * (R(RT_N2O2_H1) + t * R(RT_N2O2_H2));
+    const R q = Math<R>::sqrt(h);
+    const R dphi = q + t * (R(RT_N2O2_H1) + R(2.0 * RT_N2O2_H2) * t) / (R(2.0) * q);
+    t = t - (t * q + s) / dphi;
+  }
+  lo = R(RT_N2O2_X0) + t;
 }
 
 // M08 [NII]/Ha (metscales.py:994-999): first root (np.roots order) with root+8.69 in [7.1, 9.4].

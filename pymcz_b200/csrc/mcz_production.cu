@@ -66,6 +66,7 @@ struct ProdParams {
   int nstore;
   int scap;                                // global variant: samples whose KK04 loop state lives in shared memory
   int bsm;                                 // global variant: the inputs and the state of the KK04 loops fit in shared memory
+  int ring;                                // global variant: per-warp prefetch rings for the gather pass
   int cper, cng;                           // cluster kernel: samples per block, 128-sample groups streamed per block
   signed char slot_of_key[NKEYS];
   signed char key_of_slot[NKEYS];
@@ -1317,7 +1318,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
 #endif
       // (global variant: the gather pass prefetches through a per-warp ring behind the candidate areas --
       // the space the KK04 loops used)
-      float* ring = GLOBAL ? reinterpret_cast<float*>(work + (size_t)PW * (HIST_BYTES + CAND_FLOATS * sizeof(float))) + warp * RING_FLOATS
+      float* ring = (GLOBAL && p.ring) ? reinterpret_cast<float*>(work + (size_t)PW * (HIST_BYTES + CAND_FLOATS * sizeof(float))) + warp * RING_FLOATS
                            : nullptr;
       warp_percentiles<PACK16, GLOBAL ? 0 : SLOTS * PT / 128>(vals + (long long)sl * Npad, Npad, hist, cand, pc, nv, stt, ring);
 #ifdef MCZ_PHASE_TIMING
@@ -1421,6 +1422,7 @@ struct ProdPlan {
   bool wide;      // global variant with 32-bit histogram counters (Npad >= 65536)
   int scap;       // global variant: samples with their loop state in shared memory
   int bsm;        // global variant: loop inputs + state of all samples in shared memory (20 bytes + 1 bit each)
+  int ring;       // global variant: room for the per-warp prefetch rings of the gather pass
   int cper, cng;  // cluster kernel: samples per block, 128-sample groups per block
   int Npad, grid;
   size_t smem;
@@ -1510,6 +1512,7 @@ static ProdPlan make_plan(long long G, long long N, int nstore) {
   pl.wide = false;
   pl.scap = 0;
   pl.bsm = 0;
+  pl.ring = 0;
   pl.cluster = 1;
   pl.cper = 0; pl.cng = 0;
   // Longer columns, up to 8 x 2304 samples: a cluster of blocks per galaxy, each block laid out like the
@@ -1566,14 +1569,16 @@ static ProdPlan make_plan(long long G, long long N, int nstore) {
     // while the loops run -- so the loops read nothing from global memory (MCZ_BSM=0: never)
     // (phase D: a 9 KB prefetch ring per warp in the same space)
     const size_t ring_bytes = base + (size_t)PW * RING_FLOATS * sizeof(float);
-    if (pl.smem < ring_bytes) pl.smem = ring_bytes;
+    pl.ring = ring_bytes <= 227ull * 1024;             // (not next to the 32-bit histogram counters of >= 65536-sample columns)
+    if (pl.ring && pl.smem < ring_bytes) pl.smem = ring_bytes;
     const size_t nq = (size_t)((N + 3) / 4 * 4);
     const size_t bsm_bytes = CTRL_BYTES + 20 * nq + 4 * ((nq + 31) / 32) + 16;
     const char* envb = getenv("MCZ_BSM");
     if (bsm_bytes <= 227ull * 1024 && !(envb && envb[0] == '0')) {
       pl.bsm = 1;
       pl.scap = 0;
-      pl.smem = bsm_bytes > ring_bytes ? bsm_bytes : ring_bytes;
+      pl.smem = (!pl.ring || bsm_bytes > ring_bytes) ? bsm_bytes : ring_bytes;
+      if (pl.smem < base) pl.smem = base;
     }
     pl.per_block_floats = ((long long)nstore + 4 + 6) * pl.Npad;
   }
@@ -1663,7 +1668,7 @@ int launch_production(const float* meas, const float* err, long long G, long lon
   const ProdPlan pl = make_plan(G, n_draw, p.nstore);
   if (scratch_bytes < ((ws && ws->world > 1) ? wide_private_bytes(n_draw, tok) : production_scratch_bytes(G, n_draw, tok)))
     return set_error("mcz_forward_production: scratch too small");
-  p.meas = meas; p.err = err; p.G = G; p.N = (int)n_draw; p.Npad = pl.Npad; p.scap = pl.scap; p.bsm = pl.bsm; p.cper = pl.cper; p.cng = pl.cng; p.tok = tok; p.dust = dust;
+  p.meas = meas; p.err = err; p.G = G; p.N = (int)n_draw; p.Npad = pl.Npad; p.scap = pl.scap; p.bsm = pl.bsm; p.ring = pl.ring; p.cper = pl.cper; p.cng = pl.cng; p.tok = tok; p.dust = dust;
   p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32); p.goff = galaxy_offset;
   p.correlated = sample_mode == 1; p.deterministic = deterministic != 0;
   p.calls = philox_calls(tok, p.correlated, p.deterministic);

@@ -29,7 +29,7 @@ WANT = [
 ]
 
 
-def main(rep, galaxies, tag, n_draw=2200):
+def main(rep, galaxies, tag, n_draw=2200, md="all", kernel_base=None):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, row = rows[0], rows[1], rows[2]
@@ -56,6 +56,13 @@ def main(rep, galaxies, tag, n_draw=2200):
                                                   (int(galaxies) * n_draw)),
         "issue_slots_per_galaxy_sample": float(vals["smsp__inst_executed.sum"][0]) * 32 / (int(galaxies) * n_draw),
         "source": os.path.basename(rep),
+        # what bench.py matches a capture against: the kernel launch_production() picks, the launch shape,
+        # the tokens, and the commit of the profiled build
+        "kernel_base": kernel_base, "md": md,
+        "commit": subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip(),
+        "sm__inst_executed_pipe_xu": float(vals["sm__inst_executed_pipe_xu.sum"][0].replace(",", "")) if "sm__inst_executed_pipe_xu.sum" in vals else None,
+        "sm__inst_executed_pipe_alu": float(vals["sm__inst_executed_pipe_alu.sum"][0].replace(",", "")) if "sm__inst_executed_pipe_alu.sum" in vals else None,
+        "sm__inst_executed_pipe_fma": float(vals["sm__inst_executed_pipe_fma.sum"][0].replace(",", "")) if "sm__inst_executed_pipe_fma.sum" in vals else None,
     }
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     with open(os.path.join(ROOT, "profiles", "%s_production_kernel.json" % tag), "w") as f:
@@ -81,4 +88,5 @@ def main(rep, galaxies, tag, n_draw=2200):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2], sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else 2200)
+    main(sys.argv[1], sys.argv[2], sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else 2200,
+         sys.argv[5] if len(sys.argv) > 5 else "all", sys.argv[6] if len(sys.argv) > 6 else None)
