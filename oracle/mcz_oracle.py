@@ -636,7 +636,8 @@ class Diag:
         self.mds["D16"] = v
 
 
-def calculation(flux, mds='all', dust_corr=True, ignoredust=False, roots_mode="loop", normal=None):
+def calculation(flux, mds='all', dust_corr=True, ignoredust=False, roots_mode="loop", normal=None,
+                dropnegatives=False):
     """``metallicity.calculation`` (metallicity.py:86-257) for ONE galaxy.
 
     flux : float64 array [11, N] in ``LINES`` order (NaN rows = line absent) -- it is sanitised
@@ -655,7 +656,7 @@ def calculation(flux, mds='all', dust_corr=True, ignoredust=False, roots_mode="l
         for k in range(11):                                                # metallicity.py:94-99
             row = flux[k]
             row[~np.isfinite(row)] = 0.0
-            row[row < 0] = 0.0
+            row[row < 0] = np.nan if dropnegatives else 0.0                # DROPNEGATIVES / FIXNEGATIVES, metallicity.py:23-26, 98-102
         o34959 = flux[L_O3] / 3.                                           # metallicity.py:108
         d.set_hab(flux[L_HA], flux[L_HB])
         if dust_corr and d.has['Ha'] and d.has['Hb']:                      # metallicity.py:113-115

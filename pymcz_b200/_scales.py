@@ -24,6 +24,8 @@ NLINES = len(LINES)
 T_D02, T_Z94, T_M91, T_PP04, T_P10, T_M08, T_M08ALL, T_M13, T_KD02, T_P05, T_C01, T_P01, T_DP00, T_D16 = (
     1 << i for i in range(14))
 T_ALL = T_D02 | T_Z94 | T_M91 | T_PP04 | T_P10 | T_M08 | T_M13 | T_KD02
+#: not a scale: the reference's DROPNEGATIVES sanitise mode (metallicity.py:23-26) rides in the token mask
+T_DROPNEG = 1 << 30
 
 _TOKEN_BITS = {
     'all': T_ALL, 'D02': T_D02, 'Z94': T_Z94, 'M91': T_M91, 'PP04': T_PP04, 'P10': T_P10,

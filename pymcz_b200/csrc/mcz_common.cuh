@@ -73,7 +73,10 @@ enum Token : uint32_t {
   T_D02 = 1u << 0, T_Z94 = 1u << 1, T_M91 = 1u << 2, T_PP04 = 1u << 3, T_P10 = 1u << 4,
   T_M08 = 1u << 5, T_M08ALL = 1u << 6, T_M13 = 1u << 7, T_KD02 = 1u << 8, T_P05 = 1u << 9,
   T_C01 = 1u << 10, T_P01 = 1u << 11, T_DP00 = 1u << 12, T_D16 = 1u << 13,
-  T_ALL = T_D02 | T_Z94 | T_M91 | T_PP04 | T_P10 | T_M08 | T_M13 | T_KD02   // metallicity.py:161-188
+  T_ALL = T_D02 | T_Z94 | T_M91 | T_PP04 | T_P10 | T_M08 | T_M13 | T_KD02,  // metallicity.py:161-188
+  // not a scale: the sanitise mode of metallicity.py:23-26, 98-102 rides in the token mask.  Set: the
+  // reference's DROPNEGATIVES (a negative flux sample becomes NaN); clear: FIXNEGATIVES (it becomes 0).
+  T_DROPNEG = 1u << 30
 };
 
 // dust request passed by the caller (metallicity.py:113-132)

@@ -613,9 +613,10 @@ production_kernel(const __grid_constant__ ProdParams p) {
             float f[NUSED], e[5];
 #pragma unroll
             for (int u = 0; u < NUSED; ++u) {
-              float v = fmaf(le[u], (!MODE && p.correlated) ? z[5] : z[5 + u], lm[u]);   // mcz.py:442 / :589
-              v = fmaxf(v, 0.0f);                       // NaN -> 0 and negative -> 0 (metallicity.py:96, 99)
+              const float raw = fmaf(le[u], (!MODE && p.correlated) ? z[5] : z[5 + u], lm[u]);   // mcz.py:442 / :589
+              float v = fmaxf(raw, 0.0f);               // NaN -> 0 and negative -> 0 (metallicity.py:96, 99)
               if (!MODE && !(v <= FLT_MAX)) v = 0.0f;   // +inf -> 0 (metallicity.py:96); cannot happen when `bounded`
+              if (!MODE && (p.tok & T_DROPNEG) && raw < 0.0f && raw >= -FLT_MAX) v = Math<float>::nan();   // DROPNEGATIVES (metallicity.py:101-102)
               f[u] = v;
               const bool pos = (u >= U_S2B) ? (v > 1e-9f) : (v > 0.0f);
               if (pos) seen |= 1u << u;
@@ -1842,9 +1843,10 @@ wide_kernel(const __grid_constant__ ProdParams p) {
           float f[NUSED], e[5];
 #pragma unroll
           for (int u = 0; u < NUSED; ++u) {
-            float v = fmaf(le[u], p.correlated ? z[5] : z[5 + u], lm[u]);
-            v = fmaxf(v, 0.0f);
+            const float raw = fmaf(le[u], p.correlated ? z[5] : z[5 + u], lm[u]);
+            float v = fmaxf(raw, 0.0f);
             if (!(v <= FLT_MAX)) v = 0.0f;
+            if ((p.tok & T_DROPNEG) && raw < 0.0f && raw >= -FLT_MAX) v = Math<float>::nan();
             f[u] = v;
             const bool pos = (u >= U_S2B) ? (v > 1e-9f) : (v > 0.0f);
             if (pos) seen |= 1u << u;
@@ -2442,9 +2444,10 @@ sample_export_kernel(const __grid_constant__ ProdParams p, float* __restrict__ f
     for (int u = 0; u < NUSED; ++u) {
       const float lm = p.meas[g * NLINES + used2line[u]];
       const float le = p.deterministic ? 0.0f : p.err[g * NLINES + used2line[u]];
-      float v = fmaf(le, p.correlated ? z[5] : z[5 + u], lm);
-      v = fmaxf(v, 0.0f);
+      const float raw = fmaf(le, p.correlated ? z[5] : z[5 + u], lm);
+      float v = fmaxf(raw, 0.0f);
       if (!(v <= FLT_MAX)) v = 0.0f;
+      if ((p.tok & T_DROPNEG) && raw < 0.0f && raw >= -FLT_MAX) v = Math<float>::nan();
       flux[(g * NUSED + u) * p.N + s] = v;
     }
     const float sg[5] = {0.05f, 0.1f, 0.027f, 0.024f, 0.012f};

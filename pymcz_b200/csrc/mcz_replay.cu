@@ -10,9 +10,9 @@ namespace mcz {
 
 static constexpr int RB = 256;   // threads per block
 
-__device__ __forceinline__ double sanitise(double v) {      // metallicity.py:96-99
+__device__ __forceinline__ double sanitise(double v, bool dropneg) {      // metallicity.py:96-102
   if (!(fabs(v) <= 1.7976931348623157e308)) v = 0.0;
-  if (v < 0.0) v = 0.0;
+  if (v < 0.0) v = dropneg ? Math<double>::nan() : 0.0;       // DROPNEGATIVES / FIXNEGATIVES
   return v;
 }
 
@@ -50,7 +50,7 @@ replay_kernel(const double* __restrict__ flux, const double* __restrict__ noise,
     for (long long s = tid; s < N; s += RB) {
 #pragma unroll
       for (int u = 0; u < NUSED; ++u) {
-        const double v = sanitise(flux[((long long)used2line[u] * G + g) * N + s]);
+        const double v = sanitise(flux[((long long)used2line[u] * G + g) * N + s], (tok & T_DROPNEG) != 0u);
         const bool pos = (u >= U_S2B) ? (v > 1e-9) : (v > 0.0);
         if (pos) local |= 1u << u;
       }
@@ -68,7 +68,7 @@ replay_kernel(const double* __restrict__ flux, const double* __restrict__ noise,
       R f[NUSED], e[5];
 #pragma unroll
       for (int u = 0; u < NUSED; ++u)
-        f[u] = (R)sanitise(flux[((long long)used2line[u] * G + g) * N + s]);
+        f[u] = (R)sanitise(flux[((long long)used2line[u] * G + g) * N + s], (tok & T_DROPNEG) != 0u);
 #pragma unroll
       for (int j = 0; j < 5; ++j) e[j] = noise ? (R)noise[((long long)j * G + g) * N + s] : R(0);
       double* auxs = aux ? aux + ((long long)g * NAUX) * N + s : nullptr;

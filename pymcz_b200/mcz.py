@@ -203,6 +203,8 @@ def run(fi, nsample, mds, multiproc, logf, unpickle=False, dust_corr=True, verbo
 
     meas_t, err_t = tables_from_structured(flux, err, nm)
     tokens, third, _unknown = sc.parse_md(mds)
+    if metallicity.DROPNEGATIVES:                                          # metallicity.py:24, 101-102
+        tokens |= sc.T_DROPNEG
     for t in third + (['D13'] if 'all' in mds.split(',') else []):
         metallicity.printsafemulti("WARNING: %s scales need third-party code (pyqz / HII-CHI-mistry) that this "
                                    "build does not vendor; they are left empty" % t, logf, 1)

@@ -13,7 +13,7 @@ from . import _scales as sc
 IGNOREDUST = False        # metallicity.py:21 (sticky, set at :127)
 MP = True
 FIXNEGATIVES = True       # metallicity.py:23
-DROPNEGATIVES = False     # metallicity.py:24 (not supported: the kernels zero negatives)
+DROPNEGATIVES = False     # metallicity.py:24: negative flux samples become NaN instead of 0 (wins over FIXNEGATIVES, :25-26)
 
 Zs = list(sc.KEYS)        # metallicity.py:29-56
 Zserr = list(sc.ERRKEYS)  # metallicity.py:59
@@ -62,9 +62,12 @@ def calculation(mscales, measured, num, mds, nps, logf, dust_corr=True, disp=Fal
     raw_lines = {'[OIII]5007': np.array([float('NaN')]), 'Hb': np.array([float('NaN')])}
     for k in list(measured.keys()):                                        # metallicity.py:94-104
         measured[k][~(np.isfinite(measured[k][:]))] = 0.0
-        if FIXNEGATIVES:
+        if FIXNEGATIVES and not DROPNEGATIVES:
             measured[k][measured[k] < 0] = 0.0
+        if DROPNEGATIVES:                                                  # metallicity.py:101-102
+            measured[k][measured[k] < 0] = np.nan
         raw_lines[k] = measured[k]
+    mscales._dropneg = bool(DROPNEGATIVES)
     raw_lines['[OIII]4959'] = raw_lines['[OIII]5007'] / 3.                 # metallicity.py:108
     mscales.setHab(raw_lines['Ha'], raw_lines['Hb'])                       # KeyError without 'Ha', as the reference
 

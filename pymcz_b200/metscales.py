@@ -51,6 +51,7 @@ class diagnostics:
         self.N26584 = self.S26717 = self.S26731 = self.S39069 = self.S39532 = None
         self.mds = {Z: None for Z in sc.KEYS}
         self._dust = sc.DUST_ON          # what calculation() decided (metallicity.py:113-132)
+        self._dropneg = False            # calculation() ran with DROPNEGATIVES (metallicity.py:24, 101-102)
         self._noise = np.zeros((5, 1, 1))
         self.trips = (0, 0)              # trips of the KK04_N2Ha / KK04_R23 loops of the last run
         self.ret = None
@@ -121,7 +122,10 @@ class diagnostics:
                 continue
             arr = np.asarray(arr, dtype=np.float64)
             if arr.shape == (n,):
-                flux[sc.LINES.index(name), 0] = arr
+                # DROPNEGATIVES: calculation() has already turned the negative samples into NaN in the
+                # caller's arrays (after zeroing the non-finite ones); the kernel sanitises what it is
+                # given, so they travel as negatives and become NaN again there (T_DROPNEG)
+                flux[sc.LINES.index(name), 0] = np.where(np.isnan(arr), -1.0, arr) if self._dropneg else arr
         return flux
 
     def _run(self, tokens, keys=None):
@@ -132,6 +136,8 @@ class diagnostics:
         n = flux.shape[2]
         noise = self._noise if self._noise.shape == (5, 1, n) else np.zeros((5, 1, n))
         dev = torch.device("cuda", torch.cuda.current_device())
+        if self._dropneg:
+            tokens |= sc.T_DROPNEG
         Z, present, trips, ret, aux = ops.forward_replay(torch.from_numpy(flux).to(dev), torch.from_numpy(noise).to(dev),
                                                          tokens, self._dust, "f64", return_aux=True)
         pres = ops.present_to_bool(present)[0].cpu().numpy()

@@ -59,15 +59,17 @@ def main(rep, galaxies, tag, n_draw=2200, md="all", kernel_base=None):
         # what bench.py matches a capture against: the kernel launch_production() picks, the launch shape,
         # the tokens, and the commit of the profiled build
         "kernel_base": kernel_base, "md": md,
-        "commit": subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip(),
+        "commit": os.environ.get("MCZ_COMMIT") or subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"],
+                                                                  capture_output=True, text=True).stdout.strip(),
         "sm__inst_executed_pipe_xu": float(vals["sm__inst_executed_pipe_xu.sum"][0].replace(",", "")) if "sm__inst_executed_pipe_xu.sum" in vals else None,
         "sm__inst_executed_pipe_alu": float(vals["sm__inst_executed_pipe_alu.sum"][0].replace(",", "")) if "sm__inst_executed_pipe_alu.sum" in vals else None,
         "sm__inst_executed_pipe_fma": float(vals["sm__inst_executed_pipe_fma.sum"][0].replace(",", "")) if "sm__inst_executed_pipe_fma.sum" in vals else None,
     }
-    os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
-    with open(os.path.join(ROOT, "profiles", "%s_production_kernel.json" % tag), "w") as f:
+    outdir = os.environ.get("MCZ_PROFILE_DIR") or os.path.join(ROOT, "profiles")      # (on the GPU box: under gpurun_out/)
+    os.makedirs(outdir, exist_ok=True)
+    with open(os.path.join(outdir, "%s_production_kernel.json" % tag), "w") as f:
         json.dump(out, f, indent=1)
-    with open(os.path.join(ROOT, "profiles", "%s_production_kernel.txt" % tag), "w") as f:
+    with open(os.path.join(outdir, "%s_production_kernel.txt" % tag), "w") as f:
         f.write("ncu --set full --clock-control none, one launch of %s over %s galaxies x %d samples\n" % (out["kernel"], galaxies, n_draw))
         for k in WANT:
             if k in vals:
@@ -81,7 +83,7 @@ def main(rep, galaxies, tag, n_draw=2200, md="all", kernel_base=None):
     tmp = os.path.join("/tmp", "ncu_src_%s.csv" % tag)
     open(tmp, "w").write(src)
     hot = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), tmp, "40"], capture_output=True, text=True).stdout
-    with open(os.path.join(ROOT, "profiles", "%s_source_hotspots.txt" % tag), "w") as f:
+    with open(os.path.join(outdir, "%s_source_hotspots.txt" % tag), "w") as f:
         f.write("per source file / line: share of warp-instructions executed and of warp-stall samples (ncu source page)\n")
         f.write(hot)
     print(json.dumps(out, indent=1))
