@@ -111,10 +111,13 @@ def check_example_file():
         assert np.array_equal(raw[:, 1:], arr, equal_nan=True), name
 
 
-def run_case(meas, err, nsample, seed, mode, mds, dust_corr, reset_ignoredust=True):
-    """Per-sample golden: reference run over a table with seeded legacy numpy RNG."""
+def run_case(meas, err, nsample, seed, mode, mds, dust_corr, reset_ignoredust=True, dropnegatives=False):
+    """Per-sample golden: reference run over a table with seeded legacy numpy RNG.
+    dropnegatives: the reference's module switch DROPNEGATIVES (metallicity.py:23-26) for this case."""
     if reset_ignoredust:
         ref_met.IGNOREDUST = False
+    ref_met.DROPNEGATIVES = bool(dropnegatives)
+    ref_met.FIXNEGATIVES = not dropnegatives                               # metallicity.py:25-26
     np.random.seed(seed)
     G = meas.shape[0]
     samples = orc.draw_samples(G, nsample)
@@ -129,6 +132,7 @@ def run_case(meas, err, nsample, seed, mode, mds, dust_corr, reset_ignoredust=Tr
         present[g], Z[g] = pack(m, n)
         rets[g] = -1 if ret == -1 else 0
         trips[g] = tr
+    ref_met.DROPNEGATIVES, ref_met.FIXNEGATIVES = False, True
     return dict(meas=meas, err=err, nsample=nsample, seed=seed, mode=mode, mds=mds,
                 dust_corr=dust_corr, present=present, Z=Z, ret=rets, trips=trips)
 
@@ -222,6 +226,12 @@ def main(outdir):
     save("missing_lines_n50", merged)
     # ... and the first two rows in one run, so the sticky global (metallicity.py:127) is pinned too
     save("missing_lines_sticky_n50", run_case(rows_m[:3], rows_e[:3], 50, 320, "correlated", "all", True))
+
+    # F2: DROPNEGATIVES = True (metallicity.py:23-26): negative samples become NaN instead of 0 -- the
+    # low-SNR row, the negative-[NII] row and exampledata row 1, P10 left out (ragged arrays, see above)
+    save("dropneg_n60", run_case(np.concatenate([rows_m[10:12], EXAMPLE_MEAS[:1]]),
+                                 np.concatenate([rows_e[10:12], EXAMPLE_ERR[:1]]), 60, 330, "shuffled",
+                                 NOP10, True, dropnegatives=True))
 
     # G: percentile strings from the reference's own savehist
     save("pct_example_n2000", run_pct_case(EXAMPLE_MEAS, EXAMPLE_ERR, 2000, 2000, "correlated", "all", True))

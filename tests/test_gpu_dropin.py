@@ -85,6 +85,45 @@ def test_calculation_matches_oracle_same_seed(mds, dust):
                         assert np.all(np.abs(got - real) <= tol), (g, i, got, real)
 
 
+def test_calculation_dropnegatives_switch():
+    """metallicity.DROPNEGATIVES = True (reference metallicity.py:23-26, 101-102): calculation() turns the
+    negative samples of the caller's arrays into NaN and the scales are NaN for those samples."""
+    n = 400
+    meas, err = EX_M[0].copy(), EX_E[0].copy()
+    err[:] = np.where(np.isnan(meas), 0.0, np.abs(meas) * 0.6)            # SNR 1.7: many negative samples
+    np.random.seed(7)
+    sample = np.random.normal(0, 1, n)
+    mds = "D02,Z94,M91,PP04,M08,M13,KD02"
+    old = metallicity.DROPNEGATIVES
+    try:
+        metallicity.DROPNEGATIVES = True
+        metallicity.IGNOREDUST = False
+        fluxi = measured_dict(meas, err, sample)
+        neg = {k: v < 0 for k, v in fluxi.items()}
+        scales = ms.diagnostics(n, io.StringIO(), 2)
+        state = np.random.get_state()
+        metallicity.calculation(scales, fluxi, 1, mds, 2, io.StringIO(), dust_corr=True)
+        for k in ("Ha", "Hb", "[NII]6584", "[OII]3727"):
+            assert neg[k].any() and np.all(np.isnan(fluxi[k][neg[k]]))    # dropped in place, like the reference
+        np.random.set_state(state)
+        flux = np.array([meas[j] * np.ones(n) + err[j] * sample for j in range(11)])
+        d, _, _ = orc.calculation(flux, mds, True, False, "batched", dropnegatives=True)
+        assert scales.trips == (d.trips_n2ha, d.trips_r23)
+        for k in sc.KEYS:
+            a, b = scales.mds[k], d.mds[k]
+            assert (a is None) == (b is None), k
+            if a is None:
+                continue
+            assert np.array_equal(np.isnan(a), np.isnan(b)), k
+            fin = np.isfinite(b)
+            if fin.any():
+                assert np.max(np.abs(a[fin] - b[fin])) < 1e-8, k
+        assert np.isnan(scales.mds["E(B-V)"][neg["Ha"] | neg["Hb"]]).all()
+    finally:
+        metallicity.DROPNEGATIVES = old
+        metallicity.IGNOREDUST = False
+
+
 def test_calculation_log_lines_and_warnings():
     """The log the reference's calculation() writes when nps == 1 (printsafemulti, metallicity.py:71-78):
     "calculating X" per scale in dispatch order, and the KD02 / KK04 applicability warning of calcNIIOII

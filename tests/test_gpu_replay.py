@@ -112,6 +112,80 @@ def test_replay_golden_fixtures_from_reference(golden_dir):
     assert np.max(np.abs(Z[fin] - g["Z"][fin])) < 1e-8
 
 
+def test_replay_dropnegatives(golden_dir):
+    """DROPNEGATIVES (metallicity.py:23-26) as the T_DROPNEG flag of the token mask: the replay kernel on
+    the reference's own samples against the reference's outputs with the switch on; and production
+    mode against the oracle on the kernel's own samples."""
+    g = np.load(os.path.join(golden_dir, "dropneg_n60.npz"))
+    meas, err, mds = g["meas"], g["err"], str(g["mds"])
+    tok, _, _ = sc.parse_md(mds)
+    assert "D02" in mds.split(",") and "M13" in mds.split(",")
+    # the reference's stream: samples, then per galaxy the shuffles of perturb() and the coefficient
+    # noise of calculation(), interleaved -- replayed through the oracle with a recording normal()
+    np.random.seed(int(g["seed"]))
+    samples = orc.draw_samples(meas.shape[0], int(g["nsample"]))
+    n = len(samples[0])
+    flux = np.zeros((11, meas.shape[0], n))
+    noise = np.zeros((5, meas.shape[0], n))
+    Zo = np.zeros((meas.shape[0], sc.NKEYS, n))
+    for i in range(meas.shape[0]):
+        flux[:, i] = orc.perturb(meas[i], err[i], samples[i], str(g["mode"]))
+        rec = []
+
+        def normal(loc, scale, size, rec=rec):
+            v = np.random.normal(loc, scale, size)
+            rec.append((scale, v))
+            return v
+        d, ret, _ = orc.calculation(flux[:, i].copy(), mds, True, False, "batched", normal, dropnegatives=True)
+        rows = {0.05: 0, 0.1: 1, 0.027: 2, 0.024: 3}
+        seen12 = 0
+        for scale, v in rec:
+            if scale in rows:
+                noise[rows[scale], i] = v
+            elif seen12 == 0:
+                noise[4, i] = v
+                seen12 = 1
+        for j, k in enumerate(orc.KEYS):
+            Zo[i, j] = d.mds[k] if d.mds[k] is not None else np.nan
+    assert np.array_equal(Zo, g["Z"], equal_nan=True)            # oracle == reference on this fixture
+    Z, present, trips, ret = ops.forward_replay(torch.from_numpy(flux).cuda(), torch.from_numpy(noise).cuda(),
+                                                tok | sc.T_DROPNEG, sc.DUST_ON, "f64")
+    torch.cuda.synchronize()
+    Z = Z.cpu().numpy()
+    assert np.array_equal(ops.present_to_bool(present).cpu().numpy(), g["present"])
+    assert np.array_equal(trips.cpu().numpy(), g["trips"])
+    assert np.array_equal(np.isnan(Z), np.isnan(g["Z"]))
+    fin = np.isfinite(g["Z"])
+    assert np.max(np.abs(Z[fin] - g["Z"][fin])) < 1e-8
+    # without the flag the same samples give other masks (the negatives are zeroed, not dropped)
+    Z0 = ops.forward_replay(torch.from_numpy(flux).cuda(), torch.from_numpy(noise).cuda(), tok, sc.DUST_ON, "f64")[0]
+    assert not np.array_equal(np.isnan(Z0.cpu().numpy()), np.isnan(g["Z"]))
+
+    # production mode: the kernel's own Philox samples, the sampler's export carries the NaNs
+    from tests._helpers import kernel_samples, oracle_on_samples
+    seed, goff, N = 77, 3, 600
+    out = ops.forward_production(torch.from_numpy(meas).cuda(), torch.from_numpy(err).cuda(), N, tok | sc.T_DROPNEG,
+                                 sc.DUST_ON, seed, goff, False, False, True)
+    torch.cuda.synchronize()
+    Zp = out[5].cpu().numpy()
+    fl, nz = kernel_samples(meas, err, N, seed, goff, tok | sc.T_DROPNEG)
+    assert np.isnan(fl[:, [0, 1, 3, 5, 6, 7, 8]]).any()          # dropped samples are there
+    fl0 = np.where(np.isnan(fl), -1.0, fl)                       # the oracle drops them itself
+    Zo2 = np.full(Zp.shape, np.nan)
+    for i in range(meas.shape[0]):
+        from tests._helpers import FixedNoise
+        d, _, _ = orc.calculation(fl0[i].copy(), mds, True, False, "batched", FixedNoise(nz[i]), dropnegatives=True)
+        for j, k in enumerate(orc.KEYS):
+            if d.mds[k] is not None:
+                Zo2[i, j] = d.mds[k]
+    it = [sc.KEY_INDEX[k] for k in ("KK04_N2Ha", "KK04_R23", "KD02comb")]
+    rest = [j for j in range(sc.NKEYS) if j not in it]
+    flips = np.isnan(Zp[:, rest]) != np.isnan(Zo2[:, rest])
+    assert flips.sum() <= 2, flips.sum()
+    both = np.isfinite(Zp[:, rest]) & np.isfinite(Zo2[:, rest])
+    assert np.max(np.abs(Zp[:, rest][both] - Zo2[:, rest][both])) < 1e-3
+
+
 def test_replay_missing_lines(golden_dir):
     g = np.load(os.path.join(golden_dir, "missing_lines_n50.npz"))
     for i in range(g["meas"].shape[0]):

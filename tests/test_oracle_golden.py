@@ -21,7 +21,7 @@ def _load(golden_dir, name):
     return {k: z[k] for k in z.files}
 
 
-def _replay(meas, err, nsample, seed, mode, mds, dust_corr, roots_mode):
+def _replay(meas, err, nsample, seed, mode, mds, dust_corr, roots_mode, dropnegatives=False):
     np.random.seed(int(seed))
     G = meas.shape[0]
     samples = orc.draw_samples(G, int(nsample))
@@ -33,7 +33,7 @@ def _replay(meas, err, nsample, seed, mode, mds, dust_corr, roots_mode):
     ign = False
     for g in range(G):
         flux = orc.perturb(meas[g], err[g], samples[g], str(mode))
-        d, ret, ign = orc.calculation(flux, str(mds), bool(dust_corr), ign, roots_mode)
+        d, ret, ign = orc.calculation(flux, str(mds), bool(dust_corr), ign, roots_mode, dropnegatives=dropnegatives)
         rets[g] = -1 if ret == -1 else 0
         trips[g] = (d.trips_n2ha, d.trips_r23)
         for j, k in enumerate(orc.KEYS):
@@ -55,6 +55,22 @@ def test_oracle_matches_reference_bit_exact(golden_dir, name, roots_mode):
     assert np.array_equal(np.isnan(Z), np.isnan(g["Z"]))
     # bit-exact, not allclose: same numpy ops in the same order
     assert np.array_equal(Z, g["Z"], equal_nan=True)
+
+
+@pytest.mark.parametrize("roots_mode", ["loop", "batched"])
+def test_oracle_dropnegatives_matches_reference(golden_dir, roots_mode):
+    """The reference run with its module switch DROPNEGATIVES = True (metallicity.py:23-26): negative
+    flux samples become NaN instead of 0 (low-SNR row, negative-[NII] row, exampledata row 1)."""
+    g = _load(golden_dir, "dropneg_n60")
+    present, Z, rets, trips = _replay(g["meas"], g["err"], g["nsample"], g["seed"], g["mode"],
+                                      g["mds"], g["dust_corr"], roots_mode, dropnegatives=True)
+    assert np.array_equal(present, g["present"])
+    assert np.array_equal(rets, g["ret"])
+    assert np.array_equal(trips, g["trips"])
+    assert np.array_equal(Z, g["Z"], equal_nan=True)
+    # and the switch matters on these rows: with FIXNEGATIVES the masks differ
+    _, Z0, _, _ = _replay(g["meas"], g["err"], g["nsample"], g["seed"], g["mode"], g["mds"], g["dust_corr"], roots_mode)
+    assert not np.array_equal(np.isnan(Z0), np.isnan(g["Z"]))
 
 
 def test_oracle_missing_lines_rows(golden_dir):

@@ -1,13 +1,17 @@
 set -x
-mkdir -p gpurun_out
-# launch list of the default bench command (after it has exited 0 without ncu)
+mkdir -p gpurun_out/profiles_r2
+export MCZ_PROFILE_DIR=gpurun_out/profiles_r2
+export MCZ_COMMIT=f975dae
+cap() {  # tag config galaxies n_draw md kernel_base [extra env]
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:production_kernel -s 1 -c 1 -f -o /tmp/prof_$1 python tools/prof_bench_shape.py $2 $3 > gpurun_out/prof_ncu_$1.log 2>&1
+  python tools/ncu_summary.py /tmp/prof_$1.ncu-rep $3 $1 $4 $5 "$6" > /dev/null 2>> gpurun_out/prof_ncu_$1.log
+  rm -f /tmp/prof_$1.ncu-rep
+}
 timeout 600 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/prof_plain.log 2>&1 || exit 1
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r2.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_l_r2.log 2>&1
-# one ncu --set full capture per bench launch shape (second launch of each)
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:production_kernel -s 1 -c 1 -f -o gpurun_out/prof_r2_cfg4 python tools/prof_bench_shape.py 4 > gpurun_out/prof_ncu4.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:production_kernel -s 1 -c 1 -f -o gpurun_out/prof_r2_cfg3 python tools/prof_bench_shape.py 3 > gpurun_out/prof_ncu3.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:production_kernel -s 1 -c 1 -f -o gpurun_out/prof_r2_cfg5 python tools/prof_bench_shape.py 5 > gpurun_out/prof_ncu5.log 2>&1
-MCZ_CLUSTER=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:production_kernel -s 1 -c 1 -f -o gpurun_out/prof_r2_cluster python tools/prof_bench_shape.py 3 2000 > gpurun_out/prof_ncuc.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:wide_kernel -s 1 -c 1 -f -o gpurun_out/prof_r2_wide python tools/prof_other.py wide > gpurun_out/prof_ncuw.log 2>&1
-ls -la gpurun_out/*.ncu-rep
+cap r2_cfg4 4 1000000 2200 all "production_kernel<4,0>"
+cap r2_cfg3 3 10000 11000 all "production_kernel<0,0>"
+cap r2_cfg5 5 100000 11000 KD02 "production_kernel<0,0>"
+MCZ_CLUSTER=1 cap r2_cluster 3 2000 11000 all "production_kernel<4,0,cluster>"
+ls -la gpurun_out/profiles_r2
 echo done
