@@ -19,8 +19,11 @@ WANT = [
     "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
     "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
     "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
-    "sm__inst_executed_pipe_xu.sum", "sm__inst_executed_pipe_fma.sum", "sm__inst_executed_pipe_alu.sum",
-    "sm__inst_executed_pipe_lsu.sum", "sm__inst_executed_pipe_fp64.sum",
+    # per-pipe instruction issue, % of the pipe's peak while the SM is active (the XU pipe is the SFU: MUFU)
+    "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_adu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active",
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
     "smsp__warp_issue_stalled_barrier_per_warp_active.pct", "smsp__warp_issue_stalled_short_scoreboard_per_warp_active.pct",
     "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct", "smsp__warp_issue_stalled_mio_throttle_per_warp_active.pct",
@@ -61,9 +64,8 @@ def main(rep, galaxies, tag, n_draw=2200, md="all", kernel_base=None):
         "kernel_base": kernel_base, "md": md,
         "commit": os.environ.get("MCZ_COMMIT") or subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"],
                                                                   capture_output=True, text=True).stdout.strip(),
-        "sm__inst_executed_pipe_xu": float(vals["sm__inst_executed_pipe_xu.sum"][0].replace(",", "")) if "sm__inst_executed_pipe_xu.sum" in vals else None,
-        "sm__inst_executed_pipe_alu": float(vals["sm__inst_executed_pipe_alu.sum"][0].replace(",", "")) if "sm__inst_executed_pipe_alu.sum" in vals else None,
-        "sm__inst_executed_pipe_fma": float(vals["sm__inst_executed_pipe_fma.sum"][0].replace(",", "")) if "sm__inst_executed_pipe_fma.sum" in vals else None,
+        "pipe_pct_of_peak_active": {k.split("pipe_")[1].split(".")[0]: float(vals[k][0].replace(",", ""))
+                                    for k in vals if k.startswith("sm__inst_executed_pipe_") and k.endswith("sustained_active")},
     }
     outdir = os.environ.get("MCZ_PROFILE_DIR") or os.path.join(ROOT, "profiles")      # (on the GPU box: under gpurun_out/)
     os.makedirs(outdir, exist_ok=True)
