@@ -262,6 +262,10 @@ static constexpr int A_UNROLL = MCZ_A_UNROLL;     // samples of a thread evaluat
 #ifndef MCZ_BSM_UNROLL
 #define MCZ_BSM_UNROLL 2
 #endif
+#ifndef MCZ_BSM_TRIPS
+#define MCZ_BSM_TRIPS 2
+#endif
+static constexpr int BSM_TRIPS = MCZ_BSM_TRIPS;     // trips per block-wide reduction in the shared-memory KK04 loop (2 or 3)
 static constexpr int BSM_UNROLL = MCZ_BSM_UNROLL;   // samples of a thread evaluated side by side in the shared-memory KK04 loop
 #ifndef MCZ_FX_BITS
 #define MCZ_FX_BITS 20
@@ -910,8 +914,6 @@ production_kernel(const __grid_constant__ ProdParams p) {
         float* sQ1 = st2 + Nq;
         float* sQ2 = sQ1 + Nq;
         unsigned* sLow = reinterpret_cast<unsigned*>(sQ2 + Nq);
-        float* Fa1 = giter + 4ll * Npad;          // fields 14, 15 of the scratch: logq after the first trip
-        float* Fa2 = giter + 5ll * Npad;
         auto consts = [&](int s, IterState<float>& st) {
           Carry<float> c;
           c.y = st0[s]; c.n2ha = st1[s]; c.x = st2[s];
@@ -947,9 +949,20 @@ production_kernel(const __grid_constant__ ProdParams p) {
         }
         const bool ran1 = act1, ran2 = act2;
         bool first = true;
+        // BT trips per batch: the ~45 instructions that load a sample and rebuild its constants are paid
+        // once per batch, so three trips per batch cost less per trip than two; logq after each but
+        // the last trip of the batch goes to the global scratch (fields 10.. of the loop-state area,
+        // write-only unless a loop turns out to have ended there), and the reference's loop tests are
+        // replayed trip by trip on the BT sums.
+        constexpr int BT = BSM_TRIPS;
+        static_assert(BT >= 2 && BT <= 3, "two global arrays per loop are reserved");
+        float* Fl1 = giter;                        // [BT - 1][Npad]: N2Ha loop, logq after trips 1 .. BT-1 of the batch
+        float* Fl2 = giter + 2ll * Npad;           // same for the R23 loop
         while (act1 || act2) {
-          float sm4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-          unsigned nanb = 0u;
+          float sm1[BT], sm2[BT];
+#pragma unroll
+          for (int t = 0; t < BT; ++t) { sm1[t] = 0.0f; sm2[t] = 0.0f; }
+          unsigned nanb = 0u;                      // bit t: N2Ha trip t of the batch saw a NaN; bit BT + t: R23
 #pragma unroll BSM_UNROLL
           for (int s = tid; s < N; s += PT) {
             IterState<float> k;                       // only the constants of the loops still running
@@ -959,19 +972,18 @@ production_kernel(const __grid_constant__ ProdParams p) {
               iter_n2ha<float>(st1[s], k);
               const float cA = k.A, cB = k.B;
               const float q = sQ1[s];
-              const float Z1 = first ? q : cA - q * cB;
-              const float lq1 = first ? 0.0f : q;                                         // logq_save (:1106)
-              const float lq = (num0 + Z1 * num1) * fast_rcp(den0 + Z1 * den1);          // metscales.py:1112-1118
-              const float z = cA - lq * cB;
-              float d = fabsf(lq - lq1);
-              nanb |= (d != d) ? 1u : 0u;
-              sm4[0] += d;
-              const float lqb = (num0 + z * num1) * fast_rcp(den0 + z * den1);
-              d = fabsf(lqb - lq);
-              nanb |= (d != d) ? 2u : 0u;
-              sm4[1] += d;
-              sQ1[s] = lqb;
-              Fa1[s] = lq;
+              float Z = first ? q : cA - q * cB;
+              float lqp = first ? 0.0f : q;                                               // logq_save (:1106)
+#pragma unroll
+              for (int t = 0; t < BT; ++t) {
+                const float lq = (num0 + Z * num1) * fast_rcp(den0 + Z * den1);          // metscales.py:1112-1118
+                const float d = fabsf(lq - lqp);
+                nanb |= (d != d) ? (1u << t) : 0u;
+                sm1[t] += d;
+                if (t < BT - 1) { Fl1[(long long)t * Npad + s] = lq; Z = cA - lq * cB; }
+                lqp = lq;
+              }
+              sQ1[s] = lqp;
             }
             if (act2) {
               iter_r23<float>(st2[s], k);
@@ -979,48 +991,65 @@ production_kernel(const __grid_constant__ ProdParams p) {
               const bool lowz = (sLow[s >> 5] >> (s & 31)) & 1u;
               const float q = sQ2[s];
               bool lower = lowz && (q >= 6.7f) && (q < 8.3f);
-              const float Z2 = first ? q : (lower ? l0 : u0) - q * (lower ? l1 : u1);
-              const float lq2 = first ? 100.0f : q;                                       // logqold (:1163)
-              const float lq = (num0 + Z2 * num1) * fast_rcp(den0 + Z2 * den1);          // metscales.py:1167-1178
-              lower = lowz && (lq >= 6.7f) && (lq < 8.3f);
-              const float z = (lower ? l0 : u0) - lq * (lower ? l1 : u1);
-              float d = lq2 - lq;
-              nanb |= (d != d) ? 4u : 0u;
-              sm4[2] += d;
-              const float lqb = (num0 + z * num1) * fast_rcp(den0 + z * den1);
-              d = lq - lqb;
-              nanb |= (d != d) ? 8u : 0u;
-              sm4[3] += d;
-              sQ2[s] = lqb;
-              Fa2[s] = lq;
+              float Z = first ? q : (lower ? l0 : u0) - q * (lower ? l1 : u1);
+              float lqp = first ? 100.0f : q;                                             // logqold (:1163)
+#pragma unroll
+              for (int t = 0; t < BT; ++t) {
+                const float lq = (num0 + Z * num1) * fast_rcp(den0 + Z * den1);          // metscales.py:1167-1178
+                const float d = lqp - lq;
+                nanb |= (d != d) ? (1u << (BT + t)) : 0u;
+                sm2[t] += d;
+                if (t < BT - 1) {
+                  Fl2[(long long)t * Npad + s] = lq;
+                  lower = lowz && (lq >= 6.7f) && (lq < 8.3f);
+                  Z = (lower ? l0 : u0) - lq * (lower ? l1 : u1);
+                }
+                lqp = lq;
+              }
+              sQ2[s] = lqp;
             }
           }
           first = false;
-          block_sum2f(sm4[0], sm4[1], ctrl->redf, phase);
-          block_sum2f(sm4[2], sm4[3], ctrl->redf, phase);
+          // block sums, two at a time (one barrier per call); NaN flags by vote
+          {
+            float flat[2 * BT + 1];
+#pragma unroll
+            for (int t = 0; t < BT; ++t) { flat[t] = sm1[t]; flat[BT + t] = sm2[t]; }
+            flat[2 * BT] = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 2 * BT; i += 2) block_sum2f(flat[i], flat[i + 1], ctrl->redf, phase);
+#pragma unroll
+            for (int t = 0; t < BT; ++t) { sm1[t] = flat[t]; sm2[t] = flat[BT + t]; }
+          }
           unsigned nb = 0u;
           if (__syncthreads_or(nanb != 0u)) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) nb |= __syncthreads_or((nanb >> k) & 1u) ? (1u << k) : 0u;
+            for (int k = 0; k < 2 * BT; ++k) nb |= __syncthreads_or((nanb >> k) & 1u) ? (1u << k) : 0u;
           }
           if (act1) {                                                     // metscales.py:1111,1117
-            ++ii1;
-            if ((nb & 1u) || !(sm4[0] > tol1) || ii1 >= 100) {
-              act1 = false;       // ended after the first trip of the pair: put that logq back
-              for (int s = tid; s < N; s += PT) sQ1[s] = Fa1[s];
-            } else {
-              ++ii1;
-              act1 = !(nb & 2u) && (sm4[1] > tol1) && ii1 < 100;
+#pragma unroll
+            for (int t = 0; t < BT; ++t) {
+              if (act1) {
+                ++ii1;
+                if ((nb & (1u << t)) || !(sm1[t] > tol1) || ii1 >= 100) {
+                  act1 = false;
+                  if (t < BT - 1)     // ended before the last trip of the batch: put that logq back
+                    for (int s = tid; s < N; s += PT) sQ1[s] = Fl1[(long long)t * Npad + s];
+                }
+              }
             }
           }
           if (act2) {                                                     // metscales.py:1166,1177
-            ++ii2;
-            if ((nb & 4u) || !(fabsf(sm4[2]) > tol2) || ii2 >= 100) {
-              act2 = false;
-              for (int s = tid; s < N; s += PT) sQ2[s] = Fa2[s];
-            } else {
-              ++ii2;
-              act2 = !(nb & 8u) && (fabsf(sm4[3]) > tol2) && ii2 < 100;
+#pragma unroll
+            for (int t = 0; t < BT; ++t) {
+              if (act2) {
+                ++ii2;
+                if ((nb & (1u << (BT + t))) || !(fabsf(sm2[t]) > tol2) || ii2 >= 100) {
+                  act2 = false;
+                  if (t < BT - 1)
+                    for (int s = tid; s < N; s += PT) sQ2[s] = Fl2[(long long)t * Npad + s];
+                }
+              }
             }
           }
           if (act1 && ii1 == DIVERGENCE_CHECK_TRIP) {
