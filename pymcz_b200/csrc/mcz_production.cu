@@ -1840,13 +1840,22 @@ wide_kernel(const __grid_constant__ ProdParams p) {
   float* F = st3 + Npad;                                   // fields 0..5: Z1, Z2, lq1, lq2, lq1a, lq2a
   const int used2line[NUSED] = {L_HA, L_HB, L_O2, L_O3, L_N2, L_S2A, L_S2B, L_S39069};
 
+  // (-DMCZ_PHASE_TIMING: cycles of block 0 between the grid barriers, summed into g_phase_cycles[1..7])
+#ifdef MCZ_PHASE_TIMING
+  long long wt_ = clock64();
+#define WT(i) do { const long long n_ = clock64(); if (b == 0 && tid == 0) atomicAdd(&g_phase_cycles[i], (unsigned long long)(n_ - wt_)); wt_ = n_; } while (0)
+#else
+#define WT(i)
+#endif
   for (long long g = 0; g < p.G; ++g) {
+    if (b == 0 && tid == 0) { MCZ_TADD(0, 1); }
     // ---- reset the control block and the merged histograms ------------------------------------
     if (b == 0) {
       for (int i = tid; i < (int)(sizeof(WideCtl) / 4); i += PT) reinterpret_cast<unsigned*>(ctl)[i] = 0u;
     }
     for (long long i = (long long)b * PT + tid; i < 4ll * p.nstore * 6 * 256; i += (long long)nb * PT) ghist[i] = 0u;
     xsync();
+    WT(1);   // reset
     float lm[NUSED], le[NUSED];
     uint32_t assumed = 0u;
 #pragma unroll
@@ -1896,6 +1905,7 @@ wide_kernel(const __grid_constant__ ProdParams p) {
       if (lane == 0 && seen)
         for (int q = 0; q < W; ++q) atomicOr_system(reinterpret_cast<unsigned*>(peer(&ctl->flags, q)), seen);
       xsync();
+      WT(2);   // phase A
       const uint32_t all = *reinterpret_cast<volatile unsigned*>(&ctl->flags);
       const uint32_t actual = all & F_ALL;
       anykd = (all & SEEN_KD) != 0u;
@@ -1952,6 +1962,7 @@ wide_kernel(const __grid_constant__ ProdParams p) {
         if (b == 0 && tid < 4) ctl->sums[nx][tid] = 0;
         if (b == 0 && tid == 4) ctl->nan[nx] = 0u;
         xsync();
+        WT(3);   // KK04 batches
 #pragma unroll
         for (int k = 0; k < 4; ++k) t4[k] = *reinterpret_cast<volatile long long*>(&ctl->sums[ph][k]);
         nb = *reinterpret_cast<volatile unsigned*>(&ctl->nan[ph]);
@@ -1960,44 +1971,65 @@ wide_kernel(const __grid_constant__ ProdParams p) {
       while (act1 || act2) {
         long long sm4[4] = {0, 0, 0, 0};
         unsigned nanb = 0u;
-        for (int s = s_lo + tid; s < s_hi && s < N; s += PT) {
-          IterState<float> k;                         // only the constants of the loops still running
-          iter_logq<float>(st0[s], k);
-          if (act1) iter_n2ha<float>(st1[s], k);
-          if (act2) { iter_r23<float>(st2[s], k); k.aux = __float_as_uint(st3[s]); }
-          const float num0 = k.num0, num1 = k.num1, den0 = k.den0, den1 = k.den1;
-          if (act1) {
-            const float Z1 = F[0ll * Npad + s], lq1 = F[2ll * Npad + s];
-            const float lq = (num0 + Z1 * num1) * fast_rcp(den0 + Z1 * den1);
-            const float z = k.A - lq * k.B;
-            float d = fabsf(lq - lq1);
-            nanb |= (d != d) ? 1u : 0u;
-            sm4[0] += wfx(fminf(d, 8.0f));
-            const float lqb = (num0 + z * num1) * fast_rcp(den0 + z * den1);
-            d = fabsf(lqb - lq);
-            nanb |= (d != d) ? 2u : 0u;
-            sm4[1] += wfx(fminf(d, 8.0f));
-            F[0ll * Npad + s] = k.A - lqb * k.B;
-            F[2ll * Npad + s] = lqb;
-            F[4ll * Npad + s] = lq;
+        // two samples of the thread per iteration, all sixteen loads first: the state comes from global
+        // memory (L2 at best) and one sample's loads in flight per thread leave the pass latency-bound
+        for (int s = s_lo + tid; s < s_hi && s < N; s += 2 * PT) {
+          const bool two = s + PT < s_hi && s + PT < N;
+          const int sx[2] = {s, two ? s + PT : s};
+          float c0[2], c1[2], c2[2], c3[2], vZ1[2], vq1[2], vZ2[2], vq2[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            c0[u] = st0[sx[u]];
+            c1[u] = act1 ? st1[sx[u]] : 0.0f;
+            vZ1[u] = act1 ? F[0ll * Npad + sx[u]] : 0.0f;
+            vq1[u] = act1 ? F[2ll * Npad + sx[u]] : 0.0f;
+            c2[u] = act2 ? st2[sx[u]] : 0.0f;
+            c3[u] = act2 ? st3[sx[u]] : 0.0f;
+            vZ2[u] = act2 ? F[1ll * Npad + sx[u]] : 0.0f;
+            vq2[u] = act2 ? F[3ll * Npad + sx[u]] : 0.0f;
           }
-          if (act2) {
-            const float Z2 = F[1ll * Npad + s], lq2 = F[3ll * Npad + s];
-            const bool lowz = (k.aux & AUX_ZI_MASK) <= 1u;
-            const float lq = (num0 + Z2 * num1) * fast_rcp(den0 + Z2 * den1);
-            bool lower = lowz && (lq >= 6.7f) && (lq < 8.3f);
-            const float z = (lower ? k.L0 : k.U0) - lq * (lower ? k.L1 : k.U1);
-            float d = lq2 - lq;
-            nanb |= (d != d) ? 4u : 0u;
-            sm4[2] += wfx(fminf(fmaxf(d, -8.0f), 8.0f));
-            const float lqb = (num0 + z * num1) * fast_rcp(den0 + z * den1);
-            lower = lowz && (lqb >= 6.7f) && (lqb < 8.3f);
-            d = lq - lqb;
-            nanb |= (d != d) ? 8u : 0u;
-            sm4[3] += wfx(fminf(fmaxf(d, -8.0f), 8.0f));
-            F[1ll * Npad + s] = (lower ? k.L0 : k.U0) - lqb * (lower ? k.L1 : k.U1);
-            F[3ll * Npad + s] = lqb;
-            F[5ll * Npad + s] = lq;
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            if (u == 1 && !two) continue;
+            const int sq = sx[u];
+            IterState<float> k;                         // only the constants of the loops still running
+            iter_logq<float>(c0[u], k);
+            if (act1) iter_n2ha<float>(c1[u], k);
+            if (act2) { iter_r23<float>(c2[u], k); k.aux = __float_as_uint(c3[u]); }
+            const float num0 = k.num0, num1 = k.num1, den0 = k.den0, den1 = k.den1;
+            if (act1) {
+              const float Z1 = vZ1[u], lq1 = vq1[u];
+              const float lq = (num0 + Z1 * num1) * fast_rcp(den0 + Z1 * den1);
+              const float z = k.A - lq * k.B;
+              float d = fabsf(lq - lq1);
+              nanb |= (d != d) ? 1u : 0u;
+              sm4[0] += wfx(fminf(d, 8.0f));
+              const float lqb = (num0 + z * num1) * fast_rcp(den0 + z * den1);
+              d = fabsf(lqb - lq);
+              nanb |= (d != d) ? 2u : 0u;
+              sm4[1] += wfx(fminf(d, 8.0f));
+              F[0ll * Npad + sq] = k.A - lqb * k.B;
+              F[2ll * Npad + sq] = lqb;
+              F[4ll * Npad + sq] = lq;
+            }
+            if (act2) {
+              const float Z2 = vZ2[u], lq2 = vq2[u];
+              const bool lowz = (k.aux & AUX_ZI_MASK) <= 1u;
+              const float lq = (num0 + Z2 * num1) * fast_rcp(den0 + Z2 * den1);
+              bool lower = lowz && (lq >= 6.7f) && (lq < 8.3f);
+              const float z = (lower ? k.L0 : k.U0) - lq * (lower ? k.L1 : k.U1);
+              float d = lq2 - lq;
+              nanb |= (d != d) ? 4u : 0u;
+              sm4[2] += wfx(fminf(fmaxf(d, -8.0f), 8.0f));
+              const float lqb = (num0 + z * num1) * fast_rcp(den0 + z * den1);
+              lower = lowz && (lqb >= 6.7f) && (lqb < 8.3f);
+              d = lq - lqb;
+              nanb |= (d != d) ? 8u : 0u;
+              sm4[3] += wfx(fminf(fmaxf(d, -8.0f), 8.0f));
+              F[1ll * Npad + sq] = (lower ? k.L0 : k.U0) - lqb * (lower ? k.L1 : k.U1);
+              F[3ll * Npad + sq] = lqb;
+              F[5ll * Npad + sq] = lq;
+            }
           }
         }
         long long t4[4];
@@ -2069,6 +2101,7 @@ wide_kernel(const __grid_constant__ ProdParams p) {
       }
     }
     grid.sync();          // all columns final
+    WT(4);   // phase C
     if (p.Z) {            // optional per-sample output (pickle / --asciidistrib path): this block's slice
       for (int k = 0; k < NKEYS; ++k) {
         const int sl = p.slot_of_key[k];
@@ -2127,14 +2160,23 @@ wide_kernel(const __grid_constant__ ProdParams p) {
       const int sl = warp + h * PW;
       const float* col = vals + (long long)sl * Npad;
       unsigned lmax = 0u, lnmin = 0u;
-      for (int g0 = g_lo; g0 < g_hi; ++g0) {
-        const float4 x4 = *reinterpret_cast<const float4*>(col + 4 * lane + 128 * g0);
-        const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+      // (four 128-bit loads per lane in flight: with one, the 17 warps of a block keep 8.7 KB in flight per
+      // SM and the pass is bound by memory latency, not bandwidth)
+      for (int g0 = g_lo; g0 < g_hi; g0 += 4) {
+        float4 x4[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const unsigned u = finite_f(xs[j]) ? ordered_bits(xs[j]) : 0u;
-          lmax = max(lmax, u);
-          lnmin = max(lnmin, u ? ~u : 0u);
+        for (int q = 0; q < 4; ++q)
+          x4[q] = g0 + q < g_hi ? *reinterpret_cast<const float4*>(col + 4 * lane + 128 * (g0 + q))
+                                : make_float4(Math<float>::nan(), Math<float>::nan(), Math<float>::nan(), Math<float>::nan());
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float xs[4] = {x4[q].x, x4[q].y, x4[q].z, x4[q].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const unsigned u = finite_f(xs[j]) ? ordered_bits(xs[j]) : 0u;
+            lmax = max(lmax, u);
+            lnmin = max(lnmin, u ? ~u : 0u);
+          }
         }
       }
       lmax = __reduce_max_sync(0xffffffffu, lmax);
@@ -2146,6 +2188,7 @@ wide_kernel(const __grid_constant__ ProdParams p) {
         }
     }
     xsync();
+    WT(5);   // radix select: extremes pass
     int Rmax = 1;
     for (int sl = 0; sl < p.nstore; ++sl) {
       const unsigned umx = *reinterpret_cast<volatile unsigned*>(&ctl->umaxo[sl]);
@@ -2186,9 +2229,15 @@ wide_kernel(const __grid_constant__ ProdParams p) {
         const int gce = gc + 480 < g_hi ? gc + 480 : g_hi;
         for (int i = lane; i < 6 * 128; i += 32) hist[i] = 0u;
         __syncwarp();
-        for (int g0 = gc; g0 < gce; ++g0) {
-          const float4 x4 = *reinterpret_cast<const float4*>(col + 4 * lane + 128 * g0);
-          const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+        for (int g0 = gc; g0 < gce; g0 += 4) {
+          float4 x44[4];                       // four loads in flight (see the extremes pass)
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            x44[q] = g0 + q < gce ? *reinterpret_cast<const float4*>(col + 4 * lane + 128 * (g0 + q))
+                                  : make_float4(Math<float>::nan(), Math<float>::nan(), Math<float>::nan(), Math<float>::nan());
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+          const float xs[4] = {x44[q].x, x44[q].y, x44[q].z, x44[q].w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float x = xs[j];
@@ -2204,6 +2253,7 @@ wide_kernel(const __grid_constant__ ProdParams p) {
               const unsigned idx = (unsigned)which * 256u + bin;
               atomicAdd(hist + (idx >> 1), 1u << ((idx & 1u) << 4));
             }
+          }
           }
         }
         __syncwarp();
@@ -2222,6 +2272,7 @@ wide_kernel(const __grid_constant__ ProdParams p) {
         __syncwarp();
       }
       xsync();
+      WT(6);   // radix rounds
 #pragma unroll 1
       for (int h = 0; h < 2; ++h) {
         if (!live[h] || (round > 0 && 8 * round >= Tbits[h])) continue;
@@ -2316,6 +2367,7 @@ wide_kernel(const __grid_constant__ ProdParams p) {
       }
     }
     grid.sync();          // the scratch is reused by the next galaxy
+    WT(7);   // results + end barrier
   }
   if (p.ndst > 1) __threadfence_system();
 }
