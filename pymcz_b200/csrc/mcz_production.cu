@@ -2397,11 +2397,11 @@ static bool use_wide(long long G, long long N, const float* Z) {
   (void)Z;
   if (force && force[0] == '0') return false;
   if (force && force[0] == '1') return true;
-  // Measured on B200 (tools/time_wide.py): the wide kernel takes ~0.12 ms + 0.4 ns per sample for
-  // each galaxy, one after the other; a per-galaxy block ~26 ns per sample, up to one block per SM
-  // at a time.
+  // Measured on B200 (tools/time_wide.py): the wide kernel takes ~0.12 ms + 0.27 ns per sample for
+  // each galaxy, one after the other; a per-galaxy block ~29 ns per sample (columns of this length
+  // stream through L2 / DRAM), up to one block per SM at a time.
   if (N < 32768 || G > num_sms()) return false;
-  return (double)G * (0.12 + 4.0e-7 * (double)N) < 2.6e-5 * (double)N;
+  return (double)G * (0.12 + 2.7e-7 * (double)N) < 2.9e-5 * (double)N;
 }
 
 static int launch_wide(ProdParams& p, void* scratch, cudaStream_t stream, const WideShare* ws) {
