@@ -67,6 +67,7 @@ struct ProdParams {
   int scap;                                // global variant: samples whose KK04 loop state lives in shared memory
   int bsm;                                 // global variant: the inputs and the state of the KK04 loops fit in shared memory
   int ring;                                // global variant: per-warp prefetch rings for the gather pass
+  int pair;                                // global variant: two warps per column in phase D (nstore <= PW / 2)
   int cper, cng;                           // cluster kernel: samples per block, 128-sample groups streamed per block
   signed char slot_of_key[NKEYS];
   signed char key_of_slot[NKEYS];
@@ -426,9 +427,11 @@ namespace mcz {
 // WIDE: 32-bit histogram counters (columns of 65536 samples or more); global variant only.
 // CL: launched in clusters of ceil(N' / (SLOTS * PT)) blocks, one galaxy per CLUSTER: block r of the
 //     cluster holds samples [r SLOTS PT, (r + 1) SLOTS PT) of every column in its shared memory.
-template <int SLOTS, bool WIDE, bool CL>
+// PAIRK (global variant): two warps per column in phase D, for launches with at most PW / 2 columns.
+template <int SLOTS, bool WIDE, bool CL, bool PAIRK = false>
 __global__ void __launch_bounds__(PT, 1)
 production_kernel(const __grid_constant__ ProdParams p) {
+  static_assert(!PAIRK || (SLOTS == 0 && !WIDE && !CL), "two warps per column: global variant, 16-bit counters");
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr bool GLOBAL = (SLOTS == 0);
   static_assert(!CL || SLOTS > 0, "the cluster kernel keeps its columns in shared memory");
@@ -1338,7 +1341,10 @@ production_kernel(const __grid_constant__ ProdParams p) {
       __syncwarp();
       if (lane == 0) reinterpret_cast<unsigned*>(cand)[ClMail::PAR / 4] = cc.par;
     } else
-    for (int sl = warp; sl < p.nstore; sl += PW) {
+    for (int sl = PAIRK ? (warp >> 1) : warp; sl < p.nstore; sl += PW) {
+      // (PAIRK: at most half as many columns as warps -- `--md KD02`: 7 --, warps 2c and 2c + 1 share
+      // column c; its histogram / candidate areas are warp 2c's)
+      const int part = PAIRK ? (warp & 1) : 0;
       const int k = p.key_of_slot[sl];
       if (!((pm >> k) & 1ull)) continue;
       float pc[3];
@@ -1350,7 +1356,13 @@ production_kernel(const __grid_constant__ ProdParams p) {
       // the space the KK04 loops used)
       float* ring = (GLOBAL && p.ring) ? reinterpret_cast<float*>(work + (size_t)PW * (HIST_BYTES + CAND_FLOATS * sizeof(float))) + warp * RING_FLOATS
                            : nullptr;
-      warp_percentiles<PACK16, GLOBAL ? 0 : SLOTS * PT / 128>(vals + (long long)sl * Npad, Npad, hist, cand, pc, nv, stt, ring);
+      if constexpr (PAIRK) {
+        unsigned* phist = reinterpret_cast<unsigned*>(work + (size_t)(warp & ~1) * HIST_BYTES);
+        float* pcand = cand - (warp & 1) * CAND_FLOATS;
+        warp_percentiles<PACK16, 0, true>(vals + (long long)sl * Npad, Npad, phist, pcand, pc, nv, stt, ring, part, 1 + sl);
+      } else {
+        warp_percentiles<PACK16, GLOBAL ? 0 : SLOTS * PT / 128>(vals + (long long)sl * Npad, Npad, hist, cand, pc, nv, stt, ring);
+      }
 #ifdef MCZ_PHASE_TIMING
       if (lane == 0) {
         const unsigned long long dt = (unsigned long long)(clock64() - tc0);
@@ -1358,7 +1370,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
         atomicMax(&g_col_cycles[NKEYS + k], dt);
       }
 #endif
-      if (lane == 0) {
+      if (lane == 0 && part == 0) {
         const long long o = (p.row0 + g) * NKEYS + k;
         for (int q = 0; q < p.ndst; ++q) {
           p.status[q][o] = (signed char)stt;
@@ -1453,6 +1465,7 @@ struct ProdPlan {
   int scap;       // global variant: samples with their loop state in shared memory
   int bsm;        // global variant: loop inputs + state of all samples in shared memory (20 bytes + 1 bit each)
   int ring;       // global variant: room for the per-warp prefetch rings of the gather pass
+  int pair;       // global variant: two warps per column in phase D
   int cper, cng;  // cluster kernel: samples per block, 128-sample groups per block
   int Npad, grid;
   size_t smem;
@@ -1463,7 +1476,7 @@ struct ProdPlan {
 // count, the "227 KB of dynamic shared memory" opt-in of every kernel (a function attribute is
 // per device) and the cooperative grid limit of the wide kernel are cached per device ordinal.
 static constexpr int MAX_DEVICES = 64;
-enum KernelId { KID_PROD_SHARED = 0, KID_PROD_GLOBAL, KID_PROD_GLOBAL_WIDE, KID_PROD_CLUSTER, KID_WIDE, KID_SELECT, KID_COUNT };
+enum KernelId { KID_PROD_SHARED = 0, KID_PROD_GLOBAL, KID_PROD_GLOBAL_WIDE, KID_PROD_CLUSTER, KID_WIDE, KID_SELECT, KID_PROD_GLOBAL_PAIR, KID_COUNT };
 struct DeviceState {
   std::atomic<int> sms{0};
   std::atomic<int> attr_done[KID_COUNT];
@@ -1543,6 +1556,7 @@ static ProdPlan make_plan(long long G, long long N, int nstore) {
   pl.scap = 0;
   pl.bsm = 0;
   pl.ring = 0;
+  pl.pair = 0;
   pl.cluster = 1;
   pl.cper = 0; pl.cng = 0;
   // Longer columns, up to 8 x 2304 samples: a cluster of blocks per galaxy, each block laid out like the
@@ -1598,6 +1612,10 @@ static ProdPlan make_plan(long long G, long long N, int nstore) {
     // plus one flag bit fit in the 226 KB next to the control block -- the selection work area is dead
     // while the loops run -- so the loops read nothing from global memory (MCZ_BSM=0: never)
     // (phase D: a 9 KB prefetch ring per warp in the same space)
+    {
+      const char* envp = getenv("MCZ_PAIR");           // MCZ_PAIR=0: one warp per column whatever their number
+      pl.pair = (!pl.wide && 2 * nstore <= PW && !(envp && envp[0] == '0')) ? 1 : 0;
+    }
     const size_t ring_bytes = base + (size_t)PW * RING_FLOATS * sizeof(float);
     pl.ring = ring_bytes <= 227ull * 1024;             // (not next to the 32-bit histogram counters of >= 65536-sample columns)
     if (pl.ring && pl.smem < ring_bytes) pl.smem = ring_bytes;
@@ -1683,7 +1701,7 @@ const char* production_kernel_name(long long G, long long n_draw, uint32_t tok) 
   const ProdPlan pl = make_plan(G, n_draw, p.nstore);
   if (pl.cluster > 1) return "production_kernel<4,0,cluster>";
   if (!pl.global) return "production_kernel<4,0>";
-  return pl.wide ? "production_kernel<0,1>" : "production_kernel<0,0>";
+  return pl.wide ? "production_kernel<0,1>" : (pl.pair ? "production_kernel<0,0,pair>" : "production_kernel<0,0>");
 }
 
 int launch_production(const float* meas, const float* err, long long G, long long n_draw, uint32_t tok,
@@ -1698,7 +1716,7 @@ int launch_production(const float* meas, const float* err, long long G, long lon
   const ProdPlan pl = make_plan(G, n_draw, p.nstore);
   if (scratch_bytes < ((ws && ws->world > 1) ? wide_private_bytes(n_draw, tok) : production_scratch_bytes(G, n_draw, tok)))
     return set_error("mcz_forward_production: scratch too small");
-  p.meas = meas; p.err = err; p.G = G; p.N = (int)n_draw; p.Npad = pl.Npad; p.scap = pl.scap; p.bsm = pl.bsm; p.ring = pl.ring; p.cper = pl.cper; p.cng = pl.cng; p.tok = tok; p.dust = dust;
+  p.meas = meas; p.err = err; p.G = G; p.N = (int)n_draw; p.Npad = pl.Npad; p.scap = pl.scap; p.bsm = pl.bsm; p.ring = pl.ring; p.pair = pl.pair; p.cper = pl.cper; p.cng = pl.cng; p.tok = tok; p.dust = dust;
   p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32); p.goff = galaxy_offset;
   p.correlated = sample_mode == 1; p.deterministic = deterministic != 0;
   p.calls = philox_calls(tok, p.correlated, p.deterministic);
@@ -1748,6 +1766,9 @@ int launch_production(const float* meas, const float* err, long long G, long lon
   } else if (!pl.global) {
     if ((rc = ensure_smem_attr(production_kernel<4, false, false>, KID_PROD_SHARED, 227 * 1024))) return rc;
     production_kernel<4, false, false><<<pl.grid, PT, pl.smem, stream>>>(p);
+  } else if (!pl.wide && pl.pair) {
+    if ((rc = ensure_smem_attr(production_kernel<0, false, false, true>, KID_PROD_GLOBAL_PAIR, 227 * 1024))) return rc;
+    production_kernel<0, false, false, true><<<pl.grid, PT, pl.smem, stream>>>(p);
   } else if (!pl.wide) {
     if ((rc = ensure_smem_attr(production_kernel<0, false, false>, KID_PROD_GLOBAL, 227 * 1024))) return rc;
     production_kernel<0, false, false><<<pl.grid, PT, pl.smem, stream>>>(p);

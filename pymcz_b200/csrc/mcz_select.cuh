@@ -864,12 +864,23 @@ __device__ __forceinline__ bool exact_range(const SelWarp& w, float& scale, floa
 // NG: number of 128-sample groups when it is known at compile time (Npad == 128 * NG), else 0.
 // ring: optional staging area of the warp for long columns in global memory (RING_FLOATS floats, 16-byte
 // aligned): the gather pass then prefetches the column two chunks ahead with cp.async.
+// PAIR: TWO warps share the column (launch shapes with at most half as many columns as warps, e.g.
+// `--md KD02` on long columns): warp `part` (0 / 1) streams every other 128-sample group in pass H and
+// every other chunk in the gather pass, into the SAME histogram and candidate list (`hist`, `cand`:
+// the pair's; `ring`: the warp's own); both make the (identical) plan; they meet at the named barrier
+// `barid` (64 threads).  Warp 0 finishes and returns the result; a column that needs the general path
+// (crowded ranges, end bins) is done by warp 0 alone from the gather pass on.
 static constexpr int RING_CH = 6, RING_SLOTS = 3, RING_FLOATS = RING_SLOTS * RING_CH * 128;
-template <bool PACK16, int NG>
+template <bool PACK16, int NG, bool PAIR = false>
 __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned* hist, float* cand,
-                                 float pct[3], int& nvalid, int& status, float* ring = nullptr) {
+                                 float pct[3], int& nvalid, int& status, float* ring = nullptr, int part = 0, int barid = 0) {
   typedef FineHist<PACK16> FH;
+  static_assert(!PAIR || NG == 0, "two warps per column: long columns only");
   const int lane = threadIdx.x & 31;
+  constexpr int np = PAIR ? 2 : 1;
+  auto pair_sync = [&]() { if (PAIR) asm volatile("bar.sync %0, 64;" :: "r"(barid) : "memory"); };
+  constexpr int HSTEP = 128 * np;                           // samples between two 128-bit loads of a lane in pass H
+  const int hstart = 4 * lane + (PAIR ? 128 * part : 0);
   SelWarp w;
   w.v = v; w.Npad = Npad; w.hist = hist; w.lane = lane;
   w.rnr = 0;
@@ -899,13 +910,37 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
   // ---- pass H: the 1024-bin histogram (out-of-range finite values land in the end bins) and the
   // sum of the column (the atomics bound this pass, so the extra arithmetic is free here)
   float sum = 0.0f;
-  FH::zero(hist, lane);
+  if (!PAIR || part == 0) FH::zero(hist, lane);
+  pair_sync();
   const int nH = NG > 0 ? NG * 128 : Npad;      // (compile-time trip count when the length is known)
   const unsigned hist_sa = (unsigned)__cvta_generic_to_shared(hist);
   const unsigned lane_sa = hist_sa + 4u * (unsigned)(FH::WORDS + lane);
   if (!has_tie) {
+    int s0 = hstart;
+    if constexpr (NG == 0) {
+      // Long column in global memory: the shared-memory reductions are `asm volatile` with a memory
+      // clobber, so the compiler keeps every load behind the reductions of the iteration before --
+      // one 128-bit load per lane in flight against an L2 / HBM latency of ~1 k cycles.  Four loads
+      // are issued before the first of their samples is counted.
+      constexpr int UB = 4;
+      for (; s0 + (UB - 1) * HSTEP < nH; s0 += UB * HSTEP) {
+        float4 xb[UB];
+#pragma unroll
+        for (int u = 0; u < UB; ++u) xb[u] = *reinterpret_cast<const float4*>(v + s0 + u * HSTEP);
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+          const float xs[4] = {xb[u].x, xb[u].y, xb[u].z, xb[u].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const bool fin = finite_f(xs[j]);
+            sum += fin ? xs[j] : 0.0f;
+            FH::add_t(hist_sa, lane_sa, fine_tbits(xs[j], scale, nLs), fin);
+          }
+        }
+      }
+    }
 #pragma unroll 3
-    for (int s0 = 4 * lane; s0 < nH; s0 += 128) {
+    for (; s0 < nH; s0 += HSTEP) {
       const float4 x4 = *reinterpret_cast<const float4*>(v + s0);
       const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
@@ -917,7 +952,7 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
     }
   } else {
     int ntie = 0;
-    for (int s0 = 4 * lane; s0 < Npad; s0 += 128) {
+    for (int s0 = hstart; s0 < Npad; s0 += HSTEP) {
       const float4 x4 = *reinterpret_cast<const float4*>(v + s0);
       const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
@@ -932,6 +967,18 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
     ntie = __reduce_add_sync(0xffffffffu, ntie);
     if (lane == 0 && ntie > 0) FH::add_n(hist, fine_index(tie, scale, nLs), (unsigned)ntie);
     ntie_total = (unsigned)ntie;
+  }
+  double dsum = 0.0;
+  if (PAIR) {
+    // the two halves of the column sum and of the tie count meet in the spare words of the candidate area
+    dsum = warp_sum((double)sum);
+    if (lane == 0) {
+      reinterpret_cast<double*>(cand + 2)[part] = dsum;
+      reinterpret_cast<unsigned*>(cand)[6 + part] = ntie_total;
+    }
+    pair_sync();                                  // the histogram is complete
+    dsum = reinterpret_cast<const double*>(cand + 2)[0] + reinterpret_cast<const double*>(cand + 2)[1];
+    ntie_total = reinterpret_cast<const unsigned*>(cand)[6] + reinterpret_cast<const unsigned*>(cand)[7];
   }
   MCZ_TS(ts2);
   SelPlan P;
@@ -959,6 +1006,12 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
 #pragma unroll
   for (int r = 0; r < 3; ++r)                    // NaN / inf index into the end bins
     if (r < P.nr && (P.rlo[r] == 0 || P.rhi[r] == FB - 1)) general = true;
+  if (PAIR) {
+    if (part == 0 && lane == 0) *w.ccount = 0u;
+    pair_sync();                                 // both plans are made: the candidate list may overwrite the histogram
+    if (general && part != 0) return;            // (the general path compacts the column in place: one warp)
+    __syncwarp();
+  }
   if (!general) {
     // The streaming loop only records which samples are members (one bit each, six 128-sample
     // groups per 24-bit mask); the few members are appended after each chunk with one shared
@@ -966,7 +1019,7 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
     constexpr int CH = 6;
     constexpr int NCH = (NG + CH - 1) / CH;
     const int ngroups = Npad / 128;
-    if (lane == 0) *w.ccount = 0u;
+    if (!PAIR && lane == 0) *w.ccount = 0u;
     __syncwarp();
     bool done = false;
     if constexpr (NG > 0 && NCH <= 4) {
@@ -1021,11 +1074,13 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
       // those slots, so no synchronisation beyond the lane's own wait_group is needed.
       static_assert(CH == RING_CH, "ring layout");
       const unsigned ring_sa = (unsigned)__cvta_generic_to_shared(ring) + 16u * (unsigned)lane;
-      const int nchunks = (ngroups + CH - 1) / CH;
+      // (PAIR: this warp takes chunks part, part + 2, ...; c counts the warp's own chunks)
+      const int nchunks = PAIR ? ((ngroups + CH - 1) / CH + np - 1 - part) / np : (ngroups + CH - 1) / CH;
+      auto chunk0 = [&](int c) { return (PAIR ? np * c + part : c) * CH; };     // first 128-sample group of chunk c
       auto issue = [&](int c, int slot) {
 #pragma unroll
         for (int i = 0; i < CH; ++i) {
-          const int g = c * CH + i;
+          const int g = chunk0(c) + i;
           if (g < ngroups)
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(ring_sa + (unsigned)((slot * CH + i) * 512)),
                          "l"(v + 4 * lane + 128 * g) : "memory");
@@ -1043,7 +1098,7 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
         unsigned mask = 0u;
 #pragma unroll
         for (int i = 0; i < CH; ++i) {
-          if (c * CH + i < ngroups) {
+          if (chunk0(c) + i < ngroups) {
             float4 x4;
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x4.x), "=f"(x4.y), "=f"(x4.z), "=f"(x4.w)
                          : "r"(ring_sa + (unsigned)((slot * CH + i) * 512)) : "memory");
@@ -1063,7 +1118,7 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
           do {
             const int b = __ffs(mask) - 1;
             mask &= mask - 1u;
-            w.glist[pos & 255u] = v[4 * lane + 128 * (c * CH + (b >> 2)) + (b & 3)];
+            w.glist[pos & 255u] = v[4 * lane + 128 * (chunk0(c) + (b >> 2)) + (b & 3)];
             ++pos;
           } while (mask);
         }
@@ -1074,7 +1129,7 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
     }
     if (!done)
 #pragma unroll 1
-    for (int g0 = 0; g0 < ngroups; g0 += CH) {
+    for (int g0 = PAIR ? CH * part : 0; g0 < ngroups; g0 += PAIR ? np * CH : CH) {
       unsigned mask = 0u;
 #pragma unroll
       for (int i = 0; i < CH; ++i) {
@@ -1163,7 +1218,12 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
       bmn[r] = gm;
     }
   }
-  if (!(warp_sum((double)sum) > 0.0)) { sel_count(SEL_TRIVIAL); status = ST_NONPOS; return; }   // mcz.py:282-285
+  if (PAIR && !general) {
+    pair_sync();                                 // every candidate is in the list
+    if (part != 0) return;
+  }
+  if (!PAIR) dsum = warp_sum((double)sum);
+  if (!(dsum > 0.0)) { sel_count(SEL_TRIVIAL); status = ST_NONPOS; return; }   // mcz.py:282-285
   status = ST_OK;
   MCZ_TS(ts4);
   sel_count(SEL_FAST);

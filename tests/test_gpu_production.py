@@ -254,14 +254,20 @@ def test_cluster_kernel_long_columns(n, ngal, mds):
     assert np.allclose(pct[same], ref[0][same], rtol=0, atol=1e-5, equal_nan=True)
 
 
-@pytest.mark.parametrize("n,ngal", [(22000, 12), (11000, 100)])
-def test_large_nsample_global_variant(n, ngal):
-    """N' = 22000 (config 2 shape) and 11000 (configs 3 / 5) on the global-scratch instantiation."""
+@pytest.mark.parametrize("n,ngal,mds", [(22000, 12, "all"), (11000, 100, "all"), (11000, 100, "KD02"), (2305, 80, "KD02"),
+                                        (5000, 80, "KD02,D02"), (11000, 40, "KD02,D02,Z94")])
+def test_large_nsample_global_variant(n, ngal, mds):
+    """N' = 22000 (config 2 shape) and 11000 (configs 3 / 5) on the global-scratch instantiation; with at
+    most nine columns (`--md KD02`: seven) the instantiation that puts two warps on every column."""
     import os
+    from pymcz_b200 import _lib
     old = os.environ.get("MCZ_CLUSTER")
     os.environ["MCZ_CLUSTER"] = "0"
     try:
-        _check_long_columns(n, ngal, "all")
+        name = _lib.lib().mcz_production_kernel_name(ngal, n, sc.parse_md(mds)[0])
+        if mds in ("KD02", "all"):
+            assert (b"pair" in name) == (mds == "KD02"), name
+        _check_long_columns(n, ngal, mds)
     finally:
         if old is None:
             del os.environ["MCZ_CLUSTER"]
