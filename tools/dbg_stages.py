@@ -1,5 +1,6 @@
 """Per-stage cycles of the selection of a typical column.  Build the library with
--DMCZ_PHASE_TIMING -DMCZ_COLTIME_DUMP=2 (range+H, plan, G) or =3 (range, finish, total)."""
+-DMCZ_PHASE_TIMING -DMCZ_COLTIME_DUMP=2 (range+H, plan, G) or =3 (range, finish, total).
+   python tools/dbg_stages.py <label> [N' [galaxies [md]]]"""
 import sys, numpy as np, torch
 sys.path.insert(0, '.')
 from pymcz_b200 import _scales as sc, ops
@@ -11,9 +12,10 @@ if N <= 2304:
 else:
     meas, err = synthetic_table(G, config=3)
 m = torch.from_numpy(meas).cuda(); e = torch.from_numpy(err).cuda()
-ws = ops.ProductionWorkspace(G, N, sc.T_ALL, m.device)
-ops.forward_production(m, e, N, sc.T_ALL, workspace=ws); torch.cuda.synchronize()
-pct, nv, st, tr, ret, Z = ops.forward_production(m, e, N, sc.T_ALL, workspace=ws)
+TOK = sc.parse_md(sys.argv[4])[0] if len(sys.argv) > 4 else sc.T_ALL
+ws = ops.ProductionWorkspace(G, N, TOK, m.device)
+ops.forward_production(m, e, N, TOK, workspace=ws); torch.cuda.synchronize()
+pct, nv, st, tr, ret, Z = ops.forward_production(m, e, N, TOK, workspace=ws)
 torch.cuda.synchronize()
 t = pct.cpu().numpy().astype(np.float64); st = st.cpu().numpy()
 ok = st == 0
