@@ -149,6 +149,23 @@ __device__ __forceinline__ void block_sum2f(float& a, float& c, float2* buf, int
   phase ^= 1;
 }
 
+// The same for four floats behind ONE barrier; every total is formed in the same order as
+// block_sum2f forms it, so the two are interchangeable bit for bit.  bufA, bufB: 2 * PW float2 each.
+__device__ __forceinline__ void block_sum4f(float (&v)[4], float2* bufA, float2* bufB, int& phase) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = warp_sum(v[i]);
+  float2* a = bufA + phase * PW;
+  float2* b = bufB + phase * PW;
+  if (lane == 0) { a[warp] = make_float2(v[0], v[1]); b[warp] = make_float2(v[2], v[3]); }
+  __syncthreads();
+  const float2 pa = lane < PW ? a[lane] : make_float2(0.0f, 0.0f);
+  const float2 pb = lane < PW ? b[lane] : make_float2(0.0f, 0.0f);
+  v[0] = warp_sum(pa.x); v[1] = warp_sum(pa.y);
+  v[2] = warp_sum(pb.x); v[3] = warp_sum(pb.y);
+  phase ^= 1;
+}
+
 // ---- thread-block clusters: distributed shared memory ----------------------------------------
 // For N' > 2304 a galaxy is given to a CLUSTER of ceil(N' / 2304) thread blocks: block r holds samples
 // [2304 r, 2304 (r + 1)) in its own shared memory, exactly like the one-block kernel, and what the
@@ -608,8 +625,8 @@ production_kernel(const __grid_constant__ ProdParams p) {
         const uint32_t fl = MODE ? (uint32_t)F_ALL : flags;
         const uint32_t tk = MODE == 1 ? (uint32_t)T_ALL : (MODE == 2 ? (uint32_t)T_KD02 : p.tok);
         const int dm = MODE ? 0 : de;
-#pragma unroll A_UNROLL
         const int N = NLOC, soff = SOFF;
+#pragma unroll A_UNROLL
         for (int i = 0; i < nsl; ++i) {
           const int s = i * PT + tid;
           if (s < N) {
@@ -965,7 +982,8 @@ production_kernel(const __grid_constant__ ProdParams p) {
           float sm1[BT], sm2[BT];
 #pragma unroll
           for (int t = 0; t < BT; ++t) { sm1[t] = 0.0f; sm2[t] = 0.0f; }
-          unsigned nanb = 0u;                      // bit t: N2Ha trip t of the batch saw a NaN; bit BT + t: R23
+          // (a NaN step makes the float sum of its trip NaN, and a NaN sum fails the loop test: the loop stops
+          // there, as numpy's mean does -- no separate NaN flags are needed with float sums)
 #pragma unroll BSM_UNROLL
           for (int s = tid; s < N; s += PT) {
             IterState<float> k;                       // only the constants of the loops still running
@@ -981,7 +999,6 @@ production_kernel(const __grid_constant__ ProdParams p) {
               for (int t = 0; t < BT; ++t) {
                 const float lq = (num0 + Z * num1) * fast_rcp(den0 + Z * den1);          // metscales.py:1112-1118
                 const float d = fabsf(lq - lqp);
-                nanb |= (d != d) ? (1u << t) : 0u;
                 sm1[t] += d;
                 if (t < BT - 1) { Fl1[(long long)t * Npad + s] = lq; Z = cA - lq * cB; }
                 lqp = lq;
@@ -1000,7 +1017,6 @@ production_kernel(const __grid_constant__ ProdParams p) {
               for (int t = 0; t < BT; ++t) {
                 const float lq = (num0 + Z * num1) * fast_rcp(den0 + Z * den1);          // metscales.py:1167-1178
                 const float d = lqp - lq;
-                nanb |= (d != d) ? (1u << (BT + t)) : 0u;
                 sm2[t] += d;
                 if (t < BT - 1) {
                   Fl2[(long long)t * Npad + s] = lq;
@@ -1013,28 +1029,28 @@ production_kernel(const __grid_constant__ ProdParams p) {
             }
           }
           first = false;
-          // block sums, two at a time (one barrier per call); NaN flags by vote
+          // block sums of all the trips of the batch behind one barrier
           {
-            float flat[2 * BT + 1];
+            float flat[2 * BT];
 #pragma unroll
             for (int t = 0; t < BT; ++t) { flat[t] = sm1[t]; flat[BT + t] = sm2[t]; }
-            flat[2 * BT] = 0.0f;
+            // (second buffer: the exchange slots of the cluster kernel, unused here)
+            static_assert(sizeof(ctrl->xslot) >= 2 * PW * sizeof(float2), "second reduction buffer");
+            if constexpr (BT == 2) {
+              block_sum4f(flat, ctrl->redf, reinterpret_cast<float2*>(ctrl->xslot), phase);
+            } else {
 #pragma unroll
-            for (int i = 0; i < 2 * BT; i += 2) block_sum2f(flat[i], flat[i + 1], ctrl->redf, phase);
+              for (int i = 0; i < 2 * BT; i += 2) block_sum2f(flat[i], flat[i + 1], ctrl->redf, phase);
+            }
 #pragma unroll
             for (int t = 0; t < BT; ++t) { sm1[t] = flat[t]; sm2[t] = flat[BT + t]; }
-          }
-          unsigned nb = 0u;
-          if (__syncthreads_or(nanb != 0u)) {
-#pragma unroll
-            for (int k = 0; k < 2 * BT; ++k) nb |= __syncthreads_or((nanb >> k) & 1u) ? (1u << k) : 0u;
           }
           if (act1) {                                                     // metscales.py:1111,1117
 #pragma unroll
             for (int t = 0; t < BT; ++t) {
               if (act1) {
                 ++ii1;
-                if ((nb & (1u << t)) || !(sm1[t] > tol1) || ii1 >= 100) {
+                if (!(sm1[t] > tol1) || ii1 >= 100) {
                   act1 = false;
                   if (t < BT - 1)     // ended before the last trip of the batch: put that logq back
                     for (int s = tid; s < N; s += PT) sQ1[s] = Fl1[(long long)t * Npad + s];
@@ -1047,7 +1063,7 @@ production_kernel(const __grid_constant__ ProdParams p) {
             for (int t = 0; t < BT; ++t) {
               if (act2) {
                 ++ii2;
-                if ((nb & (1u << (BT + t))) || !(fabsf(sm2[t]) > tol2) || ii2 >= 100) {
+                if (!(fabsf(sm2[t]) > tol2) || ii2 >= 100) {
                   act2 = false;
                   if (t < BT - 1)
                     for (int s = tid; s < N; s += PT) sQ2[s] = Fl2[(long long)t * Npad + s];
@@ -1859,6 +1875,12 @@ wide_kernel(const __grid_constant__ ProdParams p) {
   float* st0 = vals + (long long)p.nstore * Npad;
   float* st1 = st0 + Npad; float* st2 = st1 + Npad; float* st3 = st2 + Npad;
   float* F = st3 + Npad;                                   // fields 0..5: Z1, Z2, lq1, lq2, lq1a, lq2a
+  // Several ranks: the blocks of a rank first merge their tables of a radix round in this LOCAL table
+  // [nstore][6][256]; after a grid barrier its non-zero counters are sent to every rank once (the private
+  // scratch of a sharded run has room behind the loop state: wide_scratch_bytes counts the shared
+  // region, which then lives in the symmetric buffer).  148 blocks x 17 columns x W destinations of
+  // system-scope atomics per round took ~0.14 ms per peer.
+  unsigned* lhist = reinterpret_cast<unsigned*>(F + 6ll * Npad);
   const int used2line[NUSED] = {L_HA, L_HB, L_O2, L_O3, L_N2, L_S2A, L_S2B, L_S39069};
 
   // (-DMCZ_PHASE_TIMING: cycles of block 0 between the grid barriers, summed into g_phase_cycles[1..7])
@@ -1875,6 +1897,8 @@ wide_kernel(const __grid_constant__ ProdParams p) {
       for (int i = tid; i < (int)(sizeof(WideCtl) / 4); i += PT) reinterpret_cast<unsigned*>(ctl)[i] = 0u;
     }
     for (long long i = (long long)b * PT + tid; i < 4ll * p.nstore * 6 * 256; i += (long long)nb * PT) ghist[i] = 0u;
+    if (W > 1)
+      for (long long i = (long long)b * PT + tid; i < (long long)p.nstore * 6 * 256; i += (long long)nb * PT) lhist[i] = 0u;
     xsync();
     WT(1);   // reset
     float lm[NUSED], le[NUSED];
@@ -2280,8 +2304,10 @@ wide_kernel(const __grid_constant__ ProdParams p) {
         __syncwarp();
         for (int i = lane; i < nu * 256; i += 32) {
           const unsigned c = rh[i];
-          if (c)
-            for (int r = 0; r < W; ++r) atomicAdd_system(reinterpret_cast<unsigned*>(peer(gh + i, r)), c);
+          if (c) {
+            if (W > 1) atomicAdd(lhist + (long long)sl * 6 * 256 + i, c);
+            else atomicAdd(gh + i, c);
+          }
         }
         __syncwarp();
         }
@@ -2291,6 +2317,17 @@ wide_kernel(const __grid_constant__ ProdParams p) {
             for (int r = 0; r < W; ++r) atomicAdd_system(reinterpret_cast<double*>(peer(&ctl->colsum[sl], r)), tot);
         }
         __syncwarp();
+      }
+      if (W > 1) {
+        grid.sync();
+        unsigned* ghr = ghist + (long long)round * p.nstore * 6 * 256;
+        for (long long i = (long long)b * PT + tid; i < (long long)p.nstore * 6 * 256; i += (long long)nb * PT) {
+          const unsigned c = lhist[i];
+          if (c) {
+            lhist[i] = 0u;
+            for (int r = 0; r < W; ++r) atomicAdd_system(reinterpret_cast<unsigned*>(peer(ghr + i, r)), c);
+          }
+        }
       }
       xsync();
       WT(6);   // radix rounds
