@@ -1194,8 +1194,18 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
     int bcm[3] = {0, 0, 0};
     int cw = 0;                                  // members compacted by this lane so far
     float* const vm = const_cast<float*>(v);
-    for (int s0 = 4 * lane; s0 < Npad; s0 += 128) {
-      const float4 x4 = *reinterpret_cast<const float4*>(v + s0);
+    // (four loads ahead on long columns; the in-place compaction writes at or before the group that is
+    // being tested, never into one whose load is still pending)
+    constexpr int UBG = NG == 0 ? 4 : 1;
+    for (int s00 = 4 * lane; s00 < Npad; s00 += 128 * UBG) {
+      float4 xg[UBG];
+#pragma unroll
+      for (int u = 0; u < UBG; ++u)
+        xg[u] = s00 + 128 * u < Npad ? *reinterpret_cast<const float4*>(v + s00 + 128 * u)
+                                     : make_float4(nanf_, nanf_, nanf_, nanf_);
+#pragma unroll
+      for (int u = 0; u < UBG; ++u) {
+      const float4 x4 = xg[u];
       const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -1223,6 +1233,7 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
             ++cw;
           }
         }
+      }
       }
     }
     int mxc = cw;
