@@ -30,3 +30,8 @@ for f, c in collections.Counter(fl.tolist()).most_common(12):
 v = tot[live & (st != 0)]
 if v.size:
     print("status != ok: %d columns, mean %.0f" % (v.size, v.mean()))
+cr = live & (st == 0) & (((nv >> 16) & 7) != 0)
+if cr.any():
+    print("columns with a crowded range: %d; mean of the three dumped values %s (COLTIME_DUMP=2: range + pass H, plan, gather; =3: range, finish, total)"
+          % (cr.sum(), [round(float(t[:, :, i][cr].mean())) for i in range(3)]))
+    print("  by key:", collections.Counter(sc.KEYS[j] for j in np.nonzero(cr)[1]).most_common(6))
