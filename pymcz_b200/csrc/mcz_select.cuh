@@ -1022,8 +1022,6 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
 #pragma unroll
   for (int r = 0; r < 3; ++r) tlo[r] += FINE_BIAS;        // the tests below compare the raw index bits
   __syncwarp();
-  unsigned gcnt = 0;                             // candidates gathered so far (same in every lane)
-  const unsigned lt = (1u << lane) - 1u;
   const float pinf = __int_as_float(0x7f800000), ninf = __int_as_float(0xff800000);
   float bmn[3] = {pinf, pinf, pinf}, bmx[3] = {ninf, ninf, ninf};
   unsigned nmin[3] = {0u, 0u, 0u};
@@ -1197,14 +1195,14 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
     int bcm[3] = {0, 0, 0};
     int cw = 0;                                  // members compacted by this lane so far
     float* const vm = const_cast<float*>(v);
-    if constexpr (NG == 0) {
-      // Long column.  The warp is usually alone on the SM by now (the other columns are done), so the
+    {
+      // The warp is usually alone on the SM by now (the other columns are done), so the
       // pass runs at the latency of ONE instruction stream (~7 cycles per instruction): no vote in the
       // loop (a candidate takes its list position with a shared atomic), no divergent branches, loads
-      // issued ahead.  The in-place compaction writes at or before the group that is being handled,
+      // issued ahead on long columns.  The in-place compaction writes at or before the group that is being handled,
       // never into one whose load is still pending.  (Per crowded column of 11000 samples: 275 k -> 175 k
       // cycles; the statistics alone were 100 k as branches.)
-      constexpr int UBG = MCZ_GEN_UBG;
+      constexpr int UBG = NG == 0 ? MCZ_GEN_UBG : 1;
       if (!PAIR && lane == 0) *w.ccount = 0u;
       __syncwarp();
       for (int s00 = 4 * lane; s00 < Npad; s00 += 128 * UBG) {
@@ -1246,37 +1244,6 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
         }
       }
       __syncwarp();
-    } else
-    for (int s0 = 4 * lane; s0 < Npad; s0 += 128) {
-      const float4 x4 = *reinterpret_cast<const float4*>(v + s0);
-      const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float x = xs[j];
-        const bool fin = finite_f(x);
-        const int f = fine_tbits(x, scale, nLs);
-        const bool take = fin && x != skip &&
-                          (((unsigned)(f - tlo[0]) <= tsp[0]) || ((unsigned)(f - tlo[1]) <= tsp[1]) ||
-                           ((unsigned)(f - tlo[2]) <= tsp[2]));
-        const unsigned m = __ballot_sync(0xffffffffu, take);
-        if (take) w.glist[(gcnt + __popc(m & lt)) & 255u] = x;
-        gcnt += __popc(m);
-        if (fin) {
-          bool member = false;
-#pragma unroll
-          for (int r = 0; r < 3; ++r)
-            if ((unsigned)(f - clo[r]) <= csp[r]) {
-              member = true;
-              if (x < bmn[r]) { bmn[r] = x; bcm[r] = 1; }
-              else if (x == bmn[r]) ++bcm[r];
-              bmx[r] = fmaxf(bmx[r], x);
-            }
-          if (member) {                          // write position <= read position: safe in place
-            vm[4 * lane + 128 * (cw >> 2) + (cw & 3)] = x;
-            ++cw;
-          }
-        }
-      }
     }
     int mxc = cw;
 #pragma unroll
