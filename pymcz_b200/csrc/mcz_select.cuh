@@ -1194,7 +1194,7 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
     for (int r = 0; r < 3; ++r) clo[r] += FINE_BIAS;
     int bcm[3] = {0, 0, 0};
     int cw = 0;                                  // members compacted by this lane so far
-    float* const vml = const_cast<float*>(v) + 4 * lane;
+    float* const vm = const_cast<float*>(v);
     {
       // The warp is usually alone on the SM by now (the other columns are done), so the
       // pass runs at the latency of ONE instruction stream (~7 cycles per instruction): no vote in the
@@ -1212,12 +1212,11 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
           xg[u] = s00 + 128 * u < Npad ? *reinterpret_cast<const float4*>(v + s00 + 128 * u)
                                        : make_float4(nanf_, nanf_, nanf_, nanf_);
         // branch-free but for the rare candidate: the statistics of the crowded ranges are updated under
-        // selects (ranges that are not crowded have a test that never matches); EVERY sample is stored at
-        // the compaction position (at or before its own place, so nothing unread is overwritten) and the
-        // position advances only past a member
+        // selects (ranges that are not crowded have a test that never matches), the compaction store
+        // and its counter are predicated.  (Storing EVERY sample at the compaction position and advancing
+        // only past members is also correct and saves the predicate, but measured slower: more spills.)
 #pragma unroll
         for (int u = 0; u < UBG; ++u) {
-          if (UBG > 1 && s00 + 128 * u >= Npad) break;      // (the padding of the last batch must not be stored)
           const float xs[4] = {xg[u].x, xg[u].y, xg[u].z, xg[u].w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -1240,7 +1239,7 @@ __device__ void warp_percentiles(const float* __restrict__ v, int Npad, unsigned
               memb = memb || in;
             }
             if (take) w.glist[atomicAdd(w.ccount, 1u) & 255u] = x;
-            vml[(cw >> 2) * 128 + (cw & 3)] = x;
+            if (memb) vm[4 * lane + 128 * (cw >> 2) + (cw & 3)] = x;
             cw += memb ? 1 : 0;
           }
         }
