@@ -2261,11 +2261,19 @@ wide_kernel(const __grid_constant__ ProdParams p) {
         const int sl = warp + h * PW;
         const float* col = vals + (long long)sl * Npad;
         // distinct prefixes among the six targets (ascending ranks -> non-decreasing prefixes)
-        unsigned uq[6];
+        // (built with constant indices only: a run-time index would put uq[] into local memory, and the
+        // match below would read it from there for every sample)
+        unsigned tp[6], uq[6];
+#pragma unroll
+        for (int t = 0; t < 6; ++t) { tp[t] = tpre[h][t]; uq[t] = 0xffffffffu; }
         int nu = 0;
 #pragma unroll
-        for (int t = 0; t < 6; ++t)
-          if (nu == 0 || tpre[h][t] != uq[nu - 1 < 0 ? 0 : nu - 1]) { uq[nu] = tpre[h][t]; ++nu; }
+        for (int t = 0; t < 6; ++t) {
+          const bool isnew = t == 0 || tp[t] != tp[t - 1];
+#pragma unroll
+          for (int k = 0; k < 6; ++k) if (isnew && nu == k) uq[k] = tp[t];
+          nu += isnew ? 1 : 0;
+        }
         float sum = 0.0f;
         unsigned* gh = ghist + (((long long)round * p.nstore + sl) * 6) * 256;
         // (16-bit counters: the slice is taken 480 groups = 61440 samples at a time)
@@ -2274,33 +2282,43 @@ wide_kernel(const __grid_constant__ ProdParams p) {
         const int gce = gc + 480 < g_hi ? gc + 480 : g_hi;
         for (int i = lane; i < 6 * 128; i += 32) hist[i] = 0u;
         __syncwarp();
-        for (int g0 = gc; g0 < gce; g0 += 4) {
-          float4 x44[4];                       // four loads in flight (see the extremes pass)
+        // The prefix of a sample is matched against the DISTINCT prefixes of the six targets: one in the
+        // first round, at most three as a rule (the two ranks of a percentile are neighbours) -- the
+        // loop is specialised on that number (a fixed six-way match was a sixth of all the instructions
+        // the kernel executes).
+        auto scan = [&](auto nuq_tag) {
+          constexpr int NUQ = decltype(nuq_tag)::value;
+          for (int g0 = gc; g0 < gce; g0 += 4) {
+            float4 x44[4];                       // four loads in flight (see the extremes pass)
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            x44[q] = g0 + q < gce ? *reinterpret_cast<const float4*>(col + 4 * lane + 128 * (g0 + q))
-                                  : make_float4(Math<float>::nan(), Math<float>::nan(), Math<float>::nan(), Math<float>::nan());
+            for (int q = 0; q < 4; ++q)
+              x44[q] = g0 + q < gce ? *reinterpret_cast<const float4*>(col + 4 * lane + 128 * (g0 + q))
+                                    : make_float4(Math<float>::nan(), Math<float>::nan(), Math<float>::nan(), Math<float>::nan());
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-          const float xs[4] = {x44[q].x, x44[q].y, x44[q].z, x44[q].w};
+            for (int q = 0; q < 4; ++q) {
+              const float xs[4] = {x44[q].x, x44[q].y, x44[q].z, x44[q].w};
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float x = xs[j];
-            if (!finite_f(x)) continue;
-            if (round == 0) sum += x;
-            const unsigned u = ordered_bits(x);
-            const unsigned pre = hi >= 32 ? 0u : (u >> hi);
-            int which = -1;
+              for (int j = 0; j < 4; ++j) {
+                const float x = xs[j];
+                const bool fin = finite_f(x);
+                if (round == 0) sum += fin ? x : 0.0f;
+                const unsigned u = ordered_bits(x);
+                const unsigned pre = hi >= 32 ? 0u : (u >> hi);
+                int which = -1;
 #pragma unroll
-            for (int i = 0; i < 6; ++i) if (i < nu && uq[i] == pre) which = i;
-            if (which >= 0) {
-              const unsigned bin = (u >> shift) & dmask;
-              const unsigned idx = (unsigned)which * 256u + bin;
-              atomicAdd(hist + (idx >> 1), 1u << ((idx & 1u) << 4));
+                for (int i = 0; i < NUQ; ++i) if ((NUQ == 1 || i < nu) && uq[i] == pre) which = i;
+                if (fin && which >= 0) {
+                  const unsigned bin = (u >> shift) & dmask;
+                  const unsigned idx = (unsigned)which * 256u + bin;
+                  atomicAdd(hist + (idx >> 1), 1u << ((idx & 1u) << 4));
+                }
+              }
             }
           }
-          }
-        }
+        };
+        if (nu == 1) scan(std::integral_constant<int, 1>());
+        else if (nu <= 3) scan(std::integral_constant<int, 3>());
+        else scan(std::integral_constant<int, 6>());
         __syncwarp();
         for (int i = lane; i < nu * 256; i += 32) {
           const unsigned c = rh[i];

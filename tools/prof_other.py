@@ -1,4 +1,4 @@
-"""Launches for ncu captures of the other kernels: `wide` (one object, 1.1e6 samples) or `global`
+"""Launches for ncu captures of the other kernels: `wide [N']` (one object, 1.1e6 samples by default) or `global`
 (1480 galaxies x 11000 samples, production_kernel<0, false>)."""
 import sys, torch
 sys.path.insert(0, '.')
@@ -6,7 +6,7 @@ from pymcz_b200 import _scales as sc, ops
 from pymcz_b200.synth import synthetic_table
 which = sys.argv[1]
 if which == "wide":
-    G, N, cfg = 1, 1100000, 4
+    G, N, cfg = 1, (int(sys.argv[2]) if len(sys.argv) > 2 else 1100000), 4
 else:
     G, N, cfg = 1480, 11000, 3
 meas, err = synthetic_table(max(G, 8), config=cfg)
