@@ -2135,14 +2135,32 @@ wide_kernel(const __grid_constant__ ProdParams p) {
           if (t4b[0] > 4 * itol1) { ii1 = 100; act1 = false; }
         }
       }
-      for (int s = s_lo + tid; s < s_hi && s < N; s += PT) {
-        IterState<float> st;
-        consts(s, st);
-        st.Z1 = F[0ll * Npad + s]; st.Z2 = F[1ll * Npad + s]; st.lq2 = F[3ll * Npad + s];
-        SlotPut<false> put{vals + s, p.col_off, 0u};
-        const float kd = has_kd ? vals[(long long)sl_kd * Npad + s] : Math<float>::nan();
-        const float m91 = vals[(long long)sl_m91 * Npad + s];
-        phase_c<float>(st, pm, ii1 >= 100, ii2 >= 100, kd, m91, put);
+      // two samples per thread, all eighteen loads first (the column stores of one sample would keep the
+      // loads of the next behind them: everything here is derived from one scratch pointer)
+      for (int s = s_lo + tid; s < s_hi && s < N; s += 2 * PT) {
+        const bool two = s + PT < s_hi && s + PT < N;
+        const int sx[2] = {s, two ? s + PT : s};
+        float cy[2], cn[2], cx[2], ca[2], z1[2], z2[2], l2[2], kdv[2], m9[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int t = sx[q];
+          cy[q] = st0[t]; cn[q] = st1[t]; cx[q] = st2[t]; ca[q] = st3[t];
+          z1[q] = F[0ll * Npad + t]; z2[q] = F[1ll * Npad + t]; l2[q] = F[3ll * Npad + t];
+          kdv[q] = has_kd ? vals[(long long)sl_kd * Npad + t] : Math<float>::nan();
+          m9[q] = vals[(long long)sl_m91 * Npad + t];
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          if (q == 1 && !two) break;
+          Carry<float> c;
+          c.y = cy[q]; c.n2ha = cn[q]; c.x = cx[q];
+          c.aux = __float_as_uint(ca[q]);
+          IterState<float> st;
+          make_iter<float>(c, 0.0f, st);
+          st.Z1 = z1[q]; st.Z2 = z2[q]; st.lq2 = l2[q];
+          SlotPut<false> put{vals + sx[q], p.col_off, 0u};
+          phase_c<float>(st, pm, ii1 >= 100, ii2 >= 100, kdv[q], m9[q], put);
+        }
       }
     }
     grid.sync();          // all columns final
