@@ -1919,33 +1919,50 @@ wide_kernel(const __grid_constant__ ProdParams p) {
     for (;;) {
       const int de = effective_dust(p.dust, flags);
       uint32_t seen = 0u;
-      for (int s = s_lo + tid; s < s_hi; s += PT) {
-        if (s < N) {
-          float z[16];
-          draw_normals((uint32_t)s, gg, p, z);
-          float f[NUSED], e[5];
+      // (as in the per-galaxy kernels: the launch shape `--md all`, every line measured, dust on, independent
+      // sampling gets a copy of the loop with flags / tokens / dust mode as compile-time constants)
+      const uint32_t need = F_ALL & ~F_S39069;
+      bool bounded = true;
 #pragma unroll
-          for (int u = 0; u < NUSED; ++u) {
-            const float raw = fmaf(le[u], p.correlated ? z[5] : z[5 + u], lm[u]);
-            float v = fmaxf(raw, 0.0f);
-            if (!(v <= FLT_MAX)) v = 0.0f;
-            if ((p.tok & T_DROPNEG) && raw < 0.0f && raw >= -FLT_MAX) v = Math<float>::nan();
-            f[u] = v;
-            const bool pos = (u >= U_S2B) ? (v > 1e-9f) : (v > 0.0f);
-            if (pos) seen |= 1u << u;
+      for (int u = 0; u < NUSED; ++u) bounded = bounded && (fabsf(lm[u]) + 6.0f * fabsf(le[u]) < FLT_MAX);
+      const bool full = (flags & need) == need && de == 0 && !p.correlated && !p.deterministic && bounded &&
+                        p.tok == T_ALL && p.calls == 7u;
+      auto pass = [&](auto mode_tag) {
+        constexpr int MODE = decltype(mode_tag)::value;      // 0 generic, 1 --md all
+        const uint32_t fl = MODE ? (uint32_t)F_ALL : flags;
+        const uint32_t tk = MODE ? (uint32_t)T_ALL : p.tok;
+        const int dm = MODE ? 0 : de;
+        for (int s = s_lo + tid; s < s_hi; s += PT) {
+          if (s < N) {
+            float z[16];
+            if (MODE == 1) draw_normals_c<7u>((uint32_t)s, gg, p, z);
+            else draw_normals((uint32_t)s, gg, p, z);
+            float f[NUSED], e[5];
+#pragma unroll
+            for (int u = 0; u < NUSED; ++u) {
+              const float raw = fmaf(le[u], (!MODE && p.correlated) ? z[5] : z[5 + u], lm[u]);
+              float v = fmaxf(raw, 0.0f);
+              if (!MODE && !(v <= FLT_MAX)) v = 0.0f;
+              if (!MODE && (p.tok & T_DROPNEG) && raw < 0.0f && raw >= -FLT_MAX) v = Math<float>::nan();
+              f[u] = v;
+              const bool pos = (u >= U_S2B) ? (v > 1e-9f) : (v > 0.0f);
+              if (pos) seen |= 1u << u;
+            }
+            e[0] = 0.05f * z[0]; e[1] = 0.1f * z[1]; e[2] = 0.027f * z[2]; e[3] = 0.024f * z[3]; e[4] = 0.012f * z[4];
+            SlotPut<false> put{vals + s, p.col_off, 0u};
+            Carry<float> c;
+            c.y = c.n2ha = c.x = 0.0f;
+            c.aux = 0u;
+            phase_a<float>(f, e, fl, tk, dm, put, c);
+            if (c.aux & AUX_KD_VALID) seen |= SEEN_KD;
+            st0[s] = c.y; st1[s] = c.n2ha; st2[s] = c.x; st3[s] = __uint_as_float(c.aux);
+          } else {
+            for (int sl = 0; sl < p.nstore; ++sl) vals[(long long)sl * Npad + s] = Math<float>::nan();
           }
-          e[0] = 0.05f * z[0]; e[1] = 0.1f * z[1]; e[2] = 0.027f * z[2]; e[3] = 0.024f * z[3]; e[4] = 0.012f * z[4];
-          SlotPut<false> put{vals + s, p.col_off, 0u};
-          Carry<float> c;
-          c.y = c.n2ha = c.x = 0.0f;
-          c.aux = 0u;
-          phase_a<float>(f, e, flags, p.tok, de, put, c);
-          if (c.aux & AUX_KD_VALID) seen |= SEEN_KD;
-          st0[s] = c.y; st1[s] = c.n2ha; st2[s] = c.x; st3[s] = __uint_as_float(c.aux);
-        } else {
-          for (int sl = 0; sl < p.nstore; ++sl) vals[(long long)sl * Npad + s] = Math<float>::nan();
         }
-      }
+      };
+      if (full) pass(std::integral_constant<int, 1>());
+      else pass(std::integral_constant<int, 0>());
       seen = __reduce_or_sync(0xffffffffu, seen);
       if (lane == 0 && seen)
         for (int q = 0; q < W; ++q) atomicOr_system(reinterpret_cast<unsigned*>(peer(&ctl->flags, q)), seen);
