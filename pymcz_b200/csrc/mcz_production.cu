@@ -11,7 +11,8 @@
 // are fetched by the 18th warp during phase D), per-scale sample columns staged in shared memory
 // [slot][sample] (conflict-free: consecutive threads own consecutive samples); nothing but the
 // 2x11 input floats and the percentile table touches HBM.  production_kernel<0, WIDE> keeps the
-// columns in an L2-resident global scratch for N' too large for 227 KB.  With several GPUs the
+// columns in an L2-resident global scratch for N' too large for 227 KB (<0, false, false, true>: two
+// warps per column in phase D, for launches that store at most nine columns).  With several GPUs the
 // result rows are written into every rank's full table (ProdParams::ndst): the gather of the
 // path is fused into the kernel.
 #include <float.h>
